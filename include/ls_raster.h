@@ -1,0 +1,156 @@
+/*
+ * ls_raster.h -- C ABI of libls_raster.so, the sm_100a Gaussian rasterizer that
+ * sits under the `diff_gaussian_rasterization` Python module.
+ *
+ * What each entry point replaces in the reference (Chrixtar/latentsplat):
+ *   ls_raster_forward   <- the forward of `GaussianRasterizer(settings)(...)`,
+ *                          /root/reference/src/model/decoder/cuda_splatting.py:146-158
+ *                          (one call per view there; `n_views` views per call here, so the
+ *                          Python loop at cuda_splatting.py:124-162 collapses to one launch
+ *                          sequence).  Settings fields: cuda_splatting.py:132-145.
+ *   ls_raster_backward  <- the autograd backward of the same call (gradients w.r.t.
+ *                          means3D, means2D, shs | colors_precomp, features, opacities,
+ *                          cov3D_precomp), triggered by ModelWrapper.manual_backward,
+ *                          /root/reference/src/model/model_wrapper.py:440.
+ *   ls_raster_sizes     <- the geometry/binning/image buffer sizing the reference's
+ *                          extension does internally with torch resize lambdas [EXT].
+ * The reference binds its rasterizer through a torch C++ extension (pybind11); the
+ * binding a maintainer would write against THIS library is the ctypes stub in
+ * INTEGRATION.md (no torch types cross this boundary).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless marked host.  The caller allocates and
+ *     owns every buffer; the library never allocates or frees device memory and keeps
+ *     no global state besides a thread-local error string.
+ *   - All work is enqueued on `stream`; no call synchronises the device.
+ *   - Return value 0 = ok, negative = error (message via ls_last_error()).  Nothing
+ *     throws across the ABI.
+ *   - fp32 everywhere; uint64 sort keys; int32 radii; uint32 counters.
+ *   - Tiles are 16x16 pixels; T = ceil(W/16)*ceil(H/16) tiles per view.
+ *   - Views are grouped into scenes: view v renders scene v / views_per_scene.  Per-Gaussian
+ *     inputs are (S,G,...) with S = n_views / views_per_scene, so one scene rendered from
+ *     several target cameras is NOT replicated per view (the reference materialises that
+ *     repeat at decoder_splatting_cuda.py:71-86).  Input gradients are (S,G,...), summed
+ *     over the views of a scene.
+ */
+#ifndef LS_RASTER_H
+#define LS_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS_RASTER_ABI_VERSION 1
+#if defined(__GNUC__)
+#define LS_API __attribute__((visibility("default")))
+#else
+#define LS_API
+#endif
+#define LS_TILE 16
+#define LS_GEOM_STRIDE 8          /* floats per Gaussian geometry record                 */
+#define LS_MAX_VALUE_CHANNELS 16  /* colour (0|3) + feature channels blended in one pass */
+
+enum { LS_COLOR_NONE = 0, LS_COLOR_PRECOMP = 1, LS_COLOR_SH = 2 };
+enum { LS_FEATURE_NONE = 0, LS_FEATURE_PRECOMP = 1, LS_FEATURE_SH = 2 };
+enum { LS_STAGE_GEOMETRY = 1, LS_STAGE_RENDER = 2 };
+
+typedef struct LsRasterScene {
+    int32_t n_views;           /* V                                                          */
+    int32_t views_per_scene;   /* V % views_per_scene == 0; S = V / views_per_scene          */
+    int32_t G, H, W;
+    int32_t C;                 /* feature channels (0 = none)                                */
+    int32_t color_mode;        /* LS_COLOR_*                                                 */
+    int32_t sh_degree;         /* colour SH degree 0..4 (cuda_splatting.py:141)              */
+    int32_t feature_mode;      /* LS_FEATURE_*; _SH evaluates 0.5+eval_sh in-kernel, fusing
+                                  cuda_splatting.py:94-101 (sh_utils.py:42-97)               */
+    int32_t feature_sh_degree; /* 0..4                                                       */
+    const float* means3D;      /* (S,G,3)                                                    */
+    const float* cov3D;        /* (S,G,6) upper triangle 00 01 02 11 12 22 (cuda_splatting.py:148) */
+    const float* opacity;      /* (S,G)                                                      */
+    const float* color;        /* PRECOMP: (S,G,3); SH: (S,G,(deg+1)^2,3) (cuda_splatting.py:91) */
+    const float* feature;      /* PRECOMP: (S,G,C); SH: (S,G,C,(fdeg+1)^2)                   */
+    const float* viewmatrix;   /* (V,16) transposed world->view (cuda_splatting.py:116)      */
+    const float* projmatrix;   /* (V,16) transposed full projection (:117)                   */
+    const float* campos;       /* (V,3)                                                      */
+    const float* tanfov;       /* (V,2) tan(fov_x/2), tan(fov_y/2) -- device, no .item()     */
+    const float* bg;           /* (V,3) colour background (features composite over 0)        */
+    const float* scene_scale;  /* (V) or NULL: means*=s, cov*=s*s (cuda_splatting.py:75-82)  */
+} LsRasterScene;
+
+/* State written by forward and read by backward. */
+typedef struct LsRasterState {
+    float*    geom;          /* (V,G,8): x, y, A, B | Cc, opacity, depth, 0  with
+                                (A,B,Cc) = (-0.5 cxx, -cxy, -0.5 cyy) * log2(e), the conic
+                                pre-scaled so that alpha = opacity * exp2(A dx^2 + B dx dy + Cc dy^2) */
+    float*    chan;          /* (V,G,chan_stride): colour(0|3) then C features               */
+    int32_t*  radii;         /* (V,G)  0 = culled                                            */
+    uint32_t* tiles_touched; /* (V,G)                                                        */
+    uint8_t*  clamped;       /* (V,G) bit c set when colour channel c was clamped at 0       */
+    uint32_t* tile_count;    /* (V*T) scratch                                                */
+    uint32_t* tile_offsets;  /* (V*T+1) exclusive prefix; [V*T] = num_rendered               */
+    uint32_t* stats;         /* (4): num_rendered, max tile count, overflow flag, 0          */
+    uint64_t* keys;          /* (capacity) depth_bits<<32 | gaussian id, sorted per tile     */
+    uint64_t* keys_tmp;      /* (capacity) scratch for tiles longer than the smem tier       */
+    int64_t   capacity;      /* entries in keys / keys_tmp                                   */
+    float*    final_T;       /* (V,H,W)                                                      */
+    uint32_t* n_contrib;     /* (V,H,W)                                                      */
+    int32_t   chan_stride;   /* floats per chan record = round_up(max(1, ncolor + C), 4)     */
+    int32_t   sort_smem_keys;/* keys of one tile held in shared memory by the per-tile sort
+                                (0 = default 4096); longer tiles sort through keys_tmp       */
+} LsRasterState;
+
+typedef struct LsRasterImages {
+    float* color;   /* (V,3,H,W) or NULL when color_mode == NONE */
+    float* feature; /* (V,C,H,W) or NULL when C == 0             */
+    float* alpha;   /* (V,H,W) accumulated alpha ("mask")        */
+    float* depth;   /* (V,H,W) sum_i depth_i alpha_i T_i         */
+} LsRasterImages;
+
+typedef struct LsRasterGrads {
+    /* upstream gradients; any may be NULL (= zero) */
+    const float* dL_dcolor;   /* (V,3,H,W) */
+    const float* dL_dfeature; /* (V,C,H,W) */
+    const float* dL_dalpha;   /* (V,H,W)   */
+    const float* dL_ddepth;   /* (V,H,W)   */
+    /* scratch */
+    float* dL_drecord;        /* (V,G,grad_stride) zero-filled by the library:
+                                 mean2D.x, .y, conic xx, xy, yy, opacity, depth, chan...     */
+    int32_t grad_stride;      /* round_up(7 + ncolor + C, 4)                                 */
+    int32_t reserved0;
+    /* outputs, zero-filled by the library, summed over the views of each scene */
+    float* dL_dmeans3D;       /* (S,G,3) */
+    float* dL_dcov3D;         /* (S,G,6) */
+    float* dL_dopacity;       /* (S,G)   */
+    float* dL_dcolor_in;      /* PRECOMP: (S,G,3); SH: (S,G,(deg+1)^2,3); NULL if none       */
+    float* dL_dfeature_in;    /* PRECOMP: (S,G,C); SH: (S,G,C,(fdeg+1)^2); NULL if none      */
+    float* dL_dmeans2D;       /* (V,G,3) screen-space sink (z = 0), per view; may be NULL    */
+} LsRasterGrads;
+
+/* Buffer sizes (in elements) for a given problem; `out` is a host pointer. */
+typedef struct LsRasterSizes {
+    int64_t n_scenes, tiles_per_view, geom, chan, per_view_gaussian, tile_slots, pixels, grad_record;
+    int32_t chan_stride, grad_stride, n_color, n_value_channels;
+} LsRasterSizes;
+
+LS_API int ls_raster_sizes(const LsRasterScene* scene, LsRasterSizes* out /* host */);
+
+/* stages: LS_STAGE_GEOMETRY runs preprocess + tile counting + scan (writes stats[0..1]);
+ * LS_STAGE_RENDER runs scatter + per-tile sort + blend and needs state->capacity >=
+ * stats[0]; pass both for a single sync-free call with a caller-chosen capacity (stats[2]
+ * is set to 1 when num_rendered exceeds it; entries past the capacity are dropped). */
+LS_API int ls_raster_forward(const LsRasterScene* scene, const LsRasterState* state, const LsRasterImages* images,
+                      int32_t stages, void* stream /* cudaStream_t */);
+
+LS_API int ls_raster_backward(const LsRasterScene* scene, const LsRasterState* state, const LsRasterGrads* grads,
+                       void* stream /* cudaStream_t */);
+
+LS_API const char* ls_last_error(void); /* thread-local, never NULL */
+LS_API int ls_raster_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS_RASTER_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of libls_raster.so (include/ls_raster.h).  No torch types cross the ABI:
+tensors are handed over as raw device pointers + sizes, the stream as a cudaStream_t.
+
+There is NO CPU fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import _build
+
+_fp = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class LsRasterScene(C.Structure):
+    _fields_ = [
+        ("n_views", C.c_int32), ("views_per_scene", C.c_int32), ("G", C.c_int32), ("H", C.c_int32),
+        ("W", C.c_int32), ("C", C.c_int32), ("color_mode", C.c_int32), ("sh_degree", C.c_int32),
+        ("feature_mode", C.c_int32), ("feature_sh_degree", C.c_int32),
+        ("means3D", C.c_void_p), ("cov3D", C.c_void_p), ("opacity", C.c_void_p), ("color", C.c_void_p),
+        ("feature", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("tanfov", C.c_void_p), ("bg", C.c_void_p), ("scene_scale", C.c_void_p),
+    ]
+
+
+class LsRasterState(C.Structure):
+    _fields_ = [
+        ("geom", C.c_void_p), ("chan", C.c_void_p), ("radii", C.c_void_p), ("tiles_touched", C.c_void_p),
+        ("clamped", C.c_void_p), ("tile_count", C.c_void_p), ("tile_offsets", C.c_void_p), ("stats", C.c_void_p),
+        ("keys", C.c_void_p), ("keys_tmp", C.c_void_p), ("capacity", C.c_int64), ("final_T", C.c_void_p),
+        ("n_contrib", C.c_void_p), ("chan_stride", C.c_int32), ("sort_smem_keys", C.c_int32),
+    ]
+
+
+class LsRasterImages(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("feature", C.c_void_p), ("alpha", C.c_void_p), ("depth", C.c_void_p)]
+
+
+class LsRasterGrads(C.Structure):
+    _fields_ = [
+        ("dL_dcolor", C.c_void_p), ("dL_dfeature", C.c_void_p), ("dL_dalpha", C.c_void_p), ("dL_ddepth", C.c_void_p),
+        ("dL_drecord", C.c_void_p), ("grad_stride", C.c_int32), ("reserved0", C.c_int32),
+        ("dL_dmeans3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dopacity", C.c_void_p),
+        ("dL_dcolor_in", C.c_void_p), ("dL_dfeature_in", C.c_void_p), ("dL_dmeans2D", C.c_void_p),
+    ]
+
+
+class LsRasterSizes(C.Structure):
+    _fields_ = [
+        ("n_scenes", C.c_int64), ("tiles_per_view", C.c_int64), ("geom", C.c_int64), ("chan", C.c_int64),
+        ("per_view_gaussian", C.c_int64), ("tile_slots", C.c_int64), ("pixels", C.c_int64),
+        ("grad_record", C.c_int64), ("chan_stride", C.c_int32), ("grad_stride", C.c_int32),
+        ("n_color", C.c_int32), ("n_value_channels", C.c_int32),
+    ]
+
+
+COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
+FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
+STAGE_GEOMETRY, STAGE_RENDER = 1, 2
+ABI_VERSION = 1
+EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version")
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.LIB
+
+
+def load() -> C.CDLL:
+    """Load libls_raster.so (built in-tree by latentsplat_b200._build).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -m latentsplat_b200._build` "
+            "(or __graft_entry__.build()).  latentsplat_b200 has no CPU fallback.")
+    lib = C.CDLL(str(path))
+    lib.ls_last_error.restype = C.c_char_p
+    lib.ls_raster_abi_version.restype = C.c_int
+    lib.ls_raster_sizes.restype = C.c_int
+    lib.ls_raster_sizes.argtypes = [C.POINTER(LsRasterScene), C.POINTER(LsRasterSizes)]
+    lib.ls_raster_forward.restype = C.c_int
+    lib.ls_raster_forward.argtypes = [C.POINTER(LsRasterScene), C.POINTER(LsRasterState), C.POINTER(LsRasterImages),
+                                      C.c_int32, C.c_void_p]
+    lib.ls_raster_backward.restype = C.c_int
+    lib.ls_raster_backward.argtypes = [C.POINTER(LsRasterScene), C.POINTER(LsRasterState), C.POINTER(LsRasterGrads),
+                                       C.c_void_p]
+    if lib.ls_raster_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {load().ls_last_error().decode()}")

@@ -1,0 +1,182 @@
+"""Host side of the splatting decoder: camera set-up and ONE batched rasterizer call.
+
+Mirrors the public functions of /root/reference/src/model/decoder/cuda_splatting.py
+(`get_projection_matrix` :19-46, `render_cuda` :56-167, `render_cuda_orthographic` :170-292,
+`render_depth_cuda` :298-340, `RenderOutput` :49-54) with the same argument meaning, but:
+  * the per-view Python loop (:124-162) is a single `rasterize_views` call over all views;
+  * no `.item()` host syncs: tan(fov/2) stays on the device (:135-136);
+  * the feature SH evaluation (:94-101) and the 1/near scene rescale (:75-82) are fused
+    into the rasterizer's preprocess kernel (`feature_shs`, `scene_scale`);
+  * `views_per_scene` lets one scene be rendered from several cameras without the
+    materialised per-view copies of decoder_splatting_cuda.py:71-86.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import isqrt
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor
+
+from ...rasterizer import RasterDebug, rasterize_views
+
+
+def get_fov(intrinsics: Tensor) -> Tensor:
+    """Field of view (x, y) of normalised intrinsics; /root/reference/src/geometry/projection.py:233-247."""
+    inv = torch.linalg.inv_ex(intrinsics, check_errors=False).inverse
+
+    def ray(v):
+        v = torch.tensor(v, dtype=torch.float32, device=intrinsics.device)
+        v = torch.einsum("bij,j->bi", inv, v)
+        return v / v.norm(dim=-1, keepdim=True)
+
+    left, right = ray([0.0, 0.5, 1.0]), ray([1.0, 0.5, 1.0])
+    top, bottom = ray([0.5, 0.0, 1.0]), ray([0.5, 1.0, 1.0])
+    return torch.stack(((left * right).sum(dim=-1).acos(), (top * bottom).sum(dim=-1).acos()), dim=-1)
+
+
+def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor) -> Tensor:
+    """x,y -> (-1,1), z -> (0,1), w = z_view (cuda_splatting.py:19-46)."""
+    tan_x, tan_y = (0.5 * fov_x).tan(), (0.5 * fov_y).tan()
+    top, right = tan_y * near, tan_x * near
+    bottom, left = -top, -right
+    out = torch.zeros((near.shape[0], 4, 4), dtype=torch.float32, device=near.device)
+    out[:, 0, 0] = 2 * near / (right - left)
+    out[:, 1, 1] = 2 * near / (top - bottom)
+    out[:, 0, 2] = (right + left) / (right - left)
+    out[:, 1, 2] = (top + bottom) / (top - bottom)
+    out[:, 3, 2] = 1
+    out[:, 2, 2] = far / (far - near)
+    out[:, 2, 3] = -(far * near) / (far - near)
+    return out
+
+
+@dataclass
+class RenderOutput:
+    color: Optional[Tensor]    # (batch, 3, h, w)
+    feature: Optional[Tensor]  # (batch, channels, h, w)
+    mask: Tensor               # (batch, h, w)
+    depth: Tensor              # (batch, h, w)
+
+
+def _upper_triangle(cov: Tensor) -> Tensor:
+    """(…,3,3) -> (…,6) in the order 00 01 02 11 12 22 (torch.triu_indices, cuda_splatting.py:148)."""
+    return torch.stack((cov[..., 0, 0], cov[..., 0, 1], cov[..., 0, 2], cov[..., 1, 1], cov[..., 1, 2],
+                        cov[..., 2, 2]), dim=-1)
+
+
+def _camera_matrices(extrinsics: Tensor, near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor):
+    """view (transposed), full projection (transposed) as at cuda_splatting.py:114-118."""
+    projection = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
+    view = torch.linalg.inv_ex(extrinsics, check_errors=False).inverse.transpose(1, 2)
+    return view, view @ projection
+
+
+def _split_sh(color_sh, feature_sh, use_sh):
+    """Shared colour/feature argument handling of render_cuda (:84-107)."""
+    kw = dict(sh_degree=0)
+    if use_sh:
+        if color_sh is not None:
+            kw["sh_degree"] = isqrt(color_sh.shape[-1]) - 1
+            kw["shs"] = color_sh.transpose(-1, -2)           # b g xyz n -> b g n xyz
+        if feature_sh is not None:
+            kw["feature_shs"] = feature_sh                    # evaluated in-kernel (0.5 + eval_sh)
+    else:
+        if color_sh is not None:
+            kw["colors_precomp"] = color_sh[..., 0]
+        if feature_sh is not None:
+            kw["features"] = feature_sh[..., 0]
+    return kw
+
+
+def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                gaussian_opacities: Tensor, gaussian_color_sh_coefficients: Optional[Tensor] = None,
+                gaussian_feature_sh_coefficients: Optional[Tensor] = None, scale_invariant: bool = True,
+                use_sh: bool = True, views_per_scene: int = 1, debug: Optional[RasterDebug] = None) -> RenderOutput:
+    """Same contract as the reference's `render_cuda`.  Camera tensors have `batch` = number of views V;
+    Gaussian tensors have V // views_per_scene rows (views_per_scene=1 reproduces the reference call)."""
+    assert gaussian_color_sh_coefficients is not None or gaussian_feature_sh_coefficients is not None
+    assert use_sh or gaussian_color_sh_coefficients is None or gaussian_color_sh_coefficients.shape[-1] == 1
+
+    scene_scale = None
+    if scale_invariant:  # keep everything in a well-conditioned range (:75-82); means/cov scaled in-kernel
+        scene_scale = 1 / near
+        extrinsics = extrinsics.clone()
+        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scene_scale[:, None]
+        near, far = near * scene_scale, far * scene_scale
+
+    h, w = image_shape
+    fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
+    tanfov = torch.stack(((0.5 * fov_x).tan(), (0.5 * fov_y).tan()), dim=-1)
+    view, full_projection = _camera_matrices(extrinsics, near, far, fov_x, fov_y)
+
+    color, feature, alpha, depth, _ = rasterize_views(
+        gaussian_means, _upper_triangle(gaussian_covariances), gaussian_opacities,
+        viewmatrix=view, projmatrix=full_projection, campos=extrinsics[:, :3, 3], tanfov=tanfov,
+        image_height=h, image_width=w, bg=background_color, scene_scale=scene_scale, debug=debug,
+        **_split_sh(gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients, use_sh))
+    return RenderOutput(color, feature, alpha, depth)
+
+
+def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,
+                             image_shape: tuple[int, int], background_features: Tensor, gaussian_means: Tensor,
+                             gaussian_covariances: Tensor, gaussian_opacities: Tensor,
+                             gaussian_color_sh_coefficients: Optional[Tensor] = None,
+                             gaussian_feature_sh_coefficients: Optional[Tensor] = None, fov_degrees: float = 0.1,
+                             use_sh: bool = True, dump: Optional[dict] = None) -> RenderOutput:
+    """Fake orthographic view: a far-away camera with a tiny field of view (cuda_splatting.py:170-292)."""
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    fov_x = torch.tensor(fov_degrees, device=extrinsics.device).deg2rad()
+    tan_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_x
+    tan_y = 0.5 * height / distance_to_near
+    fov_y = (2 * tan_y).atan()
+    near, far = near + distance_to_near, far + distance_to_near
+    move_back = torch.eye(4, dtype=torch.float32, device=extrinsics.device).repeat(b, 1, 1)
+    move_back[:, 2, 3] = -distance_to_near
+    extrinsics = extrinsics @ move_back
+    if dump is not None:
+        dump.update(extrinsics=extrinsics, fov_x=fov_x, fov_y=fov_y, near=near, far=far)
+    view, full_projection = _camera_matrices(extrinsics, near, far, fov_x.expand(b), fov_y)
+    tanfov = torch.stack((tan_x.expand(b), tan_y.expand(b)), dim=-1)
+    color, feature, alpha, depth, _ = rasterize_views(
+        gaussian_means, _upper_triangle(gaussian_covariances), gaussian_opacities,
+        viewmatrix=view, projmatrix=full_projection, campos=extrinsics[:, :3, 3], tanfov=tanfov,
+        image_height=h, image_width=w, bg=background_features,
+        **_split_sh(gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients, use_sh))
+    return RenderOutput(color, feature, alpha, depth)
+
+
+DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
+
+
+def depth_to_relative_disparity(depth: Tensor, near: Tensor, far: Tensor, eps: float = 1e-10) -> Tensor:
+    """0 at near, 1 at far (/root/reference/src/model/encoder/epipolar/conversions.py:17-27)."""
+    disp_near, disp_far, disp = 1 / (near + eps), 1 / (far + eps), 1 / (depth + eps)
+    return 1 - (disp - disp_far) / (disp_near - disp_far + eps)
+
+
+def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                      gaussian_means: Tensor, gaussian_covariances: Tensor, gaussian_opacities: Tensor,
+                      scale_invariant: bool = True, mode: DepthRenderingMode = "depth",
+                      views_per_scene: int = 1) -> Tensor:
+    """Depth (or a transform of it) rendered as a fake colour (cuda_splatting.py:298-340)."""
+    v = extrinsics.shape[0]
+    means_v = gaussian_means.repeat_interleave(views_per_scene, dim=0) if views_per_scene > 1 else gaussian_means
+    world2cam = torch.linalg.inv_ex(extrinsics, check_errors=False).inverse
+    z = torch.einsum("bj,bgj->bg", world2cam[:, 2, :3], means_v) + world2cam[:, 2, 3:4]
+    if mode == "disparity":
+        z = 1 / z
+    elif mode == "relative_disparity":
+        z = depth_to_relative_disparity(z, near[:, None], far[:, None])
+    elif mode == "log":
+        z = z.minimum(near[:, None]).maximum(far[:, None]).log()
+    covs = gaussian_covariances.repeat_interleave(views_per_scene, dim=0) if views_per_scene > 1 else gaussian_covariances
+    opac = gaussian_opacities.repeat_interleave(views_per_scene, dim=0) if views_per_scene > 1 else gaussian_opacities
+    result = render_cuda(extrinsics, intrinsics, near, far, image_shape,
+                         torch.zeros((v, 3), dtype=z.dtype, device=z.device), means_v, covs, opac,
+                         z[:, :, None, None].expand(-1, -1, 3, 1), scale_invariant=scale_invariant).color
+    return result.mean(dim=1)

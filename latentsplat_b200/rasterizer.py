@@ -1,0 +1,298 @@
+"""Differentiable Gaussian rasterizer on libls_raster.so (sm_100a), plus the
+`diff_gaussian_rasterization` API the reference imports at
+/root/reference/src/model/decoder/cuda_splatting.py:6-9 and calls at :132-158.
+
+Two entry points:
+  * `rasterize_views(...)`  -- batched: V views of S scenes in one launch sequence
+    (what our decoder uses; replaces the Python loop at cuda_splatting.py:124-162);
+  * `GaussianRasterizationSettings` / `GaussianRasterizer` -- the per-view drop-in.
+
+No CPU path exists: tensors must live on a CUDA device and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _capi
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_views", "RasterDebug"]
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: latentsplat_b200 has no CPU fallback")
+    return t.detach().to(torch.float32).contiguous()
+
+
+class RasterDebug:
+    """Optional sink: pass `debug=RasterDebug()` to keep the binning state for parity dumps."""
+    def __init__(self):
+        self.state = None
+
+
+class _Buffers:
+    """All device buffers of one forward (owned by torch, handed to the C ABI as pointers)."""
+
+    def __init__(self, scene: _capi.LsRasterScene, device, sort_smem_keys: int = 0):
+        lib = _capi.load()
+        sz = _capi.LsRasterSizes()
+        _capi.check(lib.ls_raster_sizes(C.byref(scene), C.byref(sz)), "ls_raster_sizes")
+        self.sizes = sz
+        V, G, H, W = scene.n_views, scene.G, scene.H, scene.W
+        e = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=device)
+        self.geom = e(V, G, 8)
+        self.chan = e(V, G, sz.chan_stride)
+        self.radii = e(V, G, dtype=torch.int32)
+        self.tiles_touched = e(V, G, dtype=torch.int32)
+        self.clamped = e(V, G, dtype=torch.uint8)
+        self.tile_count = e(sz.tile_slots, dtype=torch.int32)
+        self.tile_offsets = e(sz.tile_slots + 1, dtype=torch.int32)
+        self.stats = torch.zeros(4, dtype=torch.int32, device=device)
+        self.keys = None
+        self.keys_tmp = None
+        self.capacity = 0
+        self.final_T = e(V, H, W)
+        self.n_contrib = e(V, H, W, dtype=torch.int32)
+        self.sort_smem_keys = sort_smem_keys
+
+    def alloc_keys(self, capacity: int, device):
+        self.capacity = int(capacity)
+        n = max(self.capacity, 1)
+        self.keys = torch.empty(n, dtype=torch.int64, device=device)
+        self.keys_tmp = torch.empty(n, dtype=torch.int64, device=device)
+
+    def as_struct(self) -> _capi.LsRasterState:
+        return _capi.LsRasterState(
+            _ptr(self.geom), _ptr(self.chan), _ptr(self.radii), _ptr(self.tiles_touched), _ptr(self.clamped),
+            _ptr(self.tile_count), _ptr(self.tile_offsets), _ptr(self.stats), _ptr(self.keys), _ptr(self.keys_tmp),
+            self.capacity, _ptr(self.final_T), _ptr(self.n_contrib), self.sizes.chan_stride, self.sort_smem_keys)
+
+
+def _make_scene(V, vps, G, H, W, Cf, color_mode, sh_degree, feature_mode, fdeg, means3D, cov3D, opacity, color,
+                feature, viewmatrix, projmatrix, campos, tanfov, bg, scene_scale) -> _capi.LsRasterScene:
+    return _capi.LsRasterScene(V, vps, G, H, W, Cf, color_mode, sh_degree, feature_mode, fdeg, _ptr(means3D),
+                               _ptr(cov3D), _ptr(opacity), _ptr(color), _ptr(feature), _ptr(viewmatrix),
+                               _ptr(projmatrix), _ptr(campos), _ptr(tanfov), _ptr(bg), _ptr(scene_scale))
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, cov3D, opacity, color, feature, means2D, viewmatrix, projmatrix, campos, tanfov, bg,
+                scene_scale, H, W, views_per_scene, color_mode, sh_degree, feature_mode, feature_sh_degree,
+                sort_smem_keys, debug):
+        lib = _capi.load()
+        device = means3D.device
+        means3D_c = _f32c(means3D, "means3D")
+        cov3D_c = _f32c(cov3D, "cov3D")
+        opacity_c = _f32c(opacity, "opacities")
+        color_c = _f32c(color, "colour")
+        feature_c = _f32c(feature, "features")
+        viewmatrix, projmatrix = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+        campos, tanfov, bg = _f32c(campos, "campos"), _f32c(tanfov, "tanfov"), _f32c(bg, "bg")
+        scene_scale = _f32c(scene_scale, "scene_scale")
+        S, G = means3D_c.shape[0], means3D_c.shape[1]
+        V = viewmatrix.shape[0]
+        if V != S * views_per_scene:
+            raise RuntimeError(f"{V} views != {S} scenes x {views_per_scene} views per scene")
+        Cf = 0 if feature_c is None else feature_c.shape[2]
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            scene = _make_scene(V, views_per_scene, G, H, W, Cf, color_mode, sh_degree, feature_mode,
+                                feature_sh_degree, means3D_c, cov3D_c, opacity_c, color_c, feature_c, viewmatrix,
+                                projmatrix, campos, tanfov, bg, scene_scale)
+            buf = _Buffers(scene, device, sort_smem_keys)
+            images = dict(
+                color=torch.empty((V, 3, H, W), device=device) if color_mode != _capi.COLOR_NONE else None,
+                feature=torch.empty((V, Cf, H, W), device=device) if Cf else None,
+                alpha=torch.empty((V, H, W), device=device), depth=torch.empty((V, H, W), device=device))
+            im = _capi.LsRasterImages(_ptr(images["color"]), _ptr(images["feature"]), _ptr(images["alpha"]),
+                                      _ptr(images["depth"]))
+            st = buf.as_struct()
+            _capi.check(lib.ls_raster_forward(C.byref(scene), C.byref(st), C.byref(im), _capi.STAGE_GEOMETRY, stream),
+                        "ls_raster_forward(geometry)")
+            # The one host sync of the step: exact size of the key lists (the lineage does this
+            # once per view; here once per batched call).
+            num_rendered = int(buf.stats[0].item())
+            buf.alloc_keys(num_rendered, device)
+            st = buf.as_struct()
+            _capi.check(lib.ls_raster_forward(C.byref(scene), C.byref(st), C.byref(im), _capi.STAGE_RENDER, stream),
+                        "ls_raster_forward(render)")
+        ctx.buf = buf
+        ctx.cfg = (H, W, views_per_scene, color_mode, sh_degree, feature_mode, feature_sh_degree, Cf, V, S, G)
+        ctx.has_means2D = means2D is not None
+        ctx.save_for_backward(means3D_c, cov3D_c, opacity_c, color_c, feature_c, viewmatrix, projmatrix, campos,
+                              tanfov, bg, scene_scale)
+        if debug is not None:
+            debug.state = buf
+            debug.num_rendered = num_rendered
+        radii = buf.radii
+        ctx.mark_non_differentiable(radii)
+        return images["color"], images["feature"], images["alpha"], images["depth"], radii
+
+    @staticmethod
+    def backward(ctx, g_color, g_feature, g_alpha, g_depth, _g_radii):
+        lib = _capi.load()
+        (means3D, cov3D, opacity, color, feature, viewmatrix, projmatrix, campos, tanfov, bg,
+         scene_scale) = ctx.saved_tensors
+        H, W, vps, color_mode, sh_degree, feature_mode, fdeg, Cf, V, S, G = ctx.cfg
+        buf: _Buffers = ctx.buf
+        device = means3D.device
+        gc = lambda t: None if t is None else t.to(torch.float32).contiguous()
+        g_color, g_feature, g_alpha, g_depth = gc(g_color), gc(g_feature), gc(g_alpha), gc(g_depth)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            scene = _make_scene(V, vps, G, H, W, Cf, color_mode, sh_degree, feature_mode, fdeg, means3D, cov3D,
+                                opacity, color, feature, viewmatrix, projmatrix, campos, tanfov, bg, scene_scale)
+            gs = buf.sizes.grad_stride
+            record = torch.empty((V, G, gs), device=device)
+            d_means3D = torch.empty_like(means3D)
+            d_cov3D = torch.empty_like(cov3D)
+            d_opacity = torch.empty_like(opacity)
+            d_color = torch.empty_like(color) if color is not None else None
+            d_feature = torch.empty_like(feature) if feature is not None else None
+            d_means2D = torch.empty((V, G, 3), device=device) if ctx.has_means2D else None
+            grads = _capi.LsRasterGrads(_ptr(g_color), _ptr(g_feature), _ptr(g_alpha), _ptr(g_depth), _ptr(record),
+                                        gs, 0, _ptr(d_means3D), _ptr(d_cov3D), _ptr(d_opacity), _ptr(d_color),
+                                        _ptr(d_feature), _ptr(d_means2D))
+            st = buf.as_struct()
+            _capi.check(lib.ls_raster_backward(C.byref(scene), C.byref(st), C.byref(grads), stream),
+                        "ls_raster_backward")
+        return (d_means3D, d_cov3D, d_opacity, d_color, d_feature, d_means2D) + (None,) * 15
+
+
+def rasterize_views(means3D: Tensor, cov3D: Tensor, opacities: Tensor, *, viewmatrix: Tensor, projmatrix: Tensor,
+                    campos: Tensor, tanfov: Tensor, image_height: int, image_width: int,
+                    bg: Optional[Tensor] = None, shs: Optional[Tensor] = None,
+                    colors_precomp: Optional[Tensor] = None, features: Optional[Tensor] = None,
+                    feature_shs: Optional[Tensor] = None, sh_degree: int = 0, scene_scale: Optional[Tensor] = None,
+                    means2D: Optional[Tensor] = None, sort_smem_keys: int = 0, debug: Optional[RasterDebug] = None):
+    """Render V = S * views_per_scene views in one launch sequence.
+
+    means3D (S,G,3), cov3D (S,G,6), opacities (S,G); colour: `shs` (S,G,n,3) or
+    `colors_precomp` (S,G,3) or neither; features: `features` (S,G,C) pre-evaluated or
+    `feature_shs` (S,G,C,nf) evaluated in-kernel as 0.5+eval_sh (cuda_splatting.py:94-101).
+    Cameras (V,...): viewmatrix/projmatrix (V,4,4) transposed as in cuda_splatting.py:115-118,
+    campos (V,3), tanfov (V,2), bg (V,3), scene_scale (V,) or None.
+    Returns (color|None (V,3,H,W), feature|None (V,C,H,W), alpha (V,H,W), depth (V,H,W), radii (V,G)).
+    """
+    if shs is not None and colors_precomp is not None:
+        raise ValueError("Please provide only one of either SHs or precomputed colors!")
+    if features is not None and feature_shs is not None:
+        raise ValueError("Provide either pre-evaluated features or feature SH coefficients, not both")
+    V = viewmatrix.shape[0]
+    S = means3D.shape[0]
+    if V % S:
+        raise ValueError(f"{V} views cannot be split over {S} scenes")
+    if shs is not None:
+        color, color_mode = shs, _capi.COLOR_SH
+        n = shs.shape[2]
+        if (sh_degree + 1) ** 2 > n:
+            raise ValueError(f"sh_degree {sh_degree} needs {(sh_degree + 1) ** 2} coefficients, got {n}")
+        if n != (sh_degree + 1) ** 2:
+            color = shs[:, :, : (sh_degree + 1) ** 2]
+    elif colors_precomp is not None:
+        color, color_mode = colors_precomp, _capi.COLOR_PRECOMP
+    else:
+        color, color_mode = None, _capi.COLOR_NONE
+    fdeg = 0
+    if feature_shs is not None:
+        feature, feature_mode = feature_shs, _capi.FEATURE_SH
+        nf = feature_shs.shape[3]
+        fdeg = int(round(nf ** 0.5)) - 1
+        if (fdeg + 1) ** 2 != nf:
+            raise ValueError(f"feature SH coefficient count {nf} is not a square")
+    elif features is not None:
+        feature, feature_mode = features, _capi.FEATURE_PRECOMP
+    else:
+        feature, feature_mode = None, _capi.FEATURE_NONE
+    if color is None and feature is None:
+        raise ValueError("nothing to render: provide colours and/or features (cuda_splatting.py:71)")
+    if bg is None:
+        bg = torch.zeros((V, 3), device=means3D.device)
+    return _Rasterize.apply(means3D, cov3D, opacities, color, feature, means2D, viewmatrix.reshape(V, 16),
+                            projmatrix.reshape(V, 16), campos, tanfov, bg, scene_scale, int(image_height),
+                            int(image_width), V // S, color_mode, int(sh_degree), feature_mode, fdeg,
+                            int(sort_smem_keys), debug)
+
+
+# ------------------------------------------------------------------------------------------
+# diff_gaussian_rasterization drop-in (per-view API)
+# ------------------------------------------------------------------------------------------
+class GaussianRasterizationSettings(NamedTuple):
+    """The 12 fields the reference passes at cuda_splatting.py:132-145."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: Tensor
+    scale_modifier: float
+    viewmatrix: Tensor
+    projmatrix: Tensor
+    sh_degree: int
+    campos: Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _cov3d_from_scales_rotations(scales: Tensor, rotations: Tensor, scale_modifier: float) -> Tensor:
+    """[EXT] computeCov3D: Sigma = R S S^T R^T with quaternion (r,x,y,z); returns the 6 upper-triangle
+    entries.  Plain torch: the reference never takes this path (it always passes cov3D_precomp)."""
+    q = rotations / rotations.norm(dim=-1, keepdim=True)
+    r, x, y, z = q.unbind(-1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=-1).reshape(-1, 3, 3)
+    M = R * (scales * scale_modifier)[:, None, :]
+    cov = M @ M.transpose(1, 2)
+    i, j = torch.triu_indices(3, 3)
+    return cov[:, i, j]
+
+
+class GaussianRasterizer(nn.Module):
+    """Per-view rasterizer with the call signature used at cuda_splatting.py:150-158.
+
+    Returns the 5-tuple (image | None, feature_map | None, mask (1,H,W), depth_map (1,H,W), radii (G,)).
+    `shs`, `colors_precomp` and `features` may each be None; unlike stock 3DGS, passing neither colour input
+    is legal as long as features are given (model_wrapper.py:369 `return_colors=False`).
+    """
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, features=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        if shs is not None and colors_precomp is not None:
+            raise Exception("Please provide only one of either SHs or precomputed colors!")
+        if (scales is None or rotations is None) == (cov3D_precomp is None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        if not means3D.is_cuda:
+            raise RuntimeError("GaussianRasterizer needs CUDA tensors: latentsplat_b200 has no CPU fallback")
+        if cov3D_precomp is None:
+            cov3D_precomp = _cov3d_from_scales_rotations(scales, rotations, rs.scale_modifier)
+        dev = means3D.device
+        if isinstance(rs.tanfovx, Tensor) or isinstance(rs.tanfovy, Tensor):  # cuda_splatting.py:260-261
+            tanfov = torch.stack([torch.as_tensor(rs.tanfovx, device=dev).float().reshape(()),
+                                  torch.as_tensor(rs.tanfovy, device=dev).float().reshape(())]).reshape(1, 2)
+        else:
+            tanfov = torch.tensor([[float(rs.tanfovx), float(rs.tanfovy)]], dtype=torch.float32, device=dev)
+        color, feat, alpha, depth, radii = rasterize_views(
+            means3D[None], cov3D_precomp[None], opacities.reshape(1, -1),
+            viewmatrix=rs.viewmatrix.reshape(1, 4, 4), projmatrix=rs.projmatrix.reshape(1, 4, 4),
+            campos=rs.campos.reshape(1, 3), tanfov=tanfov, image_height=rs.image_height,
+            image_width=rs.image_width, bg=rs.bg.reshape(1, 3),
+            shs=None if shs is None else shs[None], colors_precomp=None if colors_precomp is None else colors_precomp[None],
+            features=None if features is None else features[None], sh_degree=rs.sh_degree,
+            means2D=None if means2D is None else means2D[None])
+        return (None if color is None else color[0], None if feat is None else feat[0], alpha, depth, radii[0])
