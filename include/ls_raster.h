@@ -55,7 +55,17 @@ extern "C" {
 
 enum { LS_COLOR_NONE = 0, LS_COLOR_PRECOMP = 1, LS_COLOR_SH = 2 };
 enum { LS_FEATURE_NONE = 0, LS_FEATURE_PRECOMP = 1, LS_FEATURE_SH = 2 };
-enum { LS_STAGE_GEOMETRY = 1, LS_STAGE_RENDER = 2 };
+/* forward stages (bit mask); each may be launched separately so that a profiler can bracket it */
+enum { LS_STAGE_GEOMETRY = 1,  /* preprocess + per-tile count + exclusive scan (writes stats[0..2]) */
+       LS_STAGE_SCATTER = 2,   /* (depth|id) keys into the tile segments                            */
+       LS_STAGE_SORT = 4,      /* per-tile radix sort                                               */
+       LS_STAGE_BLEND = 8,     /* front-to-back compositing                                         */
+       LS_STAGE_RENDER = 2 | 4 | 8,
+       LS_STAGE_ALL = 15 };
+/* backward stages */
+enum { LS_BWD_BLEND = 1,       /* back-to-front replay -> per-Gaussian gradient records             */
+       LS_BWD_GEOMETRY = 2,    /* records -> input gradients                                        */
+       LS_BWD_ALL = 3 };
 
 typedef struct LsRasterScene {
     int32_t n_views;           /* V                                                          */
@@ -137,15 +147,15 @@ typedef struct LsRasterSizes {
 
 LS_API int ls_raster_sizes(const LsRasterScene* scene, LsRasterSizes* out /* host */);
 
-/* stages: LS_STAGE_GEOMETRY runs preprocess + tile counting + scan (writes stats[0..1]);
- * LS_STAGE_RENDER runs scatter + per-tile sort + blend and needs state->capacity >=
- * stats[0]; pass both for a single sync-free call with a caller-chosen capacity (stats[2]
- * is set to 1 when num_rendered exceeds it; entries past the capacity are dropped). */
+/* stages: LS_STAGE_GEOMETRY writes stats[0..2]; the LS_STAGE_RENDER stages need
+ * state->capacity >= stats[0]; pass LS_STAGE_ALL for a single sync-free call with a
+ * caller-chosen capacity (stats[2] is set to 1 when num_rendered exceeds it; entries past
+ * the capacity are dropped). */
 LS_API int ls_raster_forward(const LsRasterScene* scene, const LsRasterState* state, const LsRasterImages* images,
                       int32_t stages, void* stream /* cudaStream_t */);
 
 LS_API int ls_raster_backward(const LsRasterScene* scene, const LsRasterState* state, const LsRasterGrads* grads,
-                       void* stream /* cudaStream_t */);
+                       int32_t stages, void* stream /* cudaStream_t */);
 
 LS_API const char* ls_last_error(void); /* thread-local, never NULL */
 LS_API int ls_raster_abi_version(void);

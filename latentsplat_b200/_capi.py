@@ -58,7 +58,8 @@ class LsRasterSizes(C.Structure):
 
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
-STAGE_GEOMETRY, STAGE_RENDER = 1, 2
+STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15
+BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
 ABI_VERSION = 1
 EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version")
 
@@ -89,7 +90,7 @@ def load() -> C.CDLL:
                                       C.c_int32, C.c_void_p]
     lib.ls_raster_backward.restype = C.c_int
     lib.ls_raster_backward.argtypes = [C.POINTER(LsRasterScene), C.POINTER(LsRasterState), C.POINTER(LsRasterGrads),
-                                       C.c_void_p]
+                                       C.c_int32, C.c_void_p]
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -367,13 +367,14 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
 using namespace ls;
 
 extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* st, const LsRasterGrads* gr,
-                                  void* stream_) {
+                                  int32_t stages, void* stream_) {
     if (ls_validate_scene(sc)) return -1;
     if (!st || !gr) return ls_fail("state/grads is NULL");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int ncol = n_color(sc->color_mode);
     const int nc = ncol + sc->C;
     if (gr->grad_stride != round_up4(7 + nc)) return ls_fail("grad_stride %d != %d", gr->grad_stride, round_up4(7 + nc));
+    if (sc->G == 0) return 0;  // nothing to differentiate; zero-sized outputs have NULL pointers
     if (!gr->dL_drecord || !gr->dL_dmeans3D || !gr->dL_dcov3D || !gr->dL_dopacity) return ls_fail("a required gradient pointer is NULL");
     if (ncol && !gr->dL_dcolor_in) return ls_fail("dL_dcolor_in is NULL");
     if (sc->C && !gr->dL_dfeature_in) return ls_fail("dL_dfeature_in is NULL");
@@ -381,7 +382,19 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
     const size_t S = (size_t)(sc->n_views / sc->views_per_scene);
     const size_t SG = S * (size_t)sc->G, VG = (size_t)sc->n_views * sc->G;
 
-    cudaMemsetAsync(gr->dL_drecord, 0, sizeof(float) * VG * gr->grad_stride, stream);
+    if (stages & LS_BWD_BLEND) {
+        cudaMemsetAsync(gr->dL_drecord, 0, sizeof(float) * VG * gr->grad_stride, stream);
+        dim3 grid(gx * gy, sc->n_views);
+        switch (nc) {
+#define LS_CASE(N) case N: launch_blend_bwd<N>(*sc, *st, *gr, ncol, grid, stream); break;
+            LS_CASE(1) LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
+            LS_CASE(9) LS_CASE(10) LS_CASE(11) LS_CASE(12) LS_CASE(13) LS_CASE(14) LS_CASE(15) LS_CASE(16)
+#undef LS_CASE
+            default: return ls_fail("unsupported channel count %d", nc);
+        }
+        if (ls_check_cuda("backward blend")) return -1;
+    }
+    if (!(stages & LS_BWD_GEOMETRY)) return 0;
     cudaMemsetAsync(gr->dL_dmeans3D, 0, sizeof(float) * SG * 3, stream);
     cudaMemsetAsync(gr->dL_dcov3D, 0, sizeof(float) * SG * 6, stream);
     cudaMemsetAsync(gr->dL_dopacity, 0, sizeof(float) * SG, stream);
@@ -392,16 +405,6 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
     if (sc->feature_mode == LS_FEATURE_PRECOMP) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C, stream);
     if (sc->feature_mode == LS_FEATURE_SH)
         cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1), stream);
-    if (sc->G == 0) return ls_check_cuda("backward memset");
-
-    dim3 grid(gx * gy, sc->n_views);
-    switch (nc) {
-#define LS_CASE(N) case N: launch_blend_bwd<N>(*sc, *st, *gr, ncol, grid, stream); break;
-        LS_CASE(1) LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
-        LS_CASE(9) LS_CASE(10) LS_CASE(11) LS_CASE(12) LS_CASE(13) LS_CASE(14) LS_CASE(15) LS_CASE(16)
-#undef LS_CASE
-        default: return ls_fail("unsupported channel count %d", nc);
-    }
     dim3 grid2((sc->G + 255) / 256, sc->n_views);
     k_preprocess_bwd<<<grid2, 256, 0, stream>>>(*sc, *st, *gr);
     return ls_check_cuda("backward");

@@ -470,9 +470,13 @@ int ls_validate_scene(const LsRasterScene* sc) {
     const int nc = n_color(sc->color_mode) + sc->C;
     if (nc < 1) return ls_fail("nothing to render: no colour and no features (cuda_splatting.py:71)");
     if (nc > LS_MAX_VALUE_CHANNELS) return ls_fail("colour+feature channels %d exceed LS_MAX_VALUE_CHANNELS=%d", nc, LS_MAX_VALUE_CHANNELS);
-    if (!sc->means3D || !sc->cov3D || !sc->opacity || !sc->viewmatrix || !sc->projmatrix || !sc->campos || !sc->tanfov) return ls_fail("a required scene pointer is NULL");
-    if (sc->color_mode != LS_COLOR_NONE && (!sc->color || !sc->bg)) return ls_fail("color/bg pointer is NULL");
-    if (sc->feature_mode != LS_FEATURE_NONE && !sc->feature) return ls_fail("feature pointer is NULL");
+    if (!sc->viewmatrix || !sc->projmatrix || !sc->campos || !sc->tanfov) return ls_fail("a required camera pointer is NULL");
+    if (sc->color_mode != LS_COLOR_NONE && !sc->bg) return ls_fail("bg pointer is NULL");
+    if (sc->G > 0) {  // zero-sized arrays legitimately have NULL data pointers
+        if (!sc->means3D || !sc->cov3D || !sc->opacity) return ls_fail("a required scene pointer is NULL");
+        if (sc->color_mode != LS_COLOR_NONE && !sc->color) return ls_fail("color pointer is NULL");
+        if (sc->feature_mode != LS_FEATURE_NONE && !sc->feature) return ls_fail("feature pointer is NULL");
+    }
     return 0;
 }
 
@@ -507,8 +511,9 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
     if (st->chan_stride != round_up4(nc)) return ls_fail("chan_stride %d != %d", st->chan_stride, round_up4(nc));
     const int gx = (sc->W + kTile - 1) / kTile, gy = (sc->H + kTile - 1) / kTile;
     const int n_slots = sc->n_views * gx * gy;
-    if (!st->geom || !st->chan || !st->radii || !st->tiles_touched || !st->clamped || !st->tile_count || !st->tile_offsets || !st->stats)
-        return ls_fail("a required state pointer is NULL");
+    if (!st->tile_count || !st->tile_offsets || !st->stats) return ls_fail("a required state pointer is NULL");
+    if (sc->G > 0 && (!st->geom || !st->chan || !st->radii || !st->tiles_touched || !st->clamped))
+        return ls_fail("a required per-Gaussian state pointer is NULL");
 
     if (stages & LS_STAGE_GEOMETRY) {
         cudaMemsetAsync(st->tile_count, 0, sizeof(uint32_t) * (size_t)n_slots, stream);
@@ -519,26 +524,31 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
         k_scan_tiles<<<1, 1024, 0, stream>>>(st->tile_count, st->tile_offsets, st->stats, n_slots, (long long)st->capacity);
         if (ls_check_cuda("geometry stage")) return -1;
     }
-    if (stages & LS_STAGE_RENDER) {
+    if ((stages & LS_STAGE_RENDER) && st->capacity > 0 && (!st->keys || !st->keys_tmp))
+        return ls_fail("keys/keys_tmp is NULL with capacity %lld", (long long)st->capacity);
+    if ((stages & LS_STAGE_SCATTER) && sc->G > 0 && st->capacity > 0) {
+        dim3 grid((sc->G + 255) / 256, sc->n_views);
+        k_scatter_keys<<<grid, 256, 0, stream>>>(*sc, *st);
+        if (ls_check_cuda("scatter stage")) return -1;
+    }
+    if ((stages & LS_STAGE_SORT) && sc->G > 0 && st->capacity > 0) {
+        int smem_keys = st->sort_smem_keys > 0 ? st->sort_smem_keys : 4096;
+        if (smem_keys > 12288) smem_keys = 12288;
+        const size_t smem_bytes = (size_t)smem_keys * 2 * sizeof(uint64_t);
+        static thread_local size_t configured = 0;
+        if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
+            if (cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
+                return ls_check_cuda("sort smem attribute");
+            configured = smem_bytes;
+        }
+        k_tile_sort<<<n_slots, kSortThreads, smem_bytes, stream>>>(st->keys, st->keys_tmp, st->tile_offsets, smem_keys,
+                                                                    (long long)st->capacity);
+        if (ls_check_cuda("sort stage")) return -1;
+    }
+    if (stages & LS_STAGE_BLEND) {
         if (!im || !im->alpha || !im->depth || !st->final_T || !st->n_contrib) return ls_fail("image/state output pointer is NULL");
         if (ncol && !im->color) return ls_fail("color image pointer is NULL");
         if (sc->C && !im->feature) return ls_fail("feature image pointer is NULL");
-        if (st->capacity > 0 && (!st->keys || !st->keys_tmp)) return ls_fail("keys/keys_tmp is NULL with capacity %lld", (long long)st->capacity);
-        if (sc->G > 0 && st->capacity > 0) {
-            dim3 grid((sc->G + 255) / 256, sc->n_views);
-            k_scatter_keys<<<grid, 256, 0, stream>>>(*sc, *st);
-            int smem_keys = st->sort_smem_keys > 0 ? st->sort_smem_keys : 4096;
-            if (smem_keys > 12288) smem_keys = 12288;
-            const size_t smem_bytes = (size_t)smem_keys * 2 * sizeof(uint64_t);
-            static thread_local size_t configured = 0;
-            if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
-                if (cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
-                    return ls_check_cuda("sort smem attribute");
-                configured = smem_bytes;
-            }
-            k_tile_sort<<<n_slots, kSortThreads, smem_bytes, stream>>>(st->keys, st->keys_tmp, st->tile_offsets, smem_keys,
-                                                                        (long long)st->capacity);
-        }
         dim3 grid(gx * gy, sc->n_views);
         switch (nc) {
 #define LS_CASE(N) case N: launch_blend_fwd<N>(*sc, *st, *im, ncol, grid, stream); break;
@@ -547,7 +557,7 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
 #undef LS_CASE
             default: return ls_fail("unsupported channel count %d", nc);
         }
-        if (ls_check_cuda("render stage")) return -1;
+        if (ls_check_cuda("blend stage")) return -1;
     }
     return 0;
 }

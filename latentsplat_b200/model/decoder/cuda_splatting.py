@@ -22,18 +22,25 @@ from torch import Tensor
 from ...rasterizer import RasterDebug, rasterize_views
 
 
+_FOV_RAYS: dict = {}
+
+
+def _fov_rays(device) -> Tensor:
+    """The four constant image-edge points of get_fov, created once per device (a per-call
+    `torch.tensor(list, device=cuda)` is a pageable H2D copy, i.e. a stream sync on every step)."""
+    key = str(device)
+    if key not in _FOV_RAYS:
+        _FOV_RAYS[key] = torch.tensor([[0.0, 0.5, 1.0], [1.0, 0.5, 1.0], [0.5, 0.0, 1.0], [0.5, 1.0, 1.0]],
+                                      dtype=torch.float32, device=device)
+    return _FOV_RAYS[key]
+
+
 def get_fov(intrinsics: Tensor) -> Tensor:
     """Field of view (x, y) of normalised intrinsics; /root/reference/src/geometry/projection.py:233-247."""
     inv = torch.linalg.inv_ex(intrinsics, check_errors=False).inverse
-
-    def ray(v):
-        v = torch.tensor(v, dtype=torch.float32, device=intrinsics.device)
-        v = torch.einsum("bij,j->bi", inv, v)
-        return v / v.norm(dim=-1, keepdim=True)
-
-    left, right = ray([0.0, 0.5, 1.0]), ray([1.0, 0.5, 1.0])
-    top, bottom = ray([0.5, 0.0, 1.0]), ray([0.5, 1.0, 1.0])
-    return torch.stack(((left * right).sum(dim=-1).acos(), (top * bottom).sum(dim=-1).acos()), dim=-1)
+    rays = torch.einsum("bij,kj->kbi", inv, _fov_rays(intrinsics.device))   # left, right, top, bottom
+    rays = rays / rays.norm(dim=-1, keepdim=True)
+    return torch.stack(((rays[0] * rays[1]).sum(dim=-1).acos(), (rays[2] * rays[3]).sum(dim=-1).acos()), dim=-1)
 
 
 def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor) -> Tensor:
@@ -90,34 +97,57 @@ def _split_sh(color_sh, feature_sh, use_sh):
     return kw
 
 
-def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
-                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
-                gaussian_opacities: Tensor, gaussian_color_sh_coefficients: Optional[Tensor] = None,
-                gaussian_feature_sh_coefficients: Optional[Tensor] = None, scale_invariant: bool = True,
-                use_sh: bool = True, views_per_scene: int = 1, debug: Optional[RasterDebug] = None) -> RenderOutput:
-    """Same contract as the reference's `render_cuda`.  Camera tensors have `batch` = number of views V;
-    Gaussian tensors have V // views_per_scene rows (views_per_scene=1 reproduces the reference call)."""
+def _raster_arguments(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
+                      gaussian_covariances, gaussian_opacities, gaussian_color_sh_coefficients,
+                      gaussian_feature_sh_coefficients, scale_invariant, use_sh):
+    """Camera set-up of render_cuda (:75-82, :108-118) -> positional/keyword arguments of rasterize_views."""
     assert gaussian_color_sh_coefficients is not None or gaussian_feature_sh_coefficients is not None
     assert use_sh or gaussian_color_sh_coefficients is None or gaussian_color_sh_coefficients.shape[-1] == 1
-
     scene_scale = None
     if scale_invariant:  # keep everything in a well-conditioned range (:75-82); means/cov scaled in-kernel
         scene_scale = 1 / near
         extrinsics = extrinsics.clone()
         extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scene_scale[:, None]
         near, far = near * scene_scale, far * scene_scale
-
     h, w = image_shape
     fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
     tanfov = torch.stack(((0.5 * fov_x).tan(), (0.5 * fov_y).tan()), dim=-1)
     view, full_projection = _camera_matrices(extrinsics, near, far, fov_x, fov_y)
+    args = (gaussian_means, _upper_triangle(gaussian_covariances), gaussian_opacities)
+    kwargs = dict(viewmatrix=view, projmatrix=full_projection, campos=extrinsics[:, :3, 3], tanfov=tanfov,
+                  image_height=h, image_width=w, bg=background_color, scene_scale=scene_scale,
+                  **_split_sh(gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients, use_sh))
+    return args, kwargs
 
-    color, feature, alpha, depth, _ = rasterize_views(
-        gaussian_means, _upper_triangle(gaussian_covariances), gaussian_opacities,
-        viewmatrix=view, projmatrix=full_projection, campos=extrinsics[:, :3, 3], tanfov=tanfov,
-        image_height=h, image_width=w, bg=background_color, scene_scale=scene_scale, debug=debug,
-        **_split_sh(gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients, use_sh))
+
+def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                gaussian_opacities: Tensor, gaussian_color_sh_coefficients: Optional[Tensor] = None,
+                gaussian_feature_sh_coefficients: Optional[Tensor] = None, scale_invariant: bool = True,
+                use_sh: bool = True, views_per_scene: int = 1, debug: Optional[RasterDebug] = None,
+                capacity: Optional[int] = None) -> RenderOutput:
+    """Same contract as the reference's `render_cuda`.  Camera tensors have `batch` = number of views V;
+    Gaussian tensors have V // views_per_scene rows (views_per_scene=1 reproduces the reference call).
+    `capacity`: see rasterize_views (None = exact, int = sync-free)."""
+    assert extrinsics.shape[0] == gaussian_means.shape[0] * views_per_scene
+    args, kwargs = _raster_arguments(extrinsics, intrinsics, near, far, image_shape, background_color,
+                                     gaussian_means, gaussian_covariances, gaussian_opacities,
+                                     gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients,
+                                     scale_invariant, use_sh)
+    color, feature, alpha, depth, _ = rasterize_views(*args, debug=debug, capacity=capacity, **kwargs)
     return RenderOutput(color, feature, alpha, depth)
+
+
+def prepare_render_call(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
+                        gaussian_covariances, gaussian_opacities, gaussian_color_sh_coefficients=None,
+                        gaussian_feature_sh_coefficients=None, scale_invariant=True, use_sh=True):
+    """render_cuda's inputs -> an un-launched RasterCall (profiling: time the rasterizer stage by stage)."""
+    from ...rasterizer import prepare_call
+    args, kwargs = _raster_arguments(extrinsics, intrinsics, near, far, image_shape, background_color,
+                                     gaussian_means, gaussian_covariances, gaussian_opacities,
+                                     gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients,
+                                     scale_invariant, use_sh)
+    return prepare_call(*args, **kwargs)
 
 
 def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,

@@ -15,6 +15,7 @@ from torch import Tensor
 
 from ..diagonal_gaussian_distribution import DiagonalGaussianDistribution
 from ..types import Gaussians
+from ...rasterizer import RasterDebug
 from .cuda_splatting import DepthRenderingMode, RenderOutput, render_cuda, render_depth_cuda
 from .decoder import Decoder, DecoderOutput
 
@@ -33,6 +34,19 @@ class DecoderSplattingCUDA(Decoder[DecoderSplattingCUDACfg]):
         self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32),
                              persistent=False)
         self.variational = variational
+        # Key-list sizing of the rasterizer: None = exact (one 4-byte host sync per forward, always right);
+        # an int = sync-free / CUDA-graph capturable with that many (tile, Gaussian) slots.  `last_raster`
+        # keeps the device-side counters of the most recent forward so that the caller can verify
+        # `last_raster.stats[2] == 0` (no overflow) whenever convenient.
+        self.raster_capacity: Optional[int] = None
+        self.last_raster = RasterDebug()
+
+    def calibrate_raster_capacity(self, slack: float = 1.5) -> int:
+        """After at least one exact forward: capacity = slack x the size that forward needed."""
+        if self.last_raster.num_rendered is None:
+            raise RuntimeError("run one forward with raster_capacity=None before calibrating")
+        self.raster_capacity = int(self.last_raster.num_rendered * slack) + 1024
+        return self.raster_capacity
 
     def render_to_decoder_output(self, render_output: RenderOutput, b: int, v: int) -> DecoderOutput:
         split = lambda t: t.reshape(b, v, *t.shape[1:])
@@ -59,7 +73,8 @@ class DecoderSplattingCUDA(Decoder[DecoderSplattingCUDACfg]):
         rendered = render_cuda(
             extrinsics.reshape(b * v, 4, 4), intrinsics.reshape(b * v, 3, 3), near.reshape(b * v),
             far.reshape(b * v), image_shape, self.background_color.expand(b * v, 3), gaussians.means,
-            gaussians.covariances, gaussians.opacities, color_sh, feature_sh, views_per_scene=v)
+            gaussians.covariances, gaussians.opacities, color_sh, feature_sh, views_per_scene=v,
+            debug=self.last_raster, capacity=self.raster_capacity)
         out = self.render_to_decoder_output(rendered, b, v)
         if depth_mode is not None and depth_mode != "depth":
             out.depth = self.render_depth(gaussians, extrinsics, intrinsics, near, far, image_shape, depth_mode)

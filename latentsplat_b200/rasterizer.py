@@ -19,7 +19,7 @@ from torch import Tensor, nn
 
 from . import _capi
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_views", "RasterDebug"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_views", "RasterDebug", "RasterCall"]
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
@@ -38,6 +38,8 @@ class RasterDebug:
     """Optional sink: pass `debug=RasterDebug()` to keep the binning state for parity dumps."""
     def __init__(self):
         self.state = None
+        self.num_rendered = None
+        self.stats = None   # device int32 (4): num_rendered, longest tile list, overflow flag, 0
 
 
 class _Buffers:
@@ -85,113 +87,135 @@ def _make_scene(V, vps, G, H, W, Cf, color_mode, sh_degree, feature_mode, fdeg, 
                                _ptr(projmatrix), _ptr(campos), _ptr(tanfov), _ptr(bg), _ptr(scene_scale))
 
 
+class RasterCall:
+    """One batched rasterizer invocation: owns the prepared (contiguous fp32) inputs, the state buffers and
+    the output images, and launches the C-ABI stages.  `_Rasterize` drives it for autograd; bench.py /
+    profiling drive it stage by stage to bracket individual kernels with CUDA events."""
+
+    def __init__(self, means3D, cov3D, opacity, color, feature, viewmatrix, projmatrix, campos, tanfov, bg,
+                 scene_scale, H, W, views_per_scene, color_mode, sh_degree, feature_mode, feature_sh_degree,
+                 sort_smem_keys=0, capacity=None):
+        self.lib = _capi.load()
+        self.capacity = capacity
+        self.device = means3D.device
+        self.means3D = _f32c(means3D, "means3D")
+        self.cov3D = _f32c(cov3D, "cov3D")
+        self.opacity = _f32c(opacity, "opacities")
+        self.color = _f32c(color, "colour")
+        self.feature = _f32c(feature, "features")
+        self.viewmatrix, self.projmatrix = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+        self.campos, self.tanfov, self.bg = _f32c(campos, "campos"), _f32c(tanfov, "tanfov"), _f32c(bg, "bg")
+        self.scene_scale = _f32c(scene_scale, "scene_scale")
+        S, G = self.means3D.shape[0], self.means3D.shape[1]
+        V = self.viewmatrix.shape[0]
+        if V != S * views_per_scene:
+            raise RuntimeError(f"{V} views != {S} scenes x {views_per_scene} views per scene")
+        Cf = 0 if self.feature is None else self.feature.shape[2]
+        self.cfg = (H, W, views_per_scene, color_mode, sh_degree, feature_mode, feature_sh_degree, Cf, V, S, G)
+        self.scene = _make_scene(V, views_per_scene, G, H, W, Cf, color_mode, sh_degree, feature_mode,
+                                 feature_sh_degree, self.means3D, self.cov3D, self.opacity, self.color,
+                                 self.feature, self.viewmatrix, self.projmatrix, self.campos, self.tanfov, self.bg,
+                                 self.scene_scale)
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.buf = _Buffers(self.scene, dev, sort_smem_keys)
+            self.images = dict(
+                color=torch.empty((V, 3, H, W), device=dev) if color_mode != _capi.COLOR_NONE else None,
+                feature=torch.empty((V, Cf, H, W), device=dev) if Cf else None,
+                alpha=torch.empty((V, H, W), device=dev), depth=torch.empty((V, H, W), device=dev))
+        self.num_rendered = None
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def forward_stage(self, stages: int) -> None:
+        im = _capi.LsRasterImages(_ptr(self.images["color"]), _ptr(self.images["feature"]),
+                                  _ptr(self.images["alpha"]), _ptr(self.images["depth"]))
+        st = self.buf.as_struct()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.ls_raster_forward(C.byref(self.scene), C.byref(st), C.byref(im), stages,
+                                                   self._stream()), f"ls_raster_forward(stages={stages})")
+
+    def size_keys(self) -> int:
+        """The one host sync of a step: exact size of the key lists (the lineage syncs once per VIEW for
+        the same number; here once per batched call)."""
+        self.num_rendered = int(self.buf.stats[0].item())
+        self.buf.alloc_keys(self.num_rendered, self.device)
+        return self.num_rendered
+
+    def forward(self):
+        if self.capacity is None:           # exact: one 4-byte D2H sync per batched call
+            self.forward_stage(_capi.STAGE_GEOMETRY)
+            self.size_keys()
+            self.forward_stage(_capi.STAGE_RENDER)
+        else:                               # sync-free (CUDA-graph capturable): caller-chosen capacity;
+            self.buf.alloc_keys(int(self.capacity), self.device)   # stats[2] flags an overflow
+            self.forward_stage(_capi.STAGE_ALL)
+        return self.images
+
+    def alloc_grads(self, want_means2D: bool):
+        H, W, vps, color_mode, sh_degree, feature_mode, fdeg, Cf, V, S, G = self.cfg
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.grad_out = dict(
+                record=torch.empty((V, G, self.buf.sizes.grad_stride), device=dev),
+                means3D=torch.empty_like(self.means3D), cov3D=torch.empty_like(self.cov3D),
+                opacity=torch.empty_like(self.opacity),
+                color=torch.empty_like(self.color) if self.color is not None else None,
+                feature=torch.empty_like(self.feature) if self.feature is not None else None,
+                means2D=torch.empty((V, G, 3), device=dev) if want_means2D else None)
+        return self.grad_out
+
+    def backward_stage(self, stages: int, g_color, g_feature, g_alpha, g_depth) -> None:
+        o = self.grad_out
+        grads = _capi.LsRasterGrads(_ptr(g_color), _ptr(g_feature), _ptr(g_alpha), _ptr(g_depth), _ptr(o["record"]),
+                                    self.buf.sizes.grad_stride, 0, _ptr(o["means3D"]), _ptr(o["cov3D"]),
+                                    _ptr(o["opacity"]), _ptr(o["color"]), _ptr(o["feature"]), _ptr(o["means2D"]))
+        st = self.buf.as_struct()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.ls_raster_backward(C.byref(self.scene), C.byref(st), C.byref(grads), stages,
+                                                    self._stream()), f"ls_raster_backward(stages={stages})")
+
+
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, cov3D, opacity, color, feature, means2D, viewmatrix, projmatrix, campos, tanfov, bg,
                 scene_scale, H, W, views_per_scene, color_mode, sh_degree, feature_mode, feature_sh_degree,
-                sort_smem_keys, debug):
-        lib = _capi.load()
-        device = means3D.device
-        means3D_c = _f32c(means3D, "means3D")
-        cov3D_c = _f32c(cov3D, "cov3D")
-        opacity_c = _f32c(opacity, "opacities")
-        color_c = _f32c(color, "colour")
-        feature_c = _f32c(feature, "features")
-        viewmatrix, projmatrix = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
-        campos, tanfov, bg = _f32c(campos, "campos"), _f32c(tanfov, "tanfov"), _f32c(bg, "bg")
-        scene_scale = _f32c(scene_scale, "scene_scale")
-        S, G = means3D_c.shape[0], means3D_c.shape[1]
-        V = viewmatrix.shape[0]
-        if V != S * views_per_scene:
-            raise RuntimeError(f"{V} views != {S} scenes x {views_per_scene} views per scene")
-        Cf = 0 if feature_c is None else feature_c.shape[2]
-        with torch.cuda.device(device):
-            stream = torch.cuda.current_stream().cuda_stream
-            scene = _make_scene(V, views_per_scene, G, H, W, Cf, color_mode, sh_degree, feature_mode,
-                                feature_sh_degree, means3D_c, cov3D_c, opacity_c, color_c, feature_c, viewmatrix,
-                                projmatrix, campos, tanfov, bg, scene_scale)
-            buf = _Buffers(scene, device, sort_smem_keys)
-            images = dict(
-                color=torch.empty((V, 3, H, W), device=device) if color_mode != _capi.COLOR_NONE else None,
-                feature=torch.empty((V, Cf, H, W), device=device) if Cf else None,
-                alpha=torch.empty((V, H, W), device=device), depth=torch.empty((V, H, W), device=device))
-            im = _capi.LsRasterImages(_ptr(images["color"]), _ptr(images["feature"]), _ptr(images["alpha"]),
-                                      _ptr(images["depth"]))
-            st = buf.as_struct()
-            _capi.check(lib.ls_raster_forward(C.byref(scene), C.byref(st), C.byref(im), _capi.STAGE_GEOMETRY, stream),
-                        "ls_raster_forward(geometry)")
-            # The one host sync of the step: exact size of the key lists (the lineage does this
-            # once per view; here once per batched call).
-            num_rendered = int(buf.stats[0].item())
-            buf.alloc_keys(num_rendered, device)
-            st = buf.as_struct()
-            _capi.check(lib.ls_raster_forward(C.byref(scene), C.byref(st), C.byref(im), _capi.STAGE_RENDER, stream),
-                        "ls_raster_forward(render)")
-        ctx.buf = buf
-        ctx.cfg = (H, W, views_per_scene, color_mode, sh_degree, feature_mode, feature_sh_degree, Cf, V, S, G)
+                sort_smem_keys, capacity, debug):
+        call = RasterCall(means3D, cov3D, opacity, color, feature, viewmatrix, projmatrix, campos, tanfov, bg,
+                          scene_scale, H, W, views_per_scene, color_mode, sh_degree, feature_mode,
+                          feature_sh_degree, sort_smem_keys, capacity)
+        images = call.forward()
+        ctx.call = call
         ctx.has_means2D = means2D is not None
-        ctx.save_for_backward(means3D_c, cov3D_c, opacity_c, color_c, feature_c, viewmatrix, projmatrix, campos,
-                              tanfov, bg, scene_scale)
         if debug is not None:
-            debug.state = buf
-            debug.num_rendered = num_rendered
-        radii = buf.radii
+            debug.state = call.buf
+            debug.num_rendered = call.num_rendered
+            debug.stats = call.buf.stats
+        radii = call.buf.radii
         ctx.mark_non_differentiable(radii)
         return images["color"], images["feature"], images["alpha"], images["depth"], radii
 
     @staticmethod
     def backward(ctx, g_color, g_feature, g_alpha, g_depth, _g_radii):
-        lib = _capi.load()
-        (means3D, cov3D, opacity, color, feature, viewmatrix, projmatrix, campos, tanfov, bg,
-         scene_scale) = ctx.saved_tensors
-        H, W, vps, color_mode, sh_degree, feature_mode, fdeg, Cf, V, S, G = ctx.cfg
-        buf: _Buffers = ctx.buf
-        device = means3D.device
+        call: RasterCall = ctx.call
         gc = lambda t: None if t is None else t.to(torch.float32).contiguous()
-        g_color, g_feature, g_alpha, g_depth = gc(g_color), gc(g_feature), gc(g_alpha), gc(g_depth)
-        with torch.cuda.device(device):
-            stream = torch.cuda.current_stream().cuda_stream
-            scene = _make_scene(V, vps, G, H, W, Cf, color_mode, sh_degree, feature_mode, fdeg, means3D, cov3D,
-                                opacity, color, feature, viewmatrix, projmatrix, campos, tanfov, bg, scene_scale)
-            gs = buf.sizes.grad_stride
-            record = torch.empty((V, G, gs), device=device)
-            d_means3D = torch.empty_like(means3D)
-            d_cov3D = torch.empty_like(cov3D)
-            d_opacity = torch.empty_like(opacity)
-            d_color = torch.empty_like(color) if color is not None else None
-            d_feature = torch.empty_like(feature) if feature is not None else None
-            d_means2D = torch.empty((V, G, 3), device=device) if ctx.has_means2D else None
-            grads = _capi.LsRasterGrads(_ptr(g_color), _ptr(g_feature), _ptr(g_alpha), _ptr(g_depth), _ptr(record),
-                                        gs, 0, _ptr(d_means3D), _ptr(d_cov3D), _ptr(d_opacity), _ptr(d_color),
-                                        _ptr(d_feature), _ptr(d_means2D))
-            st = buf.as_struct()
-            _capi.check(lib.ls_raster_backward(C.byref(scene), C.byref(st), C.byref(grads), stream),
-                        "ls_raster_backward")
-        return (d_means3D, d_cov3D, d_opacity, d_color, d_feature, d_means2D) + (None,) * 15
+        o = call.alloc_grads(ctx.has_means2D)
+        call.backward_stage(_capi.BWD_ALL, gc(g_color), gc(g_feature), gc(g_alpha), gc(g_depth))
+        return (o["means3D"], o["cov3D"], o["opacity"], o["color"], o["feature"], o["means2D"]) + (None,) * 16
 
 
-def rasterize_views(means3D: Tensor, cov3D: Tensor, opacities: Tensor, *, viewmatrix: Tensor, projmatrix: Tensor,
-                    campos: Tensor, tanfov: Tensor, image_height: int, image_width: int,
-                    bg: Optional[Tensor] = None, shs: Optional[Tensor] = None,
-                    colors_precomp: Optional[Tensor] = None, features: Optional[Tensor] = None,
-                    feature_shs: Optional[Tensor] = None, sh_degree: int = 0, scene_scale: Optional[Tensor] = None,
-                    means2D: Optional[Tensor] = None, sort_smem_keys: int = 0, debug: Optional[RasterDebug] = None):
-    """Render V = S * views_per_scene views in one launch sequence.
-
-    means3D (S,G,3), cov3D (S,G,6), opacities (S,G); colour: `shs` (S,G,n,3) or
-    `colors_precomp` (S,G,3) or neither; features: `features` (S,G,C) pre-evaluated or
-    `feature_shs` (S,G,C,nf) evaluated in-kernel as 0.5+eval_sh (cuda_splatting.py:94-101).
-    Cameras (V,...): viewmatrix/projmatrix (V,4,4) transposed as in cuda_splatting.py:115-118,
-    campos (V,3), tanfov (V,2), bg (V,3), scene_scale (V,) or None.
-    Returns (color|None (V,3,H,W), feature|None (V,C,H,W), alpha (V,H,W), depth (V,H,W), radii (V,G)).
-    """
+def _normalize(means3D, cov3D, opacities, *, viewmatrix, projmatrix, campos, tanfov, image_height, image_width,
+               bg=None, shs=None, colors_precomp=None, features=None, feature_shs=None, sh_degree=0,
+               scene_scale=None, sort_smem_keys=0, capacity=None):
+    """Argument checking shared by rasterize_views and prepare_call; returns RasterCall's positional args."""
     if shs is not None and colors_precomp is not None:
         raise ValueError("Please provide only one of either SHs or precomputed colors!")
     if features is not None and feature_shs is not None:
         raise ValueError("Provide either pre-evaluated features or feature SH coefficients, not both")
     V = viewmatrix.shape[0]
     S = means3D.shape[0]
-    if V % S:
+    if S == 0 or V % S:
         raise ValueError(f"{V} views cannot be split over {S} scenes")
     if shs is not None:
         color, color_mode = shs, _capi.COLOR_SH
@@ -219,10 +243,41 @@ def rasterize_views(means3D: Tensor, cov3D: Tensor, opacities: Tensor, *, viewma
         raise ValueError("nothing to render: provide colours and/or features (cuda_splatting.py:71)")
     if bg is None:
         bg = torch.zeros((V, 3), device=means3D.device)
-    return _Rasterize.apply(means3D, cov3D, opacities, color, feature, means2D, viewmatrix.reshape(V, 16),
-                            projmatrix.reshape(V, 16), campos, tanfov, bg, scene_scale, int(image_height),
-                            int(image_width), V // S, color_mode, int(sh_degree), feature_mode, fdeg,
-                            int(sort_smem_keys), debug)
+    return (means3D, cov3D, opacities, color, feature, viewmatrix.reshape(V, 16), projmatrix.reshape(V, 16), campos,
+            tanfov, bg, scene_scale, int(image_height), int(image_width), V // S, color_mode, int(sh_degree),
+            feature_mode, fdeg, int(sort_smem_keys), None if capacity is None else int(capacity))
+
+
+def prepare_call(*args, **kwargs) -> RasterCall:
+    """Same arguments as rasterize_views (minus means2D/debug); returns an un-launched RasterCall so that a
+    profiler can run and time the stages one by one (no autograd)."""
+    return RasterCall(*_normalize(*args, **kwargs))
+
+
+def rasterize_views(means3D: Tensor, cov3D: Tensor, opacities: Tensor, *, viewmatrix: Tensor, projmatrix: Tensor,
+                    campos: Tensor, tanfov: Tensor, image_height: int, image_width: int,
+                    bg: Optional[Tensor] = None, shs: Optional[Tensor] = None,
+                    colors_precomp: Optional[Tensor] = None, features: Optional[Tensor] = None,
+                    feature_shs: Optional[Tensor] = None, sh_degree: int = 0, scene_scale: Optional[Tensor] = None,
+                    means2D: Optional[Tensor] = None, sort_smem_keys: int = 0, capacity: Optional[int] = None,
+                    debug: Optional[RasterDebug] = None):
+    """Render V = S * views_per_scene views in one launch sequence.
+
+    means3D (S,G,3), cov3D (S,G,6), opacities (S,G); colour: `shs` (S,G,n,3) or
+    `colors_precomp` (S,G,3) or neither; features: `features` (S,G,C) pre-evaluated or
+    `feature_shs` (S,G,C,nf) evaluated in-kernel as 0.5+eval_sh (cuda_splatting.py:94-101).
+    Cameras (V,...): viewmatrix/projmatrix (V,4,4) transposed as in cuda_splatting.py:115-118,
+    campos (V,3), tanfov (V,2), bg (V,3), scene_scale (V,) or None.
+    `capacity`: None = exact sizing of the key lists (one 4-byte host sync per call); an int = sync-free
+    mode with that many (tile, Gaussian) slots -- `debug.stats[2]` is 1 if the scene needed more (the excess
+    entries of the affected tiles are dropped), `debug.stats[0]` is the number it needed.
+    Returns (color|None (V,3,H,W), feature|None (V,C,H,W), alpha (V,H,W), depth (V,H,W), radii (V,G)).
+    """
+    a = _normalize(means3D, cov3D, opacities, viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos,
+                   tanfov=tanfov, image_height=image_height, image_width=image_width, bg=bg, shs=shs,
+                   colors_precomp=colors_precomp, features=features, feature_shs=feature_shs, sh_degree=sh_degree,
+                   scene_scale=scene_scale, sort_smem_keys=sort_smem_keys, capacity=capacity)
+    return _Rasterize.apply(*a[:5], means2D, *a[5:], debug)
 
 
 # ------------------------------------------------------------------------------------------

@@ -55,7 +55,8 @@ def _structs(prec: str):
                     ("num_rendered", C.c_int64), ("keys_sorted", P(C.c_uint64)), ("point_list", P(C.c_uint32)),
                     ("ranges", P(C.c_uint32)), ("out_color", P(creal)), ("out_feature", P(creal)),
                     ("out_alpha", P(creal)), ("out_depth", P(creal)), ("final_T", P(creal)),
-                    ("n_contrib", P(C.c_uint32)), ("flip_bound", P(creal)), ("margin_eps", creal)]
+                    ("n_contrib", P(C.c_uint32)), ("flip_bound", P(creal)), ("margin_eps", creal),
+                    ("marginal", P(C.c_uint8))]
 
     class Grad(C.Structure):
         _fields_ = [("dL_dcolor", P(creal)), ("dL_dfeature", P(creal)), ("dL_dalpha", P(creal)),
@@ -107,7 +108,8 @@ def forward(*, means3D, cov3D, opacity, viewmatrix, projmatrix, campos, tanfovx,
              out_feature=np.zeros((Cf, H, W), npreal) if Cf else None,
              out_alpha=np.zeros((H, W), npreal), out_depth=np.zeros((H, W), npreal),
              final_T=np.zeros((H, W), npreal), n_contrib=np.zeros((H, W), np.uint32),
-             flip_bound=np.zeros((H, W), npreal) if margin_eps > 0 else None)
+             flip_bound=np.zeros((H, W), npreal) if margin_eps > 0 else None,
+             marginal=np.zeros(G, np.uint8) if margin_eps > 0 else None)
     i = In(G, H, W, Cf, int(sh_degree), _ptr(means3D, creal), _ptr(cov3D, creal), _ptr(opacity, creal),
            _ptr(shs, creal), _ptr(colors_precomp, creal), _ptr(features, creal), _ptr(viewmatrix, creal),
            _ptr(projmatrix, creal), _ptr(campos, creal), float(tanfovx), float(tanfovy), _ptr(bg, creal),
@@ -118,6 +120,7 @@ def forward(*, means3D, cov3D, opacity, viewmatrix, projmatrix, campos, tanfovx,
         setattr(o, k, _ptr(a[k], creal))
     o.radii, o.tiles_touched = _ptr(a["radii"], C.c_int32), _ptr(a["tiles_touched"], C.c_uint32)
     o.clamped, o.n_contrib = _ptr(a["clamped"], C.c_uint8), _ptr(a["n_contrib"], C.c_uint32)
+    o.marginal = _ptr(a["marginal"], C.c_uint8)
     o.margin_eps = float(margin_eps)
     fn = getattr(lib, f"oracle_forward_{prec}")
     fn.restype = C.c_int

@@ -237,6 +237,8 @@ typedef struct {
        ulps may flip exactly those terms.                                          */
     real *flip_bound;         /* (H,W) or NULL                                      */
     real margin_eps;
+    uint8_t *marginal;        /* (G) or NULL: 1 where a marginal decision concerned
+                                 this Gaussian at some pixel                        */
 } OracleOut;
 
 static inline void xform4x3(const real *m, const real *p, real *o) {
@@ -438,14 +440,22 @@ int FN(oracle_forward)(const OracleIn *in, OracleOut *out, int n_threads) {
                         const real *co = out->conic_opacity + 4 * g;
                         const real power = R(-0.5) * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
                         const real w_full = fmin(R(0.99), co[3] * EXP(fmin(power, R(0.0)))) * T;
-                        if (out->flip_bound && fabs(power) <= eps && w_full > fb) fb = w_full;
+                        if (out->flip_bound && fabs(power) <= eps) {
+                            if (w_full > fb) fb = w_full;
+                            if (out->marginal) out->marginal[g] = 1;
+                        }
                         if (power > R(0.0)) continue;
                         const real alpha = fmin(R(0.99), co[3] * EXP(power));
-                        if (out->flip_bound && fabs(alpha - R(1.0) / R(255.0)) <= eps * (R(1.0) / R(255.0)) &&
-                            alpha * T > fb) fb = alpha * T;
+                        if (out->flip_bound && fabs(alpha - R(1.0) / R(255.0)) <= eps * (R(1.0) / R(255.0))) {
+                            if (alpha * T > fb) fb = alpha * T;
+                            if (out->marginal) out->marginal[g] = 1;
+                        }
                         if (alpha < R(1.0) / R(255.0)) continue;
                         const real test_T = T * (R(1.0) - alpha);
-                        if (out->flip_bound && fabs(test_T - R(0.0001)) <= eps * R(0.0001) && T > fb) fb = T;
+                        if (out->flip_bound && fabs(test_T - R(0.0001)) <= eps * R(0.0001)) {
+                            if (T > fb) fb = T;
+                            if (out->marginal) out->marginal[g] = 1;
+                        }
                         if (test_T < R(0.0001)) break; /* [EXT] done = true */
                         const real w = alpha * T;
                         if (has_color) for (int c = 0; c < 3; ++c) acc_c[c] += out->rgb[3 * g + c] * w;

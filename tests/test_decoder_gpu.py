@@ -97,3 +97,46 @@ def test_decoder_backward_runs_and_matches_unbatched(cuda):
         rms = np.sqrt((bb ** 2).mean())
         assert np.abs(a - bb).max() <= 1e-4 * (np.abs(bb).max() + rms), k
         assert np.isfinite(a).all()
+
+
+def test_sync_free_capacity_mode_and_cuda_graph_step(cuda):
+    """capacity mode == exact mode bit for bit; overflow is flagged; forward+backward replays from one CUDA graph."""
+    from latentsplat_b200.model.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg
+    from latentsplat_b200.model.types import Gaussians
+    from latentsplat_b200.runtime import GraphedStep
+    cfg, x = _inputs(cuda)
+    dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda"), [0.2, 0.4, 0.6]).to(cuda)
+    keys = ("means", "covariances", "opacities", "color_harmonics", "feature_harmonics")
+
+    def fn(inp):
+        lv = {k: inp[k].detach().requires_grad_(True) for k in keys}
+        g = Gaussians(*[lv[k] for k in keys])
+        o = dec(g, inp["extrinsics"], inp["intrinsics"], inp["near"], inp["far"], (cfg["H"], cfg["W"]))
+        loss = (o.color ** 2).mean() + o.feature_posterior.mean.abs().mean() + o.depth.mean()
+        grads = torch.autograd.grad(loss, [lv[k] for k in keys])
+        return {"loss": loss, "color": o.color, **{f"d_{k}": g for k, g in zip(keys, grads)}}
+
+    exact = {k: v.clone() for k, v in fn(x).items()}
+    n = dec.last_raster.num_rendered
+    assert n > 0 and int(dec.last_raster.stats[0].item()) == n and int(dec.last_raster.stats[2].item()) == 0
+    cap = dec.calibrate_raster_capacity(1.25)
+    assert cap > n
+    sync_free = fn(x)
+    assert int(dec.last_raster.stats[2].item()) == 0
+    for k in exact:
+        assert torch.equal(exact[k], sync_free[k]) or k.startswith("d_"), k      # forward bit-identical
+        np.testing.assert_allclose(sync_free[k].cpu().numpy(), exact[k].cpu().numpy(), rtol=2e-4, atol=1e-7)
+    step = GraphedStep(fn, x)
+    out = step()
+    np.testing.assert_allclose(out["loss"].item(), exact["loss"].item(), rtol=1e-6)
+    assert torch.equal(out["color"], exact["color"])
+    # new inputs through the same graph
+    x2 = dict(x, opacities=x["opacities"] * 0.5)
+    out2 = {k: v.clone() for k, v in step({"opacities": x2["opacities"]}).items()}
+    dec.raster_capacity = None
+    ref2 = fn(x2)
+    assert torch.equal(out2["color"], ref2["color"])
+    # too small a capacity is flagged, not silently accepted
+    dec.raster_capacity = n // 2
+    fn(x)
+    assert int(dec.last_raster.stats[2].item()) == 1 and int(dec.last_raster.stats[0].item()) == n

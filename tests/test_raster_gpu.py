@@ -85,7 +85,7 @@ def _check_binning(r, dbg, V=0):
 
 
 def _check_images(out, r, has_color=True, C=4):
-    color, feat, alpha, depth, radii = out
+    color, feat, alpha, depth, radii = [None if o is None else o.detach() for o in out]
     fb = r.flip_bound
     if has_color:
         assert color is not None
@@ -216,15 +216,11 @@ def test_backward_matches_oracle(cuda, color, C, deg):
                             dL_dalpha=w["alpha"], dL_ddepth=w["depth"], n_threads=1)
     out, dbg, g = _run_gpu(d, cuda, grads=w)
     _check_binning(r, dbg)
-    # Gaussians touching a pixel whose keep/skip decision is marginal may legitimately differ: drop them.
-    marg = np.zeros(r.G, bool)
-    ys, xs = np.nonzero(r.flip_bound > 0)
-    gx = (d["W"] + 15) // 16
-    for y, x in zip(ys, xs):
-        s, e = r.ranges[(y // 16) * gx + x // 16]
-        marg[r.point_list[s:e]] = True
-    ok = ~marg
-    assert ok.mean() > 0.5
+    # A Gaussian whose own keep/skip decision was marginal at some pixel may legitimately gain or lose a whole
+    # blend term: drop it.  Its neighbours in that pixel move by <= 0.4% of one pixel's share, which the
+    # RMS-relative bound and the small outlier budget of _assert_grad absorb.
+    ok = r.marginal == 0
+    assert ok.mean() > 0.9
     _assert_grad(g["means3D"][ok], g_ref["dL_dmeans3D"][ok], "means3D")
     _assert_grad(g["cov3D"][ok], g_ref["dL_dcov3D"][ok], "cov3D")
     _assert_grad(g["opacities"][ok], g_ref["dL_dopacity"][ok], "opacity")
@@ -310,7 +306,7 @@ def test_fused_feature_sh_equals_torch_eval(cuda):
         + C2[3] * y * z * fsh[..., 7] + C2[4] * (z * z - x * x) * fsh[..., 8]
     o2 = rasterize_views(means, t(d["cov3D"])[None], t(d["opacity"])[None], features=0.5 + f, **cam)
     (o2[1] * wts).sum().backward()
-    assert helpers.rel_err(o1[1].cpu().numpy(), o2[1].detach().cpu().numpy()) < 1e-5
+    assert helpers.rel_err(o1[1].detach().cpu().numpy(), o2[1].detach().cpu().numpy()) < 1e-5
     _assert_grad(g1[1].cpu().numpy(), fsh.grad.cpu().numpy(), "feature_shs")
     _assert_grad(g1[0].cpu().numpy(), means.grad.cpu().numpy(), "means3D via feature direction")
 
