@@ -92,7 +92,8 @@ typedef struct LsRasterScene {
 
 /* State written by forward and read by backward. */
 typedef struct LsRasterState {
-    float*    geom;          /* (V,G,8): x, y, A, B | Cc, opacity, depth, 0  with
+    float*    geom;          /* (V,G,8): x, y, A, B | Cc, opacity, depth, ext  with ext = two fp16
+                                half-extents of the alpha >= 1/255 region (conservative), and
                                 (A,B,Cc) = (-0.5 cxx, -cxy, -0.5 cyy) * log2(e), the conic
                                 pre-scaled so that alpha = opacity * exp2(A dx^2 + B dx dy + Cc dy^2) */
     float*    chan;          /* (V,G,chan_stride): colour(0|3) then C features               */

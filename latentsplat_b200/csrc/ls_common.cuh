@@ -1,5 +1,6 @@
 // ls_common.cuh -- shared device helpers of the sm_100a rasterizer.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -155,6 +156,12 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
         db[23][0] = -6.f * c41 * xy * z; db[23][1] = c41 * z * (zz - 3.f * xx); db[23][2] = 3.f * c41 * y * (zz - xx);
         db[24][0] = c48 * 4.f * x * (xx - 3.f * zz); db[24][1] = 0.f; db[24][2] = c48 * 4.f * z * (zz - 3.f * xx);
     }
+}
+
+// geometry record slot 7: two fp16 half-extents (x, y) of the alpha >= 1/255 region, rounded up
+__device__ __forceinline__ float2 unpack_extent(float packed) {
+    const uint32_t u = __float_as_uint(packed);
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
 // ---- small PTX wrappers ------------------------------------------------------------------

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
         cp_async_commit();
     };
 
+    const float wx = (float)(tx * kTile) + 7.5f;                       // centre of the warp's 16x2 strip
+    const float wy = (float)(ty * kTile + 2 * (tid >> 5)) + 0.5f;
     float T = T_final;
     float A = 0.f, last_alpha = 0.f, last_cg = 0.f;
     const float half_w = 0.5f * (float)sc.W, half_h = 0.5f * (float)sc.H;
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
             const uint32_t pos = (uint32_t)(b * kTilePixels + j);
             const float4 g0 = sg[j][0];
             const float4 g1 = sg[j][1];
+            const float2 ext = unpack_extent(g1.w);
+            if (fabsf(g0.y - wy) > ext.y + 0.5f || fabsf(g0.x - wx) > ext.x + 7.5f) continue;  // warp-uniform
             const float dx = g0.x - fxp, dy = g0.y - fyp;
             const float p2 = fmaf(g0.z * dx, dx, fmaf(g1.x * dy, dy, g0.w * dx * dy));
             const float Gv = ex2_approx(p2);
@@ -167,21 +171,33 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
                 val[5] = Gv * dL_dalpha;
                 val[6] = wgt * g_d;
             }
-            // warp reduction, then one vector red into the 64 B gradient record
+            // Warp reduction of K values in ~K shuffles instead of 5K: a transposing butterfly.  At each step
+            // a lane keeps one half of its values and ships the other half to its partner, so the value
+            // count halves while the lane distance halves; after 4 steps lane L holds the partial sum of
+            // value L>>1 over its 16-lane group, a last xor-1 add completes it.  Even lanes then issue ONE
+            // red.global.add over the packed gradient record (<= 64 B, one L2 line).
+            constexpr int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+            float w_[KP];
 #pragma unroll
-            for (int q = 0; q < K; ++q) {
-                float x = val[q];
-                x += __shfl_xor_sync(0xffffffffu, x, 16);
-                x += __shfl_xor_sync(0xffffffffu, x, 8);
-                x += __shfl_xor_sync(0xffffffffu, x, 4);
-                x += __shfl_xor_sync(0xffffffffu, x, 2);
-                x += __shfl_xor_sync(0xffffffffu, x, 1);
-                val[q] = x;
+            for (int q = 0; q < KP; ++q) w_[q] = q < K ? val[q] : 0.f;
+#pragma unroll
+            for (int half = KP / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int q = 0; q < half; ++q) {
+                    const float send = up ? w_[q] : w_[q + half];
+                    const float keep = up ? w_[q + half] : w_[q];
+                    w_[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
             }
-            float mine = val[0];
-#pragma unroll
-            for (int q = 1; q < K; ++q) mine = (lane == q) ? val[q] : mine;
-            if (lane < K) atomicAdd(rec + (size_t)s_id[buf][j] * gr.grad_stride + lane, mine);
+            // remaining lane bits that were not consumed by the halving (KP = 16 -> bit 0; KP = 8 -> bits 1,0)
+            float tot = w_[0];
+            if (KP <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            if (KP <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            constexpr int kShift = KP == 32 ? 0 : (KP == 16 ? 1 : 2);
+            const int vidx = lane >> kShift;
+            if ((lane & ((1 << kShift) - 1)) == 0 && vidx < K)
+                atomicAdd(rec + (size_t)s_id[buf][j] * gr.grad_stride + vidx, tot);
         }
         __syncthreads();
     }

@@ -124,8 +124,21 @@ __global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, cons
     }
 
     // ---- geometry record ------------------------------------------------------------------
+    // Conservative half-extents (pixels) of the region where alpha can reach 1/255:
+    //   o * exp(-q) >= 1/255  <=>  q <= tau = ln(255 o),  and  min_dx q(dx,dy) = dy^2 / (2 Sigma_yy)
+    // so |dy| <= sqrt(2 tau Sigma_yy), |dx| <= sqrt(2 tau Sigma_xx) with Sigma = cov2D (a, b, c).  The blend
+    // kernels use them for a warp-uniform reject before touching the per-pixel math; +0.2 % and fp16
+    // round-up keep the test strictly conservative w.r.t. the fp32 evaluation.  tau < 0: never visible.
+    const float opac = sc.opacity[si];
+    const float tau = logf(255.0f * opac);
+    float ex = -1.0f, ey = -1.0f;
+    if (tau >= 0.0f) {
+        ex = sqrtf(2.0f * tau * q.a) * 1.002f + 0.01f;
+        ey = sqrtf(2.0f * tau * q.c) * 1.002f + 0.01f;
+    }
+    const __half2 ext = __halves2half2(__float2half_ru(ex), __float2half_ru(ey));
     grec[0] = make_float4(px, py, -0.5f * kLog2e * cxx, -kLog2e * cxy);
-    grec[1] = make_float4(-0.5f * kLog2e * cyy, sc.opacity[si], zv, 0.f);
+    grec[1] = make_float4(-0.5f * kLog2e * cyy, opac, zv, __uint_as_float(*reinterpret_cast<const uint32_t*>(&ext)));
     st.radii[vi] = radius;
     st.tiles_touched[vi] = (uint32_t)ntiles;
 
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
         off[n] = s_carry;
         stats[0] = s_carry;
         stats[1] = s_max;
-        stats[2] = ((long long)s_carry > capacity) ? 1u : 0u;
+        stats[2] = (capacity >= 0 && (long long)s_carry > capacity) ? 1u : 0u;
         stats[3] = 0u;
     }
 }
@@ -360,6 +373,8 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
         cp_async_commit();
     };
 
+    const float wx = (float)(tx * kTile) + 7.5f;                       // centre of the warp's 16x2 strip
+    const float wy = (float)(ty * kTile + 2 * (tid >> 5)) + 0.5f;
     float T = 1.0f;
     float acc[NC];
 #pragma unroll
@@ -378,6 +393,8 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
         for (int j = 0; j < cnt; ++j) {
             const float4 g0 = sg[j][0];
             const float4 g1 = sg[j][1];
+            const float2 ext = unpack_extent(g1.w);
+            if (fabsf(g0.y - wy) > ext.y + 0.5f || fabsf(g0.x - wx) > ext.x + 7.5f) continue;  // warp-uniform
             const float dx = g0.x - fxp, dy = g0.y - fyp;
             const float p2 = fmaf(g0.z * dx, dx, fmaf(g1.x * dy, dy, g0.w * dx * dy));  // log2 domain, <= 0
             const float alpha = fminf(kAlphaMax, g1.y * ex2_approx(p2));
@@ -521,7 +538,9 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
             dim3 grid((sc->G + 255) / 256, sc->n_views);
             k_preprocess<<<grid, 256, 0, stream>>>(*sc, *st);
         }
-        k_scan_tiles<<<1, 1024, 0, stream>>>(st->tile_count, st->tile_offsets, st->stats, n_slots, (long long)st->capacity);
+        // geometry launched on its own = exact sizing: the caller reads stats[0] and allocates, nothing can overflow
+        const long long cap_check = (stages & LS_STAGE_RENDER) ? (long long)st->capacity : -1LL;
+        k_scan_tiles<<<1, 1024, 0, stream>>>(st->tile_count, st->tile_offsets, st->stats, n_slots, cap_check);
         if (ls_check_cuda("geometry stage")) return -1;
     }
     if ((stages & LS_STAGE_RENDER) && st->capacity > 0 && (!st->keys || !st->keys_tmp))

@@ -114,7 +114,7 @@ def test_sync_free_capacity_mode_and_cuda_graph_step(cuda):
         o = dec(g, inp["extrinsics"], inp["intrinsics"], inp["near"], inp["far"], (cfg["H"], cfg["W"]))
         loss = (o.color ** 2).mean() + o.feature_posterior.mean.abs().mean() + o.depth.mean()
         grads = torch.autograd.grad(loss, [lv[k] for k in keys])
-        return {"loss": loss, "color": o.color, **{f"d_{k}": g for k, g in zip(keys, grads)}}
+        return {"loss": loss.detach(), "color": o.color.detach(), **{f"d_{k}": g for k, g in zip(keys, grads)}}
 
     exact = {k: v.clone() for k, v in fn(x).items()}
     n = dec.last_raster.num_rendered
