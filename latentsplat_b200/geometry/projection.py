@@ -1,0 +1,110 @@
+"""Projection helpers with the semantics of /root/reference/src/geometry/projection.py.
+
+Differences that matter on a GPU: `intersect_rays` is a closed-form 3x3 solve with `torch.where` for the
+parallel case instead of boolean-mask gathers + batched `linalg.lstsq` (projection.py:176-230: ~1 M tiny
+systems through cuSOLVER and two host syncs per call in the reference).
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+
+def homogenize_points(points: Tensor) -> Tensor:
+    """(…, d) -> (…, d+1) with a trailing 1 (projection.py:9-13)."""
+    return torch.cat([points, torch.ones_like(points[..., :1])], dim=-1)
+
+
+def homogenize_vectors(vectors: Tensor) -> Tensor:
+    """(…, d) -> (…, d+1) with a trailing 0 (projection.py:16-20)."""
+    return torch.cat([vectors, torch.zeros_like(vectors[..., :1])], dim=-1)
+
+
+def transform_rigid(homogeneous_coordinates: Tensor, transformation: Tensor) -> Tensor:
+    return torch.einsum("...ij,...j->...i", transformation, homogeneous_coordinates)
+
+
+def transform_cam2world(homogeneous_coordinates: Tensor, extrinsics: Tensor) -> Tensor:
+    return transform_rigid(homogeneous_coordinates, extrinsics)
+
+
+def transform_world2cam(homogeneous_coordinates: Tensor, extrinsics: Tensor) -> Tensor:
+    return transform_rigid(homogeneous_coordinates, torch.linalg.inv_ex(extrinsics, check_errors=False).inverse)
+
+
+def project_camera_space(points: Tensor, intrinsics: Tensor, epsilon: float = torch.finfo(torch.float32).eps,
+                         infinity: float = 1e8) -> Tensor:
+    """Pinhole projection of camera-space points to normalised image coordinates (projection.py:50-59)."""
+    points = points / (points[..., -1:] + epsilon)
+    points = points.nan_to_num(posinf=infinity, neginf=-infinity)
+    points = torch.einsum("...ij,...j->...i", intrinsics, points)
+    return points[..., :-1]
+
+
+def project(points: Tensor, extrinsics: Tensor, intrinsics: Tensor,
+            epsilon: float = torch.finfo(torch.float32).eps):
+    points = transform_world2cam(homogenize_points(points), extrinsics)[..., :-1]
+    return project_camera_space(points, intrinsics, epsilon=epsilon), points[..., -1] >= 0
+
+
+def unproject(coordinates: Tensor, z: Tensor, intrinsics: Tensor) -> Tensor:
+    """Normalised image coordinates + depth -> camera-space points (projection.py:79-95)."""
+    inv = torch.linalg.inv_ex(intrinsics, check_errors=False).inverse
+    rays = torch.einsum("...ij,...j->...i", inv, homogenize_points(coordinates))
+    return rays * z[..., None]
+
+
+def get_world_rays(coordinates: Tensor, extrinsics: Tensor, intrinsics: Tensor):
+    """Unit world-space ray directions through normalised image coordinates, and their origins
+    (projection.py:98-121)."""
+    directions = unproject(coordinates, torch.ones_like(coordinates[..., 0]), intrinsics)
+    directions = directions / directions.norm(dim=-1, keepdim=True)
+    directions = transform_cam2world(homogenize_vectors(directions), extrinsics)[..., :-1]
+    origins = extrinsics[..., :-1, -1].broadcast_to(directions.shape)
+    return origins, directions
+
+
+def sample_image_grid(shape: tuple[int, ...], device=torch.device("cpu")):
+    """Pixel-centre coordinates in (0,1), xy order, plus integer ij indices (projection.py:124-142)."""
+    indices = [torch.arange(length, device=device) for length in shape]
+    stacked_indices = torch.stack(torch.meshgrid(*indices, indexing="ij"), dim=-1)
+    coordinates = [(idx + 0.5) / length for idx, length in zip(indices, shape)]
+    coordinates = torch.stack(torch.meshgrid(*reversed(coordinates), indexing="xy"), dim=-1)
+    return coordinates, stacked_indices
+
+
+def _solve3_sym(a: Tensor, b: Tensor) -> Tensor:
+    """x with a x = b for batched symmetric 3x3 `a` (…,3,3) and b (…,3), by the adjugate."""
+    a00, a01, a02 = a[..., 0, 0], a[..., 0, 1], a[..., 0, 2]
+    a11, a12, a22 = a[..., 1, 1], a[..., 1, 2], a[..., 2, 2]
+    c00 = a11 * a22 - a12 * a12
+    c01 = a02 * a12 - a01 * a22
+    c02 = a01 * a12 - a02 * a11
+    c11 = a00 * a22 - a02 * a02
+    c12 = a01 * a02 - a00 * a12
+    c22 = a00 * a11 - a01 * a01
+    det = a00 * c00 + a01 * c01 + a02 * c02
+    b0, b1, b2 = b[..., 0], b[..., 1], b[..., 2]
+    x = torch.stack((c00 * b0 + c01 * b1 + c02 * b2, c01 * b0 + c11 * b1 + c12 * b2,
+                     c02 * b0 + c12 * b1 + c22 * b2), dim=-1)
+    return x / det[..., None]
+
+
+def intersect_rays(origins_x: Tensor, directions_x: Tensor, origins_y: Tensor, directions_y: Tensor,
+                   eps: float = 1e-5, inf: float = 1e10) -> Tensor:
+    """Least-squares intersection of two rays (projection.py:176-230): the point minimising the squared
+    distance to both lines, sum_r (d_r d_r^T - I) p = sum_r (d_r d_r^T - I) o_r; `inf` where the rays are
+    parallel (dot > 1 - eps)."""
+    shape = torch.broadcast_shapes(origins_x.shape, directions_x.shape, origins_y.shape, directions_y.shape)
+    ox, dx = origins_x.broadcast_to(shape), directions_x.broadcast_to(shape)
+    oy, dy = origins_y.broadcast_to(shape), directions_y.broadcast_to(shape)
+    parallel = (dx * dy).sum(dim=-1) > 1 - eps
+    eye = torch.eye(3, dtype=ox.dtype, device=ox.device)
+    nx = dx[..., :, None] * dx[..., None, :] - eye
+    ny = dy[..., :, None] * dy[..., None, :] - eye
+    lhs = nx + ny
+    rhs = torch.einsum("...ij,...j->...i", nx, ox) + torch.einsum("...ij,...j->...i", ny, oy)
+    # keep the solve finite on the parallel entries (their result is overwritten below)
+    lhs = torch.where(parallel[..., None, None], -eye, lhs)
+    result = _solve3_sym(lhs, rhs)
+    return torch.where(parallel[..., None], torch.full_like(result, inf), result)

@@ -1,0 +1,122 @@
+"""DINO ViT (facebookresearch/dino `vision_transformer.py`, `dino_vitb8` = patch 8, dim 768, depth 12, heads 12).
+
+The reference obtains this network with `torch.hub.load("facebookresearch/dino:main", cfg.model)`
+(backbone_dino.py:33: network access, un-pinned branch) -- not available here, so the public architecture is
+restated with the SAME parameter names (`cls_token`, `pos_embed`, `patch_embed.proj`, `blocks.N.norm1`,
+`blocks.N.attn.qkv`, `blocks.N.attn.proj`, `blocks.N.norm2`, `blocks.N.mlp.fc1/fc2`, `norm`) so that DINO / latentSplat
+checkpoints load.  PARITY UNPINNED against the hub model (cannot be downloaded here).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
+        return self.proj(x.transpose(1, 2).reshape(B, N, C))
+
+
+class Block(nn.Module):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, num_heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size: int, patch_size: int, in_chans: int, embed_dim: int):
+        super().__init__()
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
+CONFIGS = {"dino_vits16": (16, 384, 12, 6), "dino_vits8": (8, 384, 12, 6),
+           "dino_vitb16": (16, 768, 12, 12), "dino_vitb8": (8, 768, 12, 12)}
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, patch_size: int = 8, embed_dim: int = 768, depth: int = 12, num_heads: int = 12,
+                 img_size: int = 224, in_chans: int = 3):
+        super().__init__()
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + 1, embed_dim))
+        self.blocks = nn.ModuleList([Block(embed_dim, num_heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+
+    def interpolate_pos_encoding(self, x: Tensor, w: int, h: int) -> Tensor:
+        npatch = x.shape[1] - 1
+        N = self.pos_embed.shape[1] - 1
+        if npatch == N and w == h:
+            return self.pos_embed
+        class_pos, patch_pos = self.pos_embed[:, 0], self.pos_embed[:, 1:]
+        dim = x.shape[-1]
+        w0, h0 = w // self.patch_size + 0.1, h // self.patch_size + 0.1   # +0.1: upstream's guard against rounding
+        side = int(math.sqrt(N))
+        patch_pos = F.interpolate(patch_pos.reshape(1, side, side, dim).permute(0, 3, 1, 2),
+                                  scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+        assert int(w0) == patch_pos.shape[-2] and int(h0) == patch_pos.shape[-1]
+        patch_pos = patch_pos.permute(0, 2, 3, 1).view(1, -1, dim)
+        return torch.cat((class_pos.unsqueeze(0), patch_pos), dim=1)
+
+    def prepare_tokens(self, x: Tensor) -> Tensor:
+        B, _, w, h = x.shape
+        x = self.patch_embed(x)
+        x = torch.cat((self.cls_token.expand(B, -1, -1), x), dim=1)
+        return x + self.interpolate_pos_encoding(x, w, h)
+
+    def get_intermediate_layers(self, x: Tensor, n: int = 1) -> list[Tensor]:
+        """Normalised outputs of the last n blocks."""
+        x = self.prepare_tokens(x)
+        output = []
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            if len(self.blocks) - i <= n:
+                output.append(self.norm(x))
+        return output
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.get_intermediate_layers(x)[0][:, 0]
+
+
+def build_dino(model: str) -> VisionTransformer:
+    patch, dim, depth, heads = CONFIGS[model]
+    return VisionTransformer(patch, dim, depth, heads)

@@ -1,0 +1,102 @@
+"""Raw per-pixel network outputs -> world-space Gaussians
+(/root/reference/src/model/encoder/common/gaussian_adapter.py:13-139)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor, nn
+
+from ....geometry.projection import get_world_rays
+from ....misc.sh_utils import sh_rotation_matrices
+from .gaussians import build_covariance
+
+
+@dataclass
+class Gaussians:
+    means: Tensor             # (*batch, 3)
+    covariances: Tensor       # (*batch, 3, 3)
+    scales: Tensor            # (*batch, 3)
+    rotations: Tensor         # (*batch, 4)
+    color_harmonics: Tensor   # (*batch, 3, d_color_sh)
+    feature_harmonics: Tensor # (*batch, channels, d_feature_sh)
+    opacities: Tensor         # (*batch)
+
+
+@dataclass
+class GaussianAdapterCfg:
+    gaussian_scale_min: float
+    gaussian_scale_max: float
+    color_sh_degree: int
+    feature_sh_degree: int
+
+
+class GaussianAdapter(nn.Module):
+    def __init__(self, cfg: GaussianAdapterCfg, n_feature_channels: int):
+        super().__init__()
+        self.cfg = cfg
+        self.n_feature_channels = n_feature_channels
+        # DC coefficient 1, band l scaled by 0.1 * 0.25**l: large DC, small view-dependent part at init (:44-61)
+        for name, degree in (("color_sh_mask", cfg.color_sh_degree), ("feature_sh_mask", cfg.feature_sh_degree)):
+            mask = torch.ones(((degree + 1) ** 2,), dtype=torch.float32)
+            for l in range(1, degree + 1):
+                mask[l * l:(l + 1) ** 2] = 0.1 * 0.25 ** l
+            self.register_buffer(name, mask, persistent=False)
+
+    def forward(self, extrinsics: Tensor, intrinsics: Tensor, coordinates: Tensor, depths: Tensor, opacities: Tensor,
+                raw_gaussians: Tensor, image_shape: tuple[int, int], eps: float = 1e-8) -> Gaussians:
+        device = extrinsics.device
+        scales, rotations, color_sh, feature_sh = raw_gaussians.split(
+            (3, 4, 3 * self.d_color_sh, self.n_feature_channels * self.d_feature_sh), dim=-1)
+
+        scale_min, scale_max = self.cfg.gaussian_scale_min, self.cfg.gaussian_scale_max
+        scales = scale_min + (scale_max - scale_min) * scales.sigmoid()
+        h, w = image_shape
+        pixel_size = 1 / torch.tensor((w, h), dtype=torch.float32, device=device)
+        scales = scales * depths[..., None] * self.get_scale_multiplier(intrinsics, pixel_size)[..., None]
+
+        rotations = rotations / (rotations.norm(dim=-1, keepdim=True) + eps)
+
+        color_sh = color_sh.unflatten(-1, (3, self.d_color_sh))
+        feature_sh = feature_sh.unflatten(-1, (self.n_feature_channels, self.d_feature_sh))
+        color_sh = color_sh.broadcast_to((*opacities.shape, 3, self.d_color_sh)) * self.color_sh_mask
+        feature_sh = feature_sh.broadcast_to((*opacities.shape, self.n_feature_channels, self.d_feature_sh)) \
+            * self.feature_sh_mask
+
+        covariances = build_covariance(scales, rotations)
+        c2w_rotations = extrinsics[..., :3, :3]
+        covariances = c2w_rotations @ covariances @ c2w_rotations.transpose(-1, -2)
+
+        origins, directions = get_world_rays(coordinates, extrinsics, intrinsics)
+        means = origins + directions * depths[..., None]
+
+        return Gaussians(means=means, covariances=covariances,
+                         color_harmonics=self._rotate(color_sh, c2w_rotations, self.cfg.color_sh_degree),
+                         feature_harmonics=self._rotate(feature_sh, c2w_rotations, self.cfg.feature_sh_degree),
+                         opacities=opacities,
+                         scales=scales,                                             # camera space (ply export only)
+                         rotations=rotations.broadcast_to((*scales.shape[:-1], 4)))
+
+    @staticmethod
+    def _rotate(sh: Tensor, c2w_rotations: Tensor, degree: int) -> Tensor:
+        """rotate_sh(sh, c2w[..., None, :, :]) (:104-105): the rotation matrices are built once per distinct
+        camera (a few per batch) and applied per degree block."""
+        mats = sh_rotation_matrices(c2w_rotations[..., None, :, :], degree)
+        parts = [torch.einsum("...ij,...j->...i", mats[l], sh[..., l * l:(l + 1) ** 2]) for l in range(degree + 1)]
+        return torch.cat(parts, dim=-1)
+
+    def get_scale_multiplier(self, intrinsics: Tensor, pixel_size: Tensor, multiplier: float = 0.1) -> Tensor:
+        inv = torch.linalg.inv_ex(intrinsics[..., :2, :2], check_errors=False).inverse
+        return (multiplier * torch.einsum("...ij,j->...i", inv, pixel_size)).sum(dim=-1)
+
+    @property
+    def d_color_sh(self) -> int:
+        return (self.cfg.color_sh_degree + 1) ** 2
+
+    @property
+    def d_feature_sh(self) -> int:
+        return (self.cfg.feature_sh_degree + 1) ** 2
+
+    @property
+    def d_in(self) -> int:
+        return 7 + 3 * self.d_color_sh + self.n_feature_channels * self.d_feature_sh

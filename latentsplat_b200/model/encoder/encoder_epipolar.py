@@ -1,0 +1,160 @@
+"""Epipolar-sampling encoder: context images + cameras -> variational Gaussians.
+
+Same constructor, parameter tree, forward signature and outputs as
+/root/reference/src/model/encoder/encoder_epipolar.py:51-268.  Two data-flow changes, both exact:
+  * `backbone_projection` (ReLU + Linear d_backbone -> d_feature, :70-73, applied per pixel at :143-145) runs on
+    the un-repeated token grid and the result is repeated, instead of repeating 512 channels to full resolution
+    first (pointwise ops commute with nearest-neighbour replication; the global token is added before the
+    projection on the coarse grid, exactly as the reference adds it before its repeat is consumed);
+  * all geometry below is sync-free (see latentsplat_b200/geometry).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from fractions import Fraction
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from ...geometry.projection import sample_image_grid
+from ..diagonal_gaussian_distribution import DiagonalGaussianDistribution
+from ..types import VariationalGaussians
+from .backbone import Backbone, BackboneCfg, get_backbone
+from .backbone.backbone_dino import BackboneDino
+from .common.gaussian_adapter import GaussianAdapter, GaussianAdapterCfg
+from .encoder import Encoder
+from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
+from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
+from .shims import apply_bounds_shim, apply_patch_shim
+
+
+@dataclass
+class OpacityMappingCfg:
+    initial: float
+    final: float
+    warm_up: int
+
+
+@dataclass
+class EncoderEpipolarCfg:
+    name: Literal["epipolar"]
+    d_backbone: int
+    d_feature: int
+    num_monocular_samples: int
+    num_surfaces: int
+    predict_opacity: bool
+    backbone: BackboneCfg
+    near_disparity: float
+    gaussian_adapter: GaussianAdapterCfg
+    apply_bounds_shim: bool
+    epipolar_transformer: EpipolarTransformerCfg
+    opacity_mapping: OpacityMappingCfg
+    gaussians_per_pixel: int
+    use_epipolar_transformer: bool
+    use_transmittance: bool
+    visualizer: Optional[dict] = None        # EncoderVisualizerEpipolarCfg in the reference (out of scope)
+    num_context_views: int = 2               # get_cfg().dataset.view_sampler.num_context_views in the reference
+
+
+class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
+    def __init__(self, cfg: EncoderEpipolarCfg, d_in: int, n_feature_channels: int, scale_factor: Fraction,
+                 variational: bool) -> None:
+        super().__init__(cfg, variational)
+        self.backbone: Backbone = get_backbone(cfg.backbone, d_in, cfg.d_backbone, scale_factor)
+        self.backbone_projection = nn.Sequential(nn.ReLU(), nn.Linear(cfg.d_backbone, cfg.d_feature))
+        self.epipolar_transformer = EpipolarTransformer(cfg.epipolar_transformer, cfg.d_feature, cfg.num_context_views) \
+            if cfg.use_epipolar_transformer else None
+        self.depth_predictor = DepthPredictorMonocular(cfg.d_feature, cfg.num_monocular_samples, cfg.num_surfaces,
+                                                       cfg.use_transmittance)
+        # NOTE twice the feature channels when variational: mean and log-variance (:87-90)
+        self.gaussian_adapter = GaussianAdapter(cfg.gaussian_adapter,
+                                                2 * n_feature_channels if variational else n_feature_channels)
+        if cfg.predict_opacity:
+            self.to_opacity = nn.Sequential(nn.ReLU(), nn.Linear(cfg.d_feature, 1), nn.Sigmoid())
+        self.to_gaussians = nn.Sequential(nn.ReLU(), nn.Linear(cfg.d_feature,
+                                                               cfg.num_surfaces * (2 + self.gaussian_adapter.d_in)))
+        # the high-resolution skip only exists without downscaling (:104-111)
+        self.high_resolution_skip = nn.Sequential(nn.Conv2d(3, cfg.d_feature, 7, 1, 3), nn.ReLU()) \
+            if scale_factor == 1 else None
+
+    def map_pdf_to_opacity(self, pdf: Tensor, global_step: int) -> Tensor:
+        """https://www.desmos.com/calculator/opvwti3ba9 (:113-126)"""
+        cfg = self.cfg.opacity_mapping
+        x = cfg.initial + min(global_step / cfg.warm_up, 1) * (cfg.final - cfg.initial)
+        exponent = 2 ** x
+        return 0.5 * (1 - (1 - pdf) ** exponent + pdf ** (1 / exponent))
+
+    def _backbone_features(self, images: Tensor) -> Tensor:
+        """(bv, c, H, W) -> projected features (bv, d_feature, h, w) == backbone_projection(backbone(x))."""
+        if isinstance(self.backbone, BackboneDino) and self.backbone.cfg.upscale_mode == "repeat":
+            local, glob = self.backbone.forward_tokens(images)
+            x = self.backbone_projection((local + glob).permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+            n = self.backbone.n_repeats
+            return x.repeat_interleave(n, dim=2).repeat_interleave(n, dim=3)
+        x = self.backbone(images)
+        return self.backbone_projection(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+    def forward(self, context: dict, global_step: int, features: Optional[Tensor] = None,
+                deterministic: bool = False, visualization_dump: Optional[dict] = None) -> VariationalGaussians:
+        b, v = context["image"].shape[:2]
+        images = context["image"].flatten(0, 1)
+        features = self._backbone_features(images if features is None else features)
+        device = features.device
+        h, w = features.shape[-2:]
+        features = features.unflatten(0, (b, v))
+
+        sampling = None
+        if self.epipolar_transformer is not None:
+            features, sampling = self.epipolar_transformer(features, context["extrinsics"], context["intrinsics"],
+                                                           context["near"], context["far"])
+        if self.high_resolution_skip is not None:
+            features = features + self.high_resolution_skip(images).unflatten(0, (b, v))
+
+        features = features.flatten(3).transpose(2, 3)                     # b v c h w -> b v (h w) c
+        depths, densities = self.depth_predictor(features, context["near"], context["far"], deterministic,
+                                                 1 if deterministic else self.cfg.gaussians_per_pixel)
+
+        xy_ray, _ = sample_image_grid((h, w), device)
+        xy_ray = xy_ray.reshape(h * w, 1, 2)
+        gaussians = self.to_gaussians(features).unflatten(-1, (self.cfg.num_surfaces, -1))   # ... (srf c) -> ... srf c
+        offset_xy = gaussians[..., :2].sigmoid()
+        pixel_size = 1 / torch.tensor((w, h), dtype=torch.float32, device=device)
+        xy_ray = xy_ray + (offset_xy - 0.5) * pixel_size
+        gpp = self.cfg.gaussians_per_pixel
+        g = self.gaussian_adapter(context["extrinsics"][:, :, None, None, None], context["intrinsics"][:, :, None, None, None],
+                                  xy_ray[..., None, :], depths, self.map_pdf_to_opacity(densities, global_step) / gpp,
+                                  gaussians[..., None, 2:], (h, w))
+
+        if visualization_dump is not None:
+            visualization_dump["depth"] = depths.unflatten(2, (h, w))
+            visualization_dump["scales"] = g.scales.flatten(1, 4)
+            visualization_dump["rotations"] = g.rotations.flatten(1, 4)
+            if sampling is not None:
+                visualization_dump["sampling"] = sampling
+
+        opacity_multiplier = self.to_opacity(features)[..., None] if self.cfg.predict_opacity else 1   # b v r () ()
+        feature_harmonics = g.feature_harmonics.flatten(1, 4)              # b v r srf spp c d -> b (v r srf spp) c d
+        feature_harmonics = DiagonalGaussianDistribution(
+            **{"params" if self.variational else "mean": feature_harmonics}, dim=-2)
+        return VariationalGaussians(g.means.flatten(1, 4), g.covariances.flatten(1, 4),
+                                    (opacity_multiplier * g.opacities).flatten(1, 4),
+                                    g.color_harmonics.flatten(1, 4), feature_harmonics)
+
+    def get_data_shim(self):
+        def data_shim(batch: dict) -> dict:
+            et = self.cfg.epipolar_transformer
+            batch = apply_patch_shim(batch, patch_size=et.self_attention.patch_size * et.downscale)
+            if self.cfg.apply_bounds_shim:
+                _, _, _, h, w = batch["context"]["image"].shape
+                batch = apply_bounds_shim(batch, self.cfg.near_disparity * min(h, w), 0.5)
+            return batch
+        return data_shim
+
+    @property
+    def sampler(self):
+        return self.epipolar_transformer.epipolar_sampler
+
+    @property
+    def last_layer_weights(self) -> Tensor:
+        return self.to_gaussians[-1].weight

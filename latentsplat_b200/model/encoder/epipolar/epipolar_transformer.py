@@ -1,0 +1,101 @@
+"""Epipolar cross-attention transformer (/root/reference/src/model/encoder/epipolar/epipolar_transformer.py:18-183).
+
+Per ray of every context view: one query token (the pixel's feature), `num_samples` key/value tokens sampled
+along the epipolar line in the other view(s) with a positional encoding of their triangulated depth, then a
+convolutional feed-forward with image self-attention; optional 4x down/up-scaling around it.
+The reference reads `num_context_views` from a global hydra config (:47); here it is a constructor argument
+(default 2, the value of every shipped experiment).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import partial
+from typing import Optional
+
+from torch import Tensor, nn
+
+from ....geometry.epipolar_lines import get_depth
+from ...encodings.positional_encoding import PositionalEncoding
+from ...transformer.transformer import Transformer
+from .conversions import depth_to_relative_disparity
+from .epipolar_sampler import EpipolarSampler, EpipolarSampling
+from .image_self_attention import ImageSelfAttention, ImageSelfAttentionCfg
+
+
+@dataclass
+class EpipolarTransformerCfg:
+    self_attention: ImageSelfAttentionCfg
+    num_octaves: int
+    num_layers: int
+    num_heads: int
+    num_samples: int
+    d_dot: int
+    d_mlp: int
+    downscale: int
+
+
+class ConvFeedForward(nn.Module):
+    """layers(self_attention(x) + x) on the (b v, c, h, w) view of the token sequence (:155-183)."""
+
+    def __init__(self, self_attention_cfg: ImageSelfAttentionCfg, d_in: int, d_hidden: int, dropout: float) -> None:
+        super().__init__()
+        self.layers = nn.Sequential(nn.Conv2d(d_in, d_hidden, 7, 1, 3), nn.GELU(), nn.Dropout(dropout),
+                                    nn.Conv2d(d_hidden, d_in, 7, 1, 3), nn.Dropout(dropout))
+        self.self_attention = ImageSelfAttention(self_attention_cfg, d_in, d_in)
+
+    def forward(self, x: Tensor, b: int, v: int, h: int, w: int) -> Tensor:
+        c = x.shape[-1]
+        x = x.reshape(b * v, h, w, c).permute(0, 3, 1, 2)          # (b v h w) () c -> (b v) c h w
+        x = self.layers(self.self_attention(x) + x)
+        return x.permute(0, 2, 3, 1).reshape(b * v * h * w, 1, c)
+
+
+class EpipolarTransformer(nn.Module):
+    def __init__(self, cfg: EpipolarTransformerCfg, d_in: int, num_context_views: int = 2) -> None:
+        super().__init__()
+        self.cfg = cfg
+        self.epipolar_sampler = EpipolarSampler(num_context_views, cfg.num_samples)
+        if cfg.num_octaves > 0:
+            pe = PositionalEncoding(cfg.num_octaves)
+            self.depth_encoding = nn.Sequential(pe, nn.Linear(pe.d_out(1), d_in))
+        self.transformer = Transformer(d_in, cfg.num_layers, cfg.num_heads, cfg.d_dot, cfg.d_mlp, selfatt=False,
+                                       kv_dim=d_in, feed_forward_layer=partial(ConvFeedForward, cfg.self_attention))
+        if cfg.downscale > 1:
+            self.downscaler = nn.Conv2d(d_in, d_in, cfg.downscale, cfg.downscale)
+            self.upscaler = nn.ConvTranspose2d(d_in, d_in, cfg.downscale, cfg.downscale)
+            self.upscale_refinement = nn.Sequential(nn.Conv2d(d_in, d_in * 2, 7, 1, 3), nn.GELU(),
+                                                    nn.Conv2d(d_in * 2, d_in, 7, 1, 3))
+        else:
+            self.downscaler = self.upscaler = self.upscale_refinement = None
+
+    def forward(self, features: Tensor, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor):
+        b, v, c, h, w = features.shape
+        if self.downscaler is not None:
+            features = self.downscaler(features.flatten(0, 1)).unflatten(0, (b, v))
+        hd, wd = h // self.cfg.downscale, w // self.cfg.downscale
+
+        sampling: EpipolarSampling = self.epipolar_sampler(features, extrinsics, intrinsics, near, far)
+        if self.cfg.num_octaves > 0:
+            collect = self.epipolar_sampler.collect
+            depths = get_depth(sampling.origins[:, :, None, :, None], sampling.directions[:, :, None, :, None],
+                               sampling.xy_sample, collect(extrinsics)[:, :, :, None, None],
+                               collect(intrinsics)[:, :, :, None, None])
+            # clip: context views may be extremely close together or oriented the same way (:113-116)
+            depths = depths.maximum(near[..., None, None, None]).minimum(far[..., None, None, None])
+            depths = depth_to_relative_disparity(depths, near[..., None, None, None], far[..., None, None, None])
+            q = sampling.features + self.depth_encoding(depths[..., None])
+        else:
+            q = sampling.features
+
+        # NB the reference's names: `kv` are the per-pixel query tokens x, `q` the sampled key/value tokens z.
+        kv = features.permute(0, 1, 3, 4, 2).reshape(b * v * hd * wd, 1, c)
+        assert q.shape[2] == 1, "the reference's rearrange 'b v () r s c' admits exactly one other view"
+        z = q.reshape(b * v * hd * wd, -1, c)                     # b v () r s c -> (b v r) s c
+        features = self.transformer(kv, z, b=b, v=v, h=hd, w=wd)
+        features = features.reshape(b, v, hd, wd, c).permute(0, 1, 4, 2, 3)
+
+        if self.upscaler is not None:
+            x = self.upscaler(features.flatten(0, 1))
+            x = self.upscale_refinement(x) + x
+            features = x.unflatten(0, (b, v))
+        return features, sampling

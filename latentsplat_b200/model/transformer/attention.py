@@ -1,0 +1,36 @@
+"""Multi-head (self or cross) attention with the parameter tree of
+/root/reference/src/model/transformer/attention.py:30-70: `to_qkv` (self) or `to_q`/`to_kv` (cross), all
+without bias, `to_out` = Sequential(Linear(+bias), Dropout), an `attend` Softmax module (the reference's
+visualiser hooks it, encoder_visualizer_epipolar.py:55-58)."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.0, selfatt=True, kv_dim=None):
+        super().__init__()
+        inner_dim = dim_head * heads
+        project_out = not (heads == 1 and dim_head == dim)
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.attend = nn.Softmax(dim=-1)
+        if selfatt:
+            self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
+        else:
+            self.to_q = nn.Linear(dim, inner_dim, bias=False)
+            self.to_kv = nn.Linear(kv_dim, inner_dim * 2, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout)) if project_out else nn.Identity()
+
+    def forward(self, x, z=None):
+        if z is None:
+            q, k, v = self.to_qkv(x).chunk(3, dim=-1)
+        else:
+            q = self.to_q(x)
+            k, v = self.to_kv(z).chunk(2, dim=-1)
+        split = lambda t: t.unflatten(-1, (self.heads, -1)).transpose(1, 2)      # b n (h d) -> b h n d
+        q, k, v = split(q), split(k), split(v)
+        dots = torch.matmul(q, k.transpose(-1, -2)) * self.scale
+        out = torch.matmul(self.attend(dots), v)
+        return self.to_out(out.transpose(1, 2).flatten(-2))                      # b h n d -> b n (h d)

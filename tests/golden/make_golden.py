@@ -129,6 +129,95 @@ def scene_inputs(seed: int, G: int, b: int, v: int, C: int = 4, color_deg: int =
 RENDER_CFG = dict(seed=4321, G=1500, b=2, v=2, H=48, W=64)
 
 
+def encoder_cfgs():
+    """Small-but-complete configuration of the epipolar encoder (reference dims where the code hard-codes them)."""
+    sa = dict(patch_size=4, num_octaves=10, num_layers=2, num_heads=4, d_token=64, d_dot=32, d_mlp=128)
+    et = dict(num_octaves=10, num_layers=2, num_heads=4, num_samples=32, d_dot=32, d_mlp=128, downscale=4)
+    ga = dict(gaussian_scale_min=0.5, gaussian_scale_max=15.0, color_sh_degree=4, feature_sh_degree=2)
+    enc = dict(name="epipolar", d_backbone=96, d_feature=64, num_monocular_samples=32, num_surfaces=1,
+               predict_opacity=False, near_disparity=3.0, apply_bounds_shim=True, gaussians_per_pixel=3,
+               use_epipolar_transformer=True, use_transmittance=False)
+    return sa, et, ga, enc
+
+
+def encoder_context(b=1, v=2, hw=32, seed=5):
+    gen = torch.Generator().manual_seed(seed)
+    extr = torch.stack([synthetic.pose(0.0, 0.0), synthetic.pose(0.6, -6.0, 0.05, 0.02)])[None].repeat(b, 1, 1, 1)
+    intr = synthetic.intrinsics(0.9)[None, None].repeat(b, v, 1, 1).clone()
+    return dict(image=torch.rand(b, v, 3, hw, hw, generator=gen), extrinsics=extr, intrinsics=intr,
+                near=torch.full((b, v), 1.0), far=torch.full((b, v), 30.0))
+
+
+def encoder_goldens(out):
+    """Goldens of the encoder-side modules from the reference's own PyTorch code (CPU).
+    Stubbed third-party pieces (documented as UNPINNED in the modules): the DINO ViT (torch.hub, no network) is
+    OUR restatement plugged into the reference's BackboneDino; e3nn's rotate_sh is OUR rotate_sh."""
+    import helpers
+    from types import SimpleNamespace
+    import src.misc.sh_utils as ref_sh
+    from latentsplat_b200.misc import sh_utils as our_sh
+    from latentsplat_b200.model.encoder.backbone import dino_vit
+    ref_sh.rotate_sh = our_sh.rotate_sh
+    import src.model.encoder.common.gaussian_adapter as ref_ga
+    ref_ga.rotate_sh = our_sh.rotate_sh
+    torch.hub.load = lambda repo, model, *a, **k: dino_vit.build_dino(model)
+    from src.global_cfg import set_cfg
+    set_cfg(SimpleNamespace(dataset=SimpleNamespace(view_sampler=SimpleNamespace(num_context_views=2))))
+
+    from src.geometry.epipolar_lines import get_depth, project_rays
+    from src.model.encoder.backbone.backbone_dino import BackboneDinoCfg
+    from src.model.encoder.common.gaussian_adapter import GaussianAdapterCfg
+    from src.model.encoder.encoder_epipolar import EncoderEpipolar, EncoderEpipolarCfg, OpacityMappingCfg
+    from src.model.encoder.epipolar.epipolar_transformer import EpipolarTransformerCfg
+    from src.model.encoder.epipolar.image_self_attention import ImageSelfAttentionCfg
+    from src.model.discriminator.discriminator_patch_gan import DiscriminatorPatchGan, DiscriminatorPatchGanCfg
+    from fractions import Fraction
+
+    # ---- geometry: project_rays / get_depth incl. rays that miss the other image ------------------------
+    gen = torch.Generator().manual_seed(11)
+    n = 400
+    origins = torch.randn(n, 3, generator=gen) * 0.3
+    directions = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen) + torch.tensor([0.0, 0.0, 1.5]), dim=-1)
+    extr = synthetic.pose(0.7, -8.0, 0.1, -0.05)[None].expand(n, 4, 4)
+    intr = synthetic.intrinsics(0.8)[None].expand(n, 3, 3)
+    pr = project_rays(origins, directions, extr, intr, torch.full((n,), 0.5), torch.full((n,), 20.0))
+    pr2 = project_rays(origins, directions, extr, intr)
+    xy = torch.rand(n, 2, generator=gen)
+    dep = get_depth(origins, directions, xy, extr, intr)
+    np.savez(out / "epipolar_geometry.npz", **{f"nf_{k}": v.numpy() for k, v in pr.items()},
+             **{f"inf_{k}": v.numpy() for k, v in pr2.items()}, depth=dep.numpy())
+
+    # ---- full encoder -----------------------------------------------------------------------------------
+    sa, et, ga, enc = encoder_cfgs()
+    cfg = EncoderEpipolarCfg(**enc, backbone=BackboneDinoCfg("dino", "dino_vitb8"), visualizer=None,
+                             gaussian_adapter=GaussianAdapterCfg(**ga),
+                             epipolar_transformer=EpipolarTransformerCfg(self_attention=ImageSelfAttentionCfg(**sa), **et),
+                             opacity_mapping=OpacityMappingCfg(0.0, 0.0, 1))
+    model = EncoderEpipolar(cfg, 3, 4, Fraction(1), True).eval()
+    inventory = helpers.init_by_name(model, seed=3)
+    ctx = encoder_context()
+    with torch.no_grad():
+        det = model(ctx, 0, deterministic=True)
+        torch.manual_seed(123)
+        sto = model(ctx, 0, deterministic=False)
+    pack = lambda g, p: {f"{p}_means": g.means.numpy(), f"{p}_cov": g.covariances.numpy(), f"{p}_opac": g.opacities.numpy(),
+                         f"{p}_csh": g.color_harmonics.numpy(), f"{p}_fsh": g.feature_harmonics.params.numpy()}
+    sub = lambda d: {k: v[:, ::5] for k, v in d.items()}      # every 5th Gaussian keeps the fixture small
+    np.savez_compressed(out / "encoder.npz", **sub(pack(det, "det")), **sub(pack(sto, "sto")),
+                        det_sum=np.array([float(det.means.double().sum()), float(det.covariances.double().sum()),
+                                          float(det.color_harmonics.double().sum()),
+                                          float(det.feature_harmonics.params.double().sum())]),
+                        inventory=np.array([f"{n}:{'x'.join(map(str, s))}" for n, s in inventory]))
+
+    # ---- PatchGAN ----------------------------------------------------------------------------------------
+    disc = DiscriminatorPatchGan(DiscriminatorPatchGanCfg("patch_gan", "kl_f8", pretrained=False), 3).eval()
+    dinv = helpers.init_by_name(disc, seed=4)
+    x = torch.rand(2, 3, 64, 64, generator=gen)
+    with torch.no_grad():
+        y = disc(x)
+    np.savez(out / "patch_gan.npz", out=y.numpy(), inventory=np.array([f"{n}:{'x'.join(map(str, s))}" for n, s in dinv]))
+
+
 def main():
     install_reference()
     out = Path(__file__).resolve().parent
@@ -168,6 +257,7 @@ def main():
         o = dec.forward(g, x["extrinsics"], x["intrinsics"], x["near"], x["far"], (cfg["H"], cfg["W"]))
     np.savez_compressed(out / "render_cuda.npz", color=o.color.numpy(), feature_mean=o.feature_posterior.mean.numpy(),
                         feature_logvar=o.feature_posterior.logvar.numpy(), mask=o.mask.numpy(), depth=o.depth.numpy())
+    encoder_goldens(out)
     print("wrote", [p.name for p in out.glob("*.npz")])
 
 

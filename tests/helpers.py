@@ -61,3 +61,24 @@ def assert_close_with_flips(got, want, flip_bound, scale_vals, rtol=1e-4, atol=1
 def rel_err(got, want):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+def init_by_name(module, seed: int = 0):
+    """Deterministic, NAME-KEYED parameter values: two modules with the same parameter tree get identical
+    weights regardless of construction order (used to compare our modules with the reference's without
+    shipping weights).  Returns the sorted (name, shape) inventory."""
+    import zlib
+    inv = []
+    with torch.no_grad():
+        for name, p in sorted(module.named_parameters()):
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) % (2 ** 31))
+            if p.dim() > 1:
+                fan_in = p[0].numel()
+                v = torch.randn(p.shape, generator=g) / math.sqrt(fan_in)
+            elif "norm" in name.lower() and name.endswith("weight"):
+                v = 1 + 0.1 * torch.randn(p.shape, generator=g)
+            else:
+                v = 0.1 * torch.randn(p.shape, generator=g)
+            p.copy_(v.to(p.dtype))
+            inv.append((name, tuple(p.shape)))
+    return inv
