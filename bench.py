@@ -4,12 +4,17 @@
     python bench.py --gpus N --steps K --warmup W            # our sm_100a path
     python bench.py --impl reference --steps K --warmup W    # the CPU restatement (oracle) on host cores
 
-Workload (config.workload): RealEstate10k-shaped synthetic batch, B scenes per GPU, each scene = G
-feature Gaussians (colour SH deg 4 + C=4 feature SH deg 2), V_t target views of 256x256 per scene,
-rendered through DecoderSplattingCUDA.forward (one batched rasterizer call) with scalar loss heads
-(mse on colour + l1 on the feature mean + mean mask/depth), then backward to every Gaussian input.
-ROUND-1 SCOPE NOTE: the encoder and the VAE decoder of BASELINE.json configs[1] are not yet inside the
-timed step; `config.workload` says so.  One step = one such batch; value = views / s over all ranks.
+Workloads (`--workload`, named in config.workload):
+  full  (default) BASELINE.json configs[1]: RealEstate10k-shaped synthetic batch, B=4 scene pairs per GPU, 2
+        context views 256x256, full encoder (DINO ViT-B/8 + epipolar transformer) -> 393 216 variational Gaussians
+        per scene -> sample -> splat V_t target views -> latent sample -> 1/8 rescale -> VAE decoder with skip
+        injection; loss = 10 mse(colour) + l1(decoded image); backward to every weight; fused Adam step; for
+        N > 1 an NCCL all-reduce of the flat gradient buffer.  fp32 weights/activations (TF32 convolutions as in
+        the reference's torch defaults).  Encoder/VAE GEMMs and convolutions currently run through
+        cuDNN/cuBLAS (library calls); the rasterizer path is our sm_100a code.
+  splat the rasterizer path alone: B scenes x G=65 536 Gaussians (colour SH deg 4 + C=4 feature SH deg 2) through
+        DecoderSplattingCUDA fwd+bwd with scalar loss heads (the round-1 kernel workload; roofline stages).
+One step = one such batch; value = target views / s over all ranks.
 
 JSON line keys follow the driver contract (metric/value/unit/n_gpus/steps/warmup/ms_per_step/...), plus
 `roofline` (dominant kernel, live CUDA-event timing), `cpu_baseline` (oracle on host cores, bounded
@@ -34,10 +39,15 @@ for _p in (ROOT, ROOT / "tests"):
 METRIC = "novel_views_per_sec_fwd_bwd_256x256"
 UNIT = "views/s"
 H = W = 256
-CFG = dict(B=4, V_t=1, G=65_536, C=4, color_sh_degree=4, feature_sh_degree=2, f=0.86, near=1.0, far=100.0)
+CFG = dict(B=4, V_t=1, V_c=2, G=65_536, C=4, color_sh_degree=4, feature_sh_degree=2, f=0.86, near=1.0, far=100.0)
 
 
 def workload_name(cfg) -> str:
+    if cfg.get("workload", "splat") == "full":
+        return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views 256x256, "
+                f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
+                "views -> VAE kl-f8 decoder with skips; fwd+bwd+fused Adam, fp32 (TF32 convs); rasterizer = our sm_100a "
+                "kernels, encoder/VAE GEMM+conv = cuDNN/cuBLAS library calls this round")
     return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views 256x256, "
             f"G={cfg['G']} feature Gaussians/scene (colour SH deg {cfg['color_sh_degree']} + C={cfg['C']} feature SH "
             f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA fwd+bwd with scalar loss heads; "
@@ -270,11 +280,310 @@ def _sh_eval_np(deg, sh, dirs):
     return r.astype(np.float32)
 
 
+
+# ================================================================================================
+# full workload (BASELINE.json configs[1]): encoder -> splat -> VAE decode, fwd + bwd + Adam
+# ================================================================================================
+def make_full_batch(cfg, rank: int):
+    """Synthetic RE10k-shaped batch: identity + 1-unit x-baseline context cameras (5 deg yaw),
+    target poses between them, near/far from the bounds-shim rule, images U[0,1)."""
+    import torch
+    from latentsplat_b200 import synthetic
+    from latentsplat_b200.model.encoder.shims import apply_bounds_shim
+    seed = 1234 + 100 * 1 + rank
+    gen = torch.Generator().manual_seed(seed)
+    B, V_t, V_c = cfg["B"], cfg["V_t"], 2
+    ctx_extr = torch.stack([synthetic.pose(0.0, 0.0), synthetic.pose(1.0, -5.0)])[None].repeat(B, 1, 1, 1).contiguous()
+    batch = {
+        "context": {"image": torch.rand(B, V_c, 3, H, W, generator=gen), "extrinsics": ctx_extr,
+                    "intrinsics": synthetic.intrinsics(cfg["f"])[None, None].repeat(B, V_c, 1, 1).contiguous()},
+        "target": {"image": torch.rand(B, V_t, 3, H, W, generator=gen),
+                   "extrinsics": synthetic.target_poses(V_t)[None].repeat(B, 1, 1, 1).contiguous(),
+                   "intrinsics": synthetic.intrinsics(cfg["f"])[None, None].repeat(B, V_t, 1, 1).contiguous()}}
+    batch = apply_bounds_shim(batch, near_disparity=3.0 * min(H, W), far_disparity=0.5)
+    for part in ("context", "target"):
+        batch[part] = {k: v.contiguous() for k, v in batch[part].items()}
+    return batch
+
+
+def flatten_batch(batch):
+    return {f"{part}.{k}": v for part in ("context", "target") for k, v in batch[part].items()}
+
+
+def unflatten_batch(flat):
+    out = {"context": {}, "target": {}}
+    for k, v in flat.items():
+        part, name = k.split(".")
+        out[part][name] = v
+    return out
+
+
+def full_loss(out, target_image):
+    """10 mse(rendered colour) + l1(decoded image): the active nll terms of config/experiment/re10k.yaml
+    (lpips / GAN terms need third-party weights and are out of scope)."""
+    return 10.0 * ((out.render.color - target_image) ** 2).mean() + (out.image - target_image).abs().mean()
+
+
+def build_pipeline(device, seed=0):
+    import torch
+    from latentsplat_b200.configs import build_modules
+    from latentsplat_b200.pipeline import RenderPipeline
+    torch.manual_seed(seed)
+    ae, enc, dec, _ = build_modules(with_discriminator=False)
+    # un-zero the skip convs so that the skip path carries gradient like a trained model's
+    for c in ae.skip_convs:
+        torch.nn.init.normal_(c.weight, std=0.02)
+    pipe = RenderPipeline(ae, enc, dec, None).to(device)
+    # only the VAE *decoder* side is on the path (autoencoder.encode is never called, SURVEY.md 3.2)
+    params = [p for n, p in pipe.named_parameters()
+              if not (n.startswith("autoencoder.model.encoder") or n.startswith("autoencoder.model.quant_conv"))
+              and not n.startswith("autoencoder.skip_convs.4")]
+    return pipe, params
+
+
+def run_full(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: latentsplat_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from latentsplat_b200 import _build, _capi
+    _build.build()
+    _capi.load()
+    from latentsplat_b200.runtime import GraphedStep
+
+    pipe, params = build_pipeline(device, seed=0)          # identical replicas on every rank
+    n_params = sum(p.numel() for p in params)
+    # one flat gradient buffer (views as .grad): a single NCCL all-reduce per step, zeroed inside the graph
+    flat_grad = torch.zeros(n_params, device=device)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.Adam(params, lr=1.5e-5, fused=True, capturable=True)
+
+    batch = make_full_batch(cfg, rank)
+    flat = flatten_batch(batch)
+    dev_flat = {k: v.to(device) for k, v in flat.items()}
+    pinned = {k: v.pin_memory() for k, v in flat.items()}
+    views_per_step = cfg["B"] * cfg["V_t"]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+
+    def fwd_bwd(inp):
+        flat_grad.zero_()
+        out = pipe(unflatten_batch(inp), global_step=0)
+        loss = full_loss(out, inp["target.image"])
+        loss.backward()
+        return {"loss": loss.detach()}
+
+    def opt_step(_inp=None):
+        opt.step()
+        return {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record(); fn(); b.record()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), (time.perf_counter() - t0) * 1000
+
+    warm = max(args.warmup, 3)
+    # exact (eager) warm-up: sizes the rasterizer's key lists, then switch to sync-free capacity mode
+    for _ in range(2):
+        fwd_bwd(dev_flat)
+    capacity = pipe.decoder.calibrate_raster_capacity(slack=1.5)
+    num_rendered = pipe.decoder.last_raster.num_rendered
+    eager_ms, _ = timed_loop(lambda: (fwd_bwd(dev_flat), opt_step()), max(3, args.steps // 4))
+    eager_ms /= max(3, args.steps // 4)
+
+    g_fb = GraphedStep(fwd_bwd, dev_flat, warmup=warm)
+    g_opt = GraphedStep(opt_step, {}, warmup=1)
+
+    def step():
+        r = g_fb.replay()
+        if world > 1:
+            dist.all_reduce(flat_grad)
+            flat_grad.div_(world)
+        g_opt.replay()
+        return r
+
+    def step_e2e():
+        g_fb.load(pinned)
+        return float(step()["loss"].item())
+
+    for _ in range(warm):
+        step(); step_e2e()
+    with ClockSampler(local_rank) as clk:
+        dev_ms, wall_ms = timed_loop(step, args.steps)
+        e2e_ms, _ = timed_loop(step_e2e, args.steps)
+    clocks = clk.summary()
+    if int(pipe.decoder.last_raster.stats[2].item()):
+        raise SystemExit(f"rasterizer key capacity {capacity} overflowed; result invalid")
+
+    t = torch.tensor([dev_ms, e2e_ms, eager_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, eager_ms = t.tolist()
+    ms_per_step = dev_ms / args.steps
+    value = world * views_per_step / (ms_per_step / 1000)
+    e2e_value = world * views_per_step / (e2e_ms / args.steps / 1000)
+
+    roofline = stages = cpu = None
+    if rank == 0:
+        roofline, stages = full_stage_profile(pipe, dev_flat, cfg, fwd_bwd)
+        if world == 1:
+            cpu = cpu_baseline_full(cfg, min_seconds=0.0, max_steps=1)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "global_batch": world * cfg["B"], "views_per_step_per_gpu": views_per_step,
+                       "gaussians_per_scene": 2 * H * W * 3, "num_rendered_per_step": num_rendered,
+                       "parameters_updated": n_params, "parallelism": f"dp{world}",
+                       "l2": "flushed between timed steps (256 MiB write), flush outside the per-step CUDA events",
+                       "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+                       "execution": "fwd+bwd in one CUDA graph, Adam in a second; flat-gradient NCCL all-reduce between them "
+                                    f"when n_gpus > 1; rasterizer sync-free ({capacity} key slots, overflow flag checked)",
+                       "eager_exact_ms_per_step": eager_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": 7, "clocks": clocks, "roofline": roofline, "stages": stages,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def full_stage_profile(pipe, dev_flat, cfg, fwd_bwd):
+    """Module-level CUDA-event timing of one eager step + the rasterizer stage table at the full-step shape."""
+    import torch
+    from latentsplat_b200 import _capi
+    from latentsplat_b200.model.decoder.cuda_splatting import prepare_render_call
+    peak, peak_src = measured_peaks()
+    batch = unflatten_batch(dev_flat)
+    B, V_t = cfg["B"], cfg["V_t"]
+    V = B * V_t
+    with torch.no_grad():
+        gaussians = pipe.encoder(batch["context"], 0).sample()
+    flat = lambda t: t.reshape(V, *t.shape[2:])
+    tg = batch["target"]
+    names = ["preprocess", "scatter", "sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
+    acc = {n: [] for n in names}
+    gcol, gfeat = torch.randn(V, 3, H, W, device="cuda"), torch.randn(V, cfg["C"], H, W, device="cuda")
+    ga, gd = torch.randn(V, H, W, device="cuda"), torch.randn(V, H, W, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    n = 0
+    for it in range(5):
+        call = prepare_render_call(flat(tg["extrinsics"]), flat(tg["intrinsics"]), flat(tg["near"]), flat(tg["far"]), (H, W),
+                                   pipe.decoder.background_color.expand(V, 3), gaussians.means, gaussians.covariances,
+                                   gaussians.opacities, gaussians.color_harmonics, gaussians.feature_harmonics)
+        call.alloc_grads(False)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(12)]
+
+        def timed(i, fn):
+            flush.zero_()
+            ev[2 * i].record(); fn(); ev[2 * i + 1].record()
+        timed(0, lambda: call.forward_stage(_capi.STAGE_GEOMETRY))
+        n = call.size_keys()
+        timed(1, lambda: call.forward_stage(_capi.STAGE_SCATTER))
+        timed(2, lambda: call.forward_stage(_capi.STAGE_SORT))
+        timed(3, lambda: call.forward_stage(_capi.STAGE_BLEND))
+        timed(4, lambda: call.backward_stage(_capi.BWD_BLEND, gcol, gfeat, ga, gd))
+        timed(5, lambda: call.backward_stage(_capi.BWD_GEOMETRY, gcol, gfeat, ga, gd))
+        torch.cuda.synchronize()
+        if it >= 2:
+            for i, nm in enumerate(names):
+                acc[nm].append(ev[2 * i].elapsed_time(ev[2 * i + 1]))
+        del call
+    ms = {k: sum(v) / len(v) for k, v in acc.items()}
+    nbytes = stage_bytes(dict(cfg, G=2 * H * W * 3), V, n)
+    stages = {k: {"ms": ms[k], "GBps": nbytes[k] / (ms[k] / 1000) / 1e9, "frac": nbytes[k] / (ms[k] / 1000) / 1e9 / peak}
+              for k in ms}
+    dom = max(ms, key=ms.get)
+    traffic = None
+    prof = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if prof.exists():
+        traffic = json.loads(prof.read_text()).get(dom + "_full", {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "num_rendered": n,
+                "algorithmic_bytes_per_launch": nbytes[dom], "kernel_ms": ms[dom],
+                "note": "dominant kernel of OUR code (rasterizer); the step itself is dominated by library conv/GEMM kernels"}
+    return roofline, stages
+
+
+def cpu_baseline_full(cfg, min_seconds=10.0, max_steps=1, threads=0):
+    """The same step on the host: our parameter-compatible PyTorch modules on CPU + the oracle rasterizer behind the
+    reference's per-view data flow (oracle/decoder_cpu.py).  Bounded sample: B=1 scene pair, V_t=1."""
+    import torch
+    from latentsplat_b200.configs import build_modules
+    from latentsplat_b200.pipeline import RenderPipeline
+    from oracle import oracle
+    from oracle.decoder_cpu import DecoderSplattingCPU
+    from oracle.raster_stub import OracleGaussianRasterizer
+    oracle.build()
+    OracleGaussianRasterizer.parallel_backward = True
+    torch.manual_seed(0)
+    ae, enc, _, _ = build_modules(with_discriminator=False)
+    for c in ae.skip_convs:
+        torch.nn.init.normal_(c.weight, std=0.02)
+    pipe = RenderPipeline(ae, enc, DecoderSplattingCPU(n_threads=threads), None)
+    small = dict(cfg, B=1, V_t=1)
+    batch = make_full_batch(small, 0)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        pipe.zero_grad(set_to_none=True)
+        out = pipe(batch, global_step=0)
+        full_loss(out, batch["target"]["image"]).backward()
+        steps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or steps >= max_steps:
+            break
+    return {"value": steps / el, "unit": UNIT, "cores": os.cpu_count() if threads == 0 else threads, "kind": "port",
+            "sample": f"{steps} step(s) of B=1 scene pair, V_t=1 (encoder + oracle splat + VAE decode, fwd+bwd, torch CPU "
+                      f"threads={torch.get_num_threads()}) in {el:.1f}s"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, cfg):
     """--impl reference: the CPU implementation of the path (oracle port; no compilable reference source exists)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if cfg.get("workload") == "full":
+        times = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_baseline_full(cfg, min_seconds=0.0, max_steps=1)
+            if i >= args.warmup:
+                times.append(1.0 / r["value"])
+        ms = 1000 * sum(times) / len(times)
+        value = 1000.0 / ms
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": workload_name(cfg), "step": "B=1 scene pair, V_t=1 per step (bounded sample)"},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     from oracle import oracle
     oracle.build()
@@ -456,10 +765,13 @@ def main():
     ap.add_argument("--target-views", type=int, default=CFG["V_t"])
     ap.add_argument("--gaussians", type=int, default=CFG["G"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
+    ap.add_argument("--workload", default="full", choices=["full", "splat"])
     args = ap.parse_args()
-    cfg = dict(CFG, V_t=args.target_views, G=args.gaussians, B=args.batch)
+    cfg = dict(CFG, V_t=args.target_views, G=args.gaussians, B=args.batch, workload=args.workload)
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.workload == "full":
+        run_full(args, cfg)
     else:
         run_ours(args, cfg)
 

@@ -8,6 +8,7 @@ import torch
 from torch import Tensor, nn
 
 from ....geometry.projection import get_world_rays
+from ....misc.cache import device_constant
 from ....misc.sh_utils import sh_rotation_matrices
 from .gaussians import build_covariance
 
@@ -52,7 +53,7 @@ class GaussianAdapter(nn.Module):
         scale_min, scale_max = self.cfg.gaussian_scale_min, self.cfg.gaussian_scale_max
         scales = scale_min + (scale_max - scale_min) * scales.sigmoid()
         h, w = image_shape
-        pixel_size = 1 / torch.tensor((w, h), dtype=torch.float32, device=device)
+        pixel_size = device_constant((1 / w, 1 / h), device)
         scales = scales * depths[..., None] * self.get_scale_multiplier(intrinsics, pixel_size)[..., None]
 
         rotations = rotations / (rotations.norm(dim=-1, keepdim=True) + eps)

@@ -18,6 +18,7 @@ import torch
 from torch import Tensor, nn
 
 from ...geometry.projection import sample_image_grid
+from ...misc.cache import device_constant
 from ..diagonal_gaussian_distribution import DiagonalGaussianDistribution
 from ..types import VariationalGaussians
 from .backbone import Backbone, BackboneCfg, get_backbone
@@ -119,7 +120,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         xy_ray = xy_ray.reshape(h * w, 1, 2)
         gaussians = self.to_gaussians(features).unflatten(-1, (self.cfg.num_surfaces, -1))   # ... (srf c) -> ... srf c
         offset_xy = gaussians[..., :2].sigmoid()
-        pixel_size = 1 / torch.tensor((w, h), dtype=torch.float32, device=device)
+        pixel_size = device_constant((1 / w, 1 / h), device)
         xy_ray = xy_ray + (offset_xy - 0.5) * pixel_size
         gpp = self.cfg.gaussians_per_pixel
         g = self.gaussian_adapter(context["extrinsics"][:, :, None, None, None], context["intrinsics"][:, :, None, None, None],

@@ -5,6 +5,8 @@ from __future__ import annotations
 import torch
 from torch import Tensor
 
+from ...misc.cache import device_constant
+
 
 def apply_patch_shim_to_views(views: dict, patch_size: int) -> dict:
     """Centre-crop to a multiple of patch_size and rescale the normalised focal lengths."""
@@ -30,7 +32,7 @@ def compute_depth_for_disparity(extrinsics: Tensor, intrinsics: Tensor, image_sh
     deltas = (origins[:, None, :, :] - origins[:, :, None, :]).norm(dim=-1).clip(min=delta_min)
     baselines = deltas.flatten(1).max(dim=1).values
     h, w = image_shape
-    pixel_size = 1 / torch.tensor((w, h), dtype=torch.float32, device=extrinsics.device)
+    pixel_size = device_constant((1 / w, 1 / h), extrinsics.device)
     inv = torch.linalg.inv_ex(intrinsics[..., :2, :2], check_errors=False).inverse
     pixel_size = torch.einsum("...ij,j->...i", inv, pixel_size)
     return baselines / (disparity * pixel_size.flatten(1).mean(dim=1))

@@ -1,4 +1,4 @@
-"""A CPU `diff_gaussian_rasterization` look-alike backed by the oracle (TEST INFRASTRUCTURE).
+"""A CPU `diff_gaussian_rasterization` look-alike backed by the oracle (TEST INFRASTRUCTURE; lives in oracle/).
 
 It lets the reference's own Python (render_cuda, DecoderSplattingCUDA) run unmodified on the CPU
 box to generate golden fixtures, and gives the tests a per-view reference with autograd.
@@ -41,7 +41,7 @@ class _OracleFn(torch.autograd.Function):
                            viewmatrix=_np(rs.viewmatrix), projmatrix=_np(rs.projmatrix), campos=_np(rs.campos),
                            tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy), H=rs.image_height,
                            W=rs.image_width, bg=_np(rs.bg), shs=_np(shs), colors_precomp=_np(colors_precomp),
-                           features=_np(features), sh_degree=rs.sh_degree, prec=prec, n_threads=0)
+                           features=_np(features), sh_degree=rs.sh_degree, prec=prec, n_threads=OracleGaussianRasterizer.n_threads)
         ctx.r = r
         ctx.shapes = (opacities.shape,)
         dt = means3D.dtype
@@ -56,7 +56,9 @@ class _OracleFn(torch.autograd.Function):
         r = ctx.r
         g = oracle.backward(r, dL_dcolor=_np(g_color), dL_dfeature=_np(g_feature),
                             dL_dalpha=None if g_alpha is None else _np(g_alpha)[0],
-                            dL_ddepth=None if g_depth is None else _np(g_depth)[0], n_threads=1)
+                            dL_ddepth=None if g_depth is None else _np(g_depth)[0],
+                            n_threads=1 if OracleGaussianRasterizer.n_threads == 0 and not OracleGaussianRasterizer.parallel_backward
+                            else OracleGaussianRasterizer.n_threads)
         dt = torch.float64 if r.prec == "f64" else torch.float32
         t = lambda a: None if a is None else torch.from_numpy(np.asarray(a)).to(dt)
         d_means2D = torch.cat([t(g["dL_dmeans2D"]), torch.zeros(r.G, 1, dtype=dt)], dim=1)
@@ -69,6 +71,8 @@ class _OracleFn(torch.autograd.Function):
 class OracleGaussianRasterizer(nn.Module):
     """Same call signature as the rasterizer object built at cuda_splatting.py:146-158."""
     prec = "f32"
+    n_threads = 0              # forward OpenMP threads (0 = all cores)
+    parallel_backward = False  # tests keep the backward single-threaded (deterministic sums); bench.py turns it on
 
     def __init__(self, raster_settings):
         super().__init__()

@@ -97,7 +97,7 @@ def install_reference():
         raise SystemExit("/root/reference is not present: fixtures can only be generated in the build container")
     sys.meta_path.insert(0, _StubFinder())
     # the rasterizer: CPU oracle behind the reference's own call signature
-    from helpers_oracle_stub import OracleGaussianRasterizer, OracleSettings
+    from oracle.raster_stub import OracleGaussianRasterizer, OracleSettings
     _stub("diff_gaussian_rasterization", GaussianRasterizationSettings=OracleSettings,
           GaussianRasterizer=OracleGaussianRasterizer)
     sys.path.insert(0, str(REF))
