@@ -404,13 +404,20 @@ def run_full(args, cfg):
         return sum(a.elapsed_time(b) for a, b in ev), (time.perf_counter() - t0) * 1000
 
     warm = max(args.warmup, 3)
-    # exact (eager) warm-up: sizes the rasterizer's key lists, then switch to sync-free capacity mode
-    for _ in range(2):
-        fwd_bwd(dev_flat)
-    capacity = pipe.decoder.calibrate_raster_capacity(slack=1.5)
-    num_rendered = pipe.decoder.last_raster.num_rendered
-    eager_ms, _ = timed_loop(lambda: (fwd_bwd(dev_flat), opt_step()), max(3, args.steps // 4))
-    eager_ms /= max(3, args.steps // 4)
+    # Exact (eager) warm-up sizes the rasterizer's key lists; then switch to sync-free capacity mode.  Everything
+    # eager runs on a side stream: AccumulateGrad nodes born on the legacy default stream would break capture.
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fwd_bwd(dev_flat)
+        capacity = pipe.decoder.calibrate_raster_capacity(slack=1.5)
+        num_rendered = pipe.decoder.last_raster.num_rendered
+        n_eager = max(3, args.steps // 4)
+        eager_ms, _ = timed_loop(lambda: (fwd_bwd(dev_flat), opt_step()), n_eager)
+        eager_ms /= n_eager
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
 
     g_fb = GraphedStep(fwd_bwd, dev_flat, warmup=warm)
     g_opt = GraphedStep(opt_step, {}, warmup=1)

@@ -56,12 +56,23 @@ class LsRasterSizes(C.Structure):
     ]
 
 
+class LsGemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
+        ("act", C.c_int32), ("split_k", C.c_int32), ("accumulate", C.c_int32),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+        ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p),
+    ]
+
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
 STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15
 BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
 ABI_VERSION = 1
-EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version")
+EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
+           "ls_gemm_tf32")
 
 _lib = None
 
@@ -91,6 +102,8 @@ def load() -> C.CDLL:
     lib.ls_raster_backward.restype = C.c_int
     lib.ls_raster_backward.argtypes = [C.POINTER(LsRasterScene), C.POINTER(LsRasterState), C.POINTER(LsRasterGrads),
                                        C.c_int32, C.c_void_p]
+    lib.ls_gemm_tf32.restype = C.c_int
+    lib.ls_gemm_tf32.argtypes = [C.POINTER(LsGemmArgs), C.c_void_p]
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

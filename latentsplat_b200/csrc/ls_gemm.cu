@@ -1,0 +1,307 @@
+// ls_gemm.cu -- TF32 tensor-core GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+//   C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias) -> activation            (see include/ls_gemm.h)
+//
+// One CTA computes one 128 x 128 output tile (optionally one K-slice of it):
+//   warp 0, one lane : TMA producer -- 128B-swizzled boxes of fp32 into a 6-stage ring (32 KB per stage)
+//   warp 1, one lane : MMA issuer   -- 4 x tcgen05.mma.cta_group::1.kind::tf32 (M128 N128 K8) per stage,
+//                                      tcgen05.commit releases the stage / publishes the accumulator
+//   warp 2           : TMEM allocator (128 fp32 columns x 128 lanes)
+//   warps 4..7       : epilogue      -- tcgen05.ld 32x32b.x32, bias + ReLU/GELU, 16-byte stores or red.add
+// fp32 operands go from HBM to the tensor core untouched: kind::tf32 reads 32-bit elements from shared memory,
+// so there is no cast pass and no bf16 copy of activations or weights.  Operands may be K-major (row = M/N index,
+// K contiguous) or MN-major (row = K index, M/N contiguous), which covers forward (X W^T), dgrad (dY W) and
+// wgrad (dY^T X) without transposed copies:
+//   K-major  tile: one TMA box {32 K-floats, 128 rows}; canonical layout ((8,n),2):((8,SBO=1024B),1)
+//   MN-major tile: four TMA boxes {32 MN-floats, 32 K-rows} in the 128B-swizzle-with-32B-atom mode, the only
+//                  MN-major layout tcgen05 accepts for 32-bit operands (CUTLASS sm100_common.inl: "for mn-major
+//                  tf32 operands, SW128_32B is the only available smem layout"): canonical
+//                  ((8,n),(4,k)):((1,LBO=4096B),(4,SBO=512B)), descriptor layout type SWIZZLE_128B_BASE32B
+// (layout algebra: CUTLASS cute/atom/mma_traits_sm100.hpp "make_umma_desc"; descriptor bit fields:
+//  cute/arch/mma_sm100_desc.hpp).  Every mbarrier wait is bounded and traps instead of hanging.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ls_gemm.h"
+#include "ls_host.h"
+
+namespace lsg {
+
+constexpr int BM = 128, BN = 128, BK = 32;   // BK fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;                    // 32 B of tf32 per instruction
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int kThreads = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();   // a protocol bug must fail loudly, never hang the device
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    const uint64_t lo = (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16);
+    const uint64_t hi = (uint64_t)(sbo_bytes >> 4) | (1ull << 14) | ((uint64_t)layout_type << 29);
+    return lo | (hi << 32);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == LS_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == LS_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    return v;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
+            const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int nkb_total = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(nkb_total, kb0 + kb_per_split) - kb0;
+    if (nkb <= 0) return;   // uniform per CTA
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+            const int k0 = (kb0 + kb) * BK;
+            const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+            if (!A_MN) {
+                tma_load_2d(a_dst, &map_a, full0 + 8 * s, k0, tile_m * BM);
+            } else {
+#pragma unroll
+                for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, full0 + 8 * s, tile_m * BM + 32 * j, k0);
+            }
+            if (!B_MN) {
+                tma_load_2d(b_dst, &map_b, full0 + 8 * s, k0, tile_n * BN);
+            } else {
+#pragma unroll
+                for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, full0 + 8 * s, tile_n * BN + 32 * j, k0);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------ MMA issuer --------------------------------
+        // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+                // K-major: step 32 B inside the 128-B swizzle row.  MN-major: step 8 K-rows = two 4-row (512 B) atoms.
+                const uint64_t adesc = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+                const uint64_t bdesc = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
+                tc_mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
+        }
+        tc_commit(tfull);                        // accumulator complete
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue ----------------------------------
+        const int q = warp - 4;                  // TMEM lane quarter == warp % 4
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int row = tile_m * BM + q * 32 + lane;
+        float* crow = C + (long long)row * ldc;
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            const int col0 = tile_n * BN + c0;
+            if (row < M && col0 < N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = col0 + j;
+                    float v[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float x = __uint_as_float(r[j + t]);
+                        if (bias != nullptr && col + t < N) x += bias[col + t];
+                        v[t] = apply_act(x, act);
+                    }
+                    if (!atomic && vec_ok && col + 3 < N) {
+                        *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (col + t < N) {
+                                if (atomic) atomicAdd(crow + col + t, v[t]); else crow[col + t] = v[t];
+                            }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    }
+}
+
+}  // namespace lsg
+
+using namespace lsg;
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [outer][inner] with row pitch ld (elements), 128B-swizzled boxes {32, box_rows}, zero fill out of bounds
+int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_rows,
+             CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ls_fail("cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {ld * sizeof(float)};
+    const cuuint32_t box[2] = {32u, box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ls_fail("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
+                                          (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+    return 0;
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
+           cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gemm_tf32<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+            return ls_check_cuda("gemm smem attribute");
+        configured = true;
+    }
+    k_gemm_tf32<A_MN, B_MN><<<grid, kThreads, SMEM_BYTES, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K, (long long)a->ldc,
+                                                                     a->act, kb_per_split, atomic);
+    return ls_check_cuda("k_gemm_tf32");
+}
+}  // namespace
+
+extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
+    if (!a) return ls_fail("gemm args is NULL");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return ls_fail("gemm: bad sizes M=%d N=%d K=%d", a->M, a->N, a->K);
+    if (!a->A || !a->B || !a->C) return ls_fail("gemm: NULL operand");
+    if ((a->lda % 4) || (a->ldb % 4)) return ls_fail("gemm: lda/ldb must be multiples of 4 elements (TMA 16-byte stride rule)");
+    if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return ls_fail("gemm: A/B must be 16-byte aligned");
+    int split = a->split_k < 1 ? 1 : a->split_k;
+    const int nkb = (a->K + BK - 1) / BK;
+    if (split > nkb) split = nkb;
+    const int kb_per_split = (nkb + split - 1) / split;
+    split = (nkb + kb_per_split - 1) / kb_per_split;
+    const int atomic = (split > 1 || a->accumulate) ? 1 : 0;
+    if (atomic && a->act != LS_ACT_NONE) return ls_fail("gemm: activation cannot be fused with split-K / accumulate");
+    if (atomic && a->bias && split > 1) return ls_fail("gemm: bias cannot be fused with split-K");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (split > 1 && !a->accumulate) {
+        if (cudaMemset2DAsync(a->C, a->ldc * sizeof(float), 0, (size_t)a->N * sizeof(float), (size_t)a->M, stream) != cudaSuccess)
+            return ls_check_cuda("gemm memset");
+    }
+    CUtensorMap ma, mb;
+    const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (a->a_mn_major ? make_map(&ma, a->A, a->M, a->K, a->lda, 32, sw_mn) : make_map(&ma, a->A, a->K, a->M, a->lda, BM, sw_k)) return -1;
+    if (a->b_mn_major ? make_map(&mb, a->B, a->N, a->K, a->ldb, 32, sw_mn) : make_map(&mb, a->B, a->K, a->N, a->ldb, BN, sw_k)) return -1;
+    dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN, split);
+    if (a->a_mn_major) return a->b_mn_major ? launch<true, true>(ma, mb, a, grid, kb_per_split, atomic, stream)
+                                            : launch<true, false>(ma, mb, a, grid, kb_per_split, atomic, stream);
+    return a->b_mn_major ? launch<false, true>(ma, mb, a, grid, kb_per_split, atomic, stream)
+                         : launch<false, false>(ma, mb, a, grid, kb_per_split, atomic, stream);
+}

@@ -1,0 +1,98 @@
+"""TF32 tcgen05 GEMM (libls_raster.so::ls_gemm_tf32, include/ls_gemm.h) and the `Linear` layer built on it.
+
+`Linear` is a drop-in `nn.Linear` (same parameter names, so reference checkpoints load) whose CUDA forward,
+input-gradient and weight-gradient GEMMs run on our sm_100a kernel with bias (and ReLU) fused into the epilogue;
+it replaces the fp32 SIMT cuBLAS GEMMs the reference gets from torch's default matmul precision.  On CPU tensors
+(host-logic tests) it is plain `F.linear`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import _capi
+
+ACT = {"none": _capi.ACT_NONE, "relu": _capi.ACT_RELU, "gelu": _capi.ACT_GELU}
+NUM_SMS = 148
+enabled = True          # set False to route CUDA linears through cuBLAS (A/B comparisons)
+
+
+def gemm_tf32(A: Tensor, B: Tensor, *, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+              bias: Optional[Tensor] = None, act: str = "none", out: Optional[Tensor] = None, split_k: int = 0,
+              accumulate: bool = False) -> Tensor:
+    """out[M,N] (+)= op(A)[M,K] @ op(B)[N,K]^T (+ bias) -> act.   A: (M,K) row-major, or (K,M) if a_mn; B likewise.
+    `split_k=0` picks a split that fills the 148 SMs when the output has few tiles (weight gradients)."""
+    if not (A.is_cuda and B.is_cuda):
+        raise RuntimeError("gemm_tf32 needs CUDA tensors: latentsplat_b200 has no CPU fallback")
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1, "operands must be row-major with unit inner stride"
+    assert tuple(A.shape) == ((K, M) if a_mn else (M, K)) and tuple(B.shape) == ((K, N) if b_mn else (N, K))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    if split_k == 0:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        nkb = (K + 31) // 32
+        split_k = 1 if tiles >= NUM_SMS else max(1, min(nkb // 4, (2 * NUM_SMS + tiles - 1) // tiles))
+        if act != "none" or (bias is not None and split_k > 1):
+            split_k = 1
+    args = _capi.LsGemmArgs(M, N, K, int(a_mn), int(b_mn), ACT[act], int(split_k), int(accumulate), A.stride(0),
+                            B.stride(0), out.stride(0), A.data_ptr(), B.data_ptr(), out.data_ptr(),
+                            None if bias is None else bias.data_ptr())
+    with torch.cuda.device(A.device):
+        _capi.check(_capi.load().ls_gemm_tf32(C.byref(args), torch.cuda.current_stream().cuda_stream), "ls_gemm_tf32")
+    return out
+
+
+def _aligned(t: Tensor) -> bool:
+    return t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d: Tensor, weight: Tensor, bias: Optional[Tensor], act: str):
+        y = gemm_tf32(x2d, weight, M=x2d.shape[0], N=weight.shape[0], K=x2d.shape[1], bias=bias, act=act)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2d, weight, y if act == "relu" else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x2d, weight, y = ctx.saved_tensors
+        gy = gy.contiguous()
+        if ctx.act == "relu":
+            gy = gy * (y > 0)
+        M, K = x2d.shape
+        N = weight.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:      # dX = dY W     : A = dY (K-major over N), B = W read MN-major
+            gx = gemm_tf32(gy, weight, M=M, N=K, K=N, b_mn=True)
+        if ctx.needs_input_grad[1]:      # dW = dY^T X   : both operands MN-major, reduce over M (split-K)
+            gw = gemm_tf32(gy, x2d, M=N, N=K, K=M, a_mn=True, b_mn=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(dim=0)
+        return gx, gw, gb, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = "none") -> Tensor:
+    """F.linear(+activation) on the tcgen05 GEMM when possible (CUDA fp32, TMA-compatible strides)."""
+    if x.is_cuda and enabled and x.dtype == torch.float32 and weight.dtype == torch.float32 and act != "gelu":
+        x2d = x.reshape(-1, x.shape[-1])
+        if not x2d.is_contiguous():
+            x2d = x2d.contiguous()
+        K, N = x2d.shape[1], weight.shape[0]
+        if K % 4 == 0 and N % 4 == 0 and _aligned(x2d) and _aligned(weight) and x2d.shape[0] > 0:
+            return _LinearFn.apply(x2d, weight, bias, act).reshape(*x.shape[:-1], N)
+    y = F.linear(x, weight, bias)
+    return F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
+
+
+class Linear(nn.Linear):
+    """nn.Linear whose CUDA path is our tcgen05 TF32 GEMM (parameters: `weight`, `bias`, as nn.Linear)."""
+
+    def forward(self, input: Tensor) -> Tensor:
+        return linear(input, self.weight, self.bias)

@@ -10,7 +10,7 @@ from torch import Tensor, nn
 from ....geometry.projection import get_world_rays
 from ....misc.cache import device_constant
 from ....misc.sh_utils import sh_rotation_matrices
-from .gaussians import build_covariance
+from .gaussians import build_covariance, outer_sym, quaternion_to_matrix  # noqa: F401
 
 
 @dataclass
@@ -60,20 +60,24 @@ class GaussianAdapter(nn.Module):
 
         color_sh = color_sh.unflatten(-1, (3, self.d_color_sh))
         feature_sh = feature_sh.unflatten(-1, (self.n_feature_channels, self.d_feature_sh))
-        color_sh = color_sh.broadcast_to((*opacities.shape, 3, self.d_color_sh)) * self.color_sh_mask
-        feature_sh = feature_sh.broadcast_to((*opacities.shape, self.n_feature_channels, self.d_feature_sh)) \
-            * self.feature_sh_mask
+        color_sh = color_sh * self.color_sh_mask
+        feature_sh = feature_sh * self.feature_sh_mask
 
-        covariances = build_covariance(scales, rotations)
+        # world-space covariance C (R S S^T R^T) C^T = (C R S)(C R S)^T, without batched 3x3 GEMMs
         c2w_rotations = extrinsics[..., :3, :3]
-        covariances = c2w_rotations @ covariances @ c2w_rotations.transpose(-1, -2)
+        local = quaternion_to_matrix(rotations) * scales[..., None, :]
+        covariances = outer_sym((c2w_rotations[..., :, :, None] * local[..., None, :, :]).sum(dim=-2))
 
         origins, directions = get_world_rays(coordinates, extrinsics, intrinsics)
         means = origins + directions * depths[..., None]
 
         return Gaussians(means=means, covariances=covariances,
-                         color_harmonics=self._rotate(color_sh, c2w_rotations, self.cfg.color_sh_degree),
-                         feature_harmonics=self._rotate(feature_sh, c2w_rotations, self.cfg.feature_sh_degree),
+                         # rotate once per ray, THEN broadcast over the samples of the ray (the reference
+                         # broadcasts first, :92-93, and rotates spp x as many coefficient vectors)
+                         color_harmonics=self._rotate(color_sh, c2w_rotations, self.cfg.color_sh_degree)
+                         .broadcast_to((*opacities.shape, 3, self.d_color_sh)),
+                         feature_harmonics=self._rotate(feature_sh, c2w_rotations, self.cfg.feature_sh_degree)
+                         .broadcast_to((*opacities.shape, self.n_feature_channels, self.d_feature_sh)),
                          opacities=opacities,
                          scales=scales,                                             # camera space (ply export only)
                          rotations=rotations.broadcast_to((*scales.shape[:-1], 4)))

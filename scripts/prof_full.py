@@ -1,0 +1,49 @@
+import os, sys, torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, R + '/tests')
+import bench
+from torch.profiler import profile, ProfilerActivity, record_function
+cfg = dict(bench.CFG, workload='full')
+dev = torch.device('cuda:0')
+pipe, params = bench.build_pipeline(dev)
+flat = {k: v.to(dev) for k, v in bench.flatten_batch(bench.make_full_batch(cfg, 0)).items()}
+if len(sys.argv) > 1 and sys.argv[1] == 'tf32':
+    torch.backends.cuda.matmul.allow_tf32 = True
+def step():
+    for p in params: p.grad = None
+    with record_function("FWD"):
+        out = pipe(bench.unflatten_batch(flat), 0)
+        loss = bench.full_loss(out, flat['target.image'])
+    with record_function("BWD"):
+        loss.backward()
+for _ in range(2): step()
+torch.cuda.synchronize()
+# coarse module timing with hooks
+times = {}
+def hook(name):
+    def pre(m, i):
+        e = torch.cuda.Event(enable_timing=True); e.record(); m._t0 = e
+    def post(m, i, o):
+        e = torch.cuda.Event(enable_timing=True); e.record(); times.setdefault(name, []).append((m._t0, e))
+    return pre, post
+mods = {"dino": pipe.encoder.backbone.dino, "backbone_mlps+proj": None, "epipolar_transformer": pipe.encoder.epipolar_transformer,
+        "epi.sampler": pipe.encoder.epipolar_transformer.epipolar_sampler, "epi.transformer": pipe.encoder.epipolar_transformer.transformer,
+        "epi.refine": pipe.encoder.epipolar_transformer.upscale_refinement, "hi_res_skip": pipe.encoder.high_resolution_skip,
+        "gaussian_adapter": pipe.encoder.gaussian_adapter, "depth_predictor": pipe.encoder.depth_predictor,
+        "encoder": pipe.encoder, "decoder(splat)": pipe.decoder, "vae.decoder.mid": pipe.autoencoder.model.decoder.mid_block,
+        "vae.up0": pipe.autoencoder.model.decoder.up_blocks[0], "vae.up1": pipe.autoencoder.model.decoder.up_blocks[1],
+        "vae.up2": pipe.autoencoder.model.decoder.up_blocks[2], "vae.up3": pipe.autoencoder.model.decoder.up_blocks[3]}
+hs = []
+for n, m in mods.items():
+    if m is None: continue
+    a, b = hook(n); hs += [m.register_forward_pre_hook(a), m.register_forward_hook(b)]
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+for p in params: p.grad = None
+e0.record(); out = pipe(bench.unflatten_batch(flat), 0); loss = bench.full_loss(out, flat['target.image']); e1.record(); loss.backward(); e2.record()
+torch.cuda.synchronize()
+print(f"FWD {e0.elapsed_time(e1):.1f} ms  BWD {e1.elapsed_time(e2):.1f} ms")
+for n, v in times.items():
+    print(f"  fwd {n:24s} {sum(a.elapsed_time(b) for a, b in v):8.2f} ms ({len(v)} calls)")
+for h in hs: h.remove()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step(); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))

@@ -11,7 +11,8 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def test_library_exports_every_declared_symbol(lib):
     header = (ROOT / "include" / "ls_raster.h").read_text()
-    declared = set(re.findall(r"LS_API\s+[\w\s\*]+?\b(ls_\w+)\s*\(", header))
+    both = header + (ROOT / "include" / "ls_gemm.h").read_text()
+    declared = set(re.findall(r"LS_API\s+[\w\s\*]+?\b(ls_\w+)\s*\(", both))
     from latentsplat_b200 import _capi
     assert declared == set(_capi.EXPORTS), declared
     for name in declared:
@@ -23,7 +24,8 @@ def test_struct_layouts_match_the_header():
     """Field order of the ctypes mirrors == field order in the header (names), a cheap drift detector."""
     from latentsplat_b200 import _capi
     header = (ROOT / "include" / "ls_raster.h").read_text()
-    for name in ("LsRasterScene", "LsRasterState", "LsRasterImages", "LsRasterGrads", "LsRasterSizes"):
+    header += (ROOT / "include" / "ls_gemm.h").read_text()
+    for name in ("LsRasterScene", "LsRasterState", "LsRasterImages", "LsRasterGrads", "LsRasterSizes", "LsGemmArgs"):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
