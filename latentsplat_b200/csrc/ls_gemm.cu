@@ -2,12 +2,14 @@
 //
 //   C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias) -> activation            (see include/ls_gemm.h)
 //
-// One CTA computes one 128 x 128 output tile (optionally one K-slice of it):
-//   warp 0, one lane : TMA producer -- 128B-swizzled boxes of fp32 into a 6-stage ring (32 KB per stage)
+// Persistent kernel, one CTA per SM, each walking a list of 128 x 128 output tiles (optionally K-slices of them):
+//   warp 0, one lane : TMA producer -- 128B-swizzled boxes of fp32 into a 6-stage ring (32 KB per stage), running
+//                                      ahead across tile boundaries
 //   warp 1, one lane : MMA issuer   -- 4 x tcgen05.mma.cta_group::1.kind::tf32 (M128 N128 K8) per stage,
 //                                      tcgen05.commit releases the stage / publishes the accumulator
-//   warp 2           : TMEM allocator (128 fp32 columns x 128 lanes)
-//   warps 4..7       : epilogue      -- tcgen05.ld 32x32b.x32, bias + ReLU/GELU, 16-byte stores or red.add
+//   warp 2           : TMEM allocator (2 x 128 fp32 columns x 128 lanes: double-buffered accumulator)
+//   warps 4..7       : epilogue      -- tcgen05.ld 32x32b.x32, smem transpose, bias + ReLU/GELU, coalesced 16-byte
+//                                      stores or red.add; overlaps the next tile's main loop
 // fp32 operands go from HBM to the tensor core untouched: kind::tf32 reads 32-bit elements from shared memory,
 // so there is no cast pass and no bf16 copy of activations or weights.  Operands may be K-major (row = M/N index,
 // K contiguous) or MN-major (row = K index, M/N contiguous), which covers forward (X W^T), dgrad (dY W) and
@@ -22,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ls_gemm.h"
 #include "ls_host.h"
@@ -30,10 +33,11 @@ namespace lsg {
 
 constexpr int BM = 128, BN = 128, BK = 32;   // BK fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;                    // 32 B of tf32 per instruction
-constexpr int STAGES = 6;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int kThreads = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int PITCH = 36;                                   // floats; 144-B rows: conflict-free float4 access
+constexpr int PATCH_BYTES = 4 * 32 * PITCH * 4;              // one 32 x 32 transpose patch per epilogue warp
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + PATCH_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,24 +106,32 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: each CTA walks the work list  item = blockIdx.x + i * gridDim.x  (item -> n-tile fastest, then m-tile,
+// then K-split, so that concurrently running CTAs share A row panels in L2).  The TMA ring runs ahead across tiles,
+// the accumulator is double buffered in TMEM (2 x 128 columns) so that the epilogue of tile i overlaps the main loop
+// of tile i+1.
+template <bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
-            const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic) {
+            const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic,
+            int tiles_m, int tiles_n, int splits) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                    // 4 x 32 x 36 floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PATCH_BYTES);    // full[S] empty[S] tfull[2] tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
     const int nkb_total = (K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * kb_per_split;
-    const int nkb = min(nkb_total, kb0 + kb_per_split) - kb0;
-    if (nkb <= 0) return;   // uniform per CTA
+    const int n_items = tiles_m * tiles_n * splits;
 
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -127,11 +139,11 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -139,25 +151,38 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+    auto decode = [&](int item, int& tile_m, int& tile_n, int& kb0, int& nkb) {
+        tile_n = item % tiles_n;
+        const int rest = item / tiles_n;
+        tile_m = rest % tiles_m;
+        kb0 = (rest / tiles_m) * kb_per_split;
+        nkb = min(nkb_total, kb0 + kb_per_split) - kb0;      // >= 1 by construction of `splits`
+    };
+
     if (warp == 0 && lane == 0) {
         // ------------------------------ TMA producer ------------------------------
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
-            mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-            const int k0 = (kb0 + kb) * BK;
-            const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-            if (!A_MN) {
-                tma_load_2d(a_dst, &map_a, full0 + 8 * s, k0, tile_m * BM);
-            } else {
+        uint32_t it = 0;                                       // global k-block counter -> stage / phase
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                const int k0 = (kb0 + kb) * BK;
+                const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                if (!A_MN) {
+                    tma_load_2d(a_dst, &map_a, full0 + 8 * s, k0, tile_m * BM);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, full0 + 8 * s, tile_m * BM + 32 * j, k0);
-            }
-            if (!B_MN) {
-                tma_load_2d(b_dst, &map_b, full0 + 8 * s, k0, tile_n * BN);
-            } else {
+                    for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, full0 + 8 * s, tile_m * BM + 32 * j, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d(b_dst, &map_b, full0 + 8 * s, k0, tile_n * BN);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, full0 + 8 * s, tile_n * BN + 32 * j, k0);
+                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, full0 + 8 * s, tile_n * BN + 32 * j, k0);
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -165,63 +190,96 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-            mbar_wait(full0 + 8 * s, ph);
+        uint32_t it = 0, local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);          // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-                // K-major: step 32 B inside the 128-B swizzle row.  MN-major: step 8 K-rows = two 4-row (512 B) atoms.
-                const uint64_t adesc = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
-                const uint64_t bdesc = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
-                tc_mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // K-major: step 32 B inside the 128-B swizzle row.  MN-major: step 8 K-rows = two 4-row (512 B) atoms.
+                    const uint64_t adesc = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+                    const uint64_t bdesc = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
+                    tc_mma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
             }
-            tc_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
+            tc_commit(tfull0 + 8 * acc);            // accumulator complete
         }
-        tc_commit(tfull);                        // accumulator complete
     } else if (warp >= 4) {
         // ------------------------------ epilogue ----------------------------------
+        // The accumulator arrives "one row per lane" (tcgen05.ld 32x32b).  Writing it out like that would touch 32
+        // different rows per store instruction; each warp therefore transposes its 32 x 32 chunk through a private
+        // 4.5 KB shared-memory patch and stores 4 rows x 128 contiguous bytes per instruction.
         const int q = warp - 4;                  // TMEM lane quarter == warp % 4
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        const int row = tile_m * BM + q * 32 + lane;
-        float* crow = C + (long long)row * ldc;
+        float* patch = patches + q * 32 * PITCH;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        uint32_t local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tc_fence_after();
+            const bool add_bias = bias != nullptr && kb0 == 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            const int col0 = tile_n * BN + c0;
-            if (row < M && col0 < N) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = tile_n * BN + c0;
+                if (col0 >= N) break;                                   // warp-uniform
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = col0 + j;
-                    float v[4];
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(patch + lane * PITCH + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const int col = col0 + sub_c;
+                float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (add_bias) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        float x = __uint_as_float(r[j + t]);
-                        if (bias != nullptr && col + t < N) x += bias[col + t];
-                        v[t] = apply_act(x, act);
-                    }
-                    if (!atomic && vec_ok && col + 3 < N) {
-                        *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else {
+                    for (int t = 0; t < 4; ++t) if (col + t < N) b4[t] = bias[col + t];
+                }
 #pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (col + t < N) {
-                                if (atomic) atomicAdd(crow + col + t, v[t]); else crow[col + t] = v[t];
-                            }
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + sub_r;
+                    const int row = tile_m * BM + q * 32 + rr;
+                    const float4 v4 = *reinterpret_cast<const float4*>(patch + rr * PITCH + sub_c);
+                    float v[4] = {apply_act(v4.x + b4[0], act), apply_act(v4.y + b4[1], act), apply_act(v4.z + b4[2], act),
+                                  apply_act(v4.w + b4[3], act)};
+                    if (row < M) {
+                        float* dst = C + (long long)row * ldc + col;
+                        if (!atomic && vec_ok && col + 3 < N) {
+                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (col + t < N) {
+                                    if (atomic) atomicAdd(dst + t, v[t]); else dst[t] = v[t];
+                                }
+                        }
                     }
                 }
+                __syncwarp();
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // 4 arrivals release the accumulator
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
     }
 }
 
@@ -261,18 +319,35 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer,
     return 0;
 }
 
-template <bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
-           cudaStream_t stream) {
+template <bool A_MN, bool B_MN, int STAGES>
+int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
+             cudaStream_t stream) {
     static bool configured = false;
+    constexpr int smem = smem_bytes(STAGES);
     if (!configured) {
-        if (cudaFuncSetAttribute(k_gemm_tf32<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_gemm_tf32<A_MN, B_MN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return ls_check_cuda("gemm smem attribute");
         configured = true;
     }
-    k_gemm_tf32<A_MN, B_MN><<<grid, kThreads, SMEM_BYTES, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K, (long long)a->ldc,
-                                                                     a->act, kb_per_split, atomic);
+    const int n_items = (int)(grid.x * grid.y * grid.z);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int ctas = n_items < num_sms ? n_items : num_sms;
+    k_gemm_tf32<A_MN, B_MN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K,
+                                                                       (long long)a->ldc, a->act, kb_per_split, atomic,
+                                                                       (int)grid.x, (int)grid.y, (int)grid.z);
     return ls_check_cuda("k_gemm_tf32");
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
+           cudaStream_t stream) {
+    return launch_s<A_MN, B_MN, 6>(ma, mb, a, grid, kb_per_split, atomic, stream);   // 6 x 32 KB ring + patches = 211 KB
 }
 }  // namespace
 
@@ -289,7 +364,6 @@ extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
     split = (nkb + kb_per_split - 1) / kb_per_split;
     const int atomic = (split > 1 || a->accumulate) ? 1 : 0;
     if (atomic && a->act != LS_ACT_NONE) return ls_fail("gemm: activation cannot be fused with split-K / accumulate");
-    if (atomic && a->bias && split > 1) return ls_fail("gemm: bias cannot be fused with split-K");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (split > 1 && !a->accumulate) {
         if (cudaMemset2DAsync(a->C, a->ldc * sizeof(float), 0, (size_t)a->N * sizeof(float), (size_t)a->M, stream) != cudaSuccess)

@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 class ResnetBlock2D(nn.Module):
@@ -40,10 +41,10 @@ class Attention(nn.Module):
     def __init__(self, channels: int, groups: int = 32, eps: float = 1e-6):
         super().__init__()
         self.group_norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
-        self.to_q = nn.Linear(channels, channels)
-        self.to_k = nn.Linear(channels, channels)
-        self.to_v = nn.Linear(channels, channels)
-        self.to_out = nn.ModuleList([nn.Linear(channels, channels), nn.Dropout(0.0)])
+        self.to_q = Linear(channels, channels)
+        self.to_k = Linear(channels, channels)
+        self.to_v = Linear(channels, channels)
+        self.to_out = nn.ModuleList([Linear(channels, channels), nn.Dropout(0.0)])
 
     def forward(self, x: Tensor) -> Tensor:
         b, c, h, w = x.shape

@@ -18,6 +18,7 @@ from torch import Tensor, nn
 
 from .backbone import Backbone
 from .dino_vit import CONFIGS, build_dino
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 @dataclass
@@ -38,8 +39,8 @@ class BackboneDino(Backbone[BackboneDinoCfg]):
         self.dino = build_dino(cfg.model)
         d = CONFIGS[cfg.model][1]
         # NB: the reference hard-codes 768 (ViT-B); ViT-S checkpoints would not fit it either.
-        self.global_token_mlp = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, self.d_out))
-        self.local_token_mlp = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, self.d_out))
+        self.global_token_mlp = nn.Sequential(Linear(d, d), nn.ReLU(), Linear(d, self.d_out))
+        self.local_token_mlp = nn.Sequential(Linear(d, d), nn.ReLU(), Linear(d, self.d_out))
 
     @property
     def patch_size(self) -> int:

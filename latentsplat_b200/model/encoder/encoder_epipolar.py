@@ -28,6 +28,7 @@ from .encoder import Encoder
 from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
 from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
 from .shims import apply_bounds_shim, apply_patch_shim
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 @dataclass
@@ -63,7 +64,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
                  variational: bool) -> None:
         super().__init__(cfg, variational)
         self.backbone: Backbone = get_backbone(cfg.backbone, d_in, cfg.d_backbone, scale_factor)
-        self.backbone_projection = nn.Sequential(nn.ReLU(), nn.Linear(cfg.d_backbone, cfg.d_feature))
+        self.backbone_projection = nn.Sequential(nn.ReLU(), Linear(cfg.d_backbone, cfg.d_feature))
         self.epipolar_transformer = EpipolarTransformer(cfg.epipolar_transformer, cfg.d_feature, cfg.num_context_views) \
             if cfg.use_epipolar_transformer else None
         self.depth_predictor = DepthPredictorMonocular(cfg.d_feature, cfg.num_monocular_samples, cfg.num_surfaces,
@@ -72,8 +73,8 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         self.gaussian_adapter = GaussianAdapter(cfg.gaussian_adapter,
                                                 2 * n_feature_channels if variational else n_feature_channels)
         if cfg.predict_opacity:
-            self.to_opacity = nn.Sequential(nn.ReLU(), nn.Linear(cfg.d_feature, 1), nn.Sigmoid())
-        self.to_gaussians = nn.Sequential(nn.ReLU(), nn.Linear(cfg.d_feature,
+            self.to_opacity = nn.Sequential(nn.ReLU(), Linear(cfg.d_feature, 1), nn.Sigmoid())
+        self.to_gaussians = nn.Sequential(nn.ReLU(), Linear(cfg.d_feature,
                                                                cfg.num_surfaces * (2 + self.gaussian_adapter.d_in)))
         # the high-resolution skip only exists without downscaling (:104-111)
         self.high_resolution_skip = nn.Sequential(nn.Conv2d(3, cfg.d_feature, 7, 1, 3), nn.ReLU()) \

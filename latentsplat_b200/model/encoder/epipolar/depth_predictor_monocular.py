@@ -7,12 +7,13 @@ from torch import Tensor, nn
 
 from .conversions import relative_disparity_to_depth
 from .distribution_sampler import DistributionSampler
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 class DepthPredictorMonocular(nn.Module):
     def __init__(self, d_in: int, num_samples: int, num_surfaces: int, use_transmittance: bool) -> None:
         super().__init__()
-        self.projection = nn.Sequential(nn.ReLU(), nn.Linear(d_in, 2 * num_samples * num_surfaces))
+        self.projection = nn.Sequential(nn.ReLU(), Linear(d_in, 2 * num_samples * num_surfaces))
         self.sampler = DistributionSampler()
         self.num_samples = num_samples
         self.num_surfaces = num_surfaces

@@ -20,6 +20,7 @@ from ...transformer.transformer import Transformer
 from .conversions import depth_to_relative_disparity
 from .epipolar_sampler import EpipolarSampler, EpipolarSampling
 from .image_self_attention import ImageSelfAttention, ImageSelfAttentionCfg
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 @dataclass
@@ -57,7 +58,7 @@ class EpipolarTransformer(nn.Module):
         self.epipolar_sampler = EpipolarSampler(num_context_views, cfg.num_samples)
         if cfg.num_octaves > 0:
             pe = PositionalEncoding(cfg.num_octaves)
-            self.depth_encoding = nn.Sequential(pe, nn.Linear(pe.d_out(1), d_in))
+            self.depth_encoding = nn.Sequential(pe, Linear(pe.d_out(1), d_in))
         self.transformer = Transformer(d_in, cfg.num_layers, cfg.num_heads, cfg.d_dot, cfg.d_mlp, selfatt=False,
                                        kv_dim=d_in, feed_forward_layer=partial(ConvFeedForward, cfg.self_attention))
         if cfg.downscale > 1:

@@ -9,6 +9,7 @@ from torch import Tensor, nn
 from ....geometry.projection import sample_image_grid
 from ...encodings.positional_encoding import PositionalEncoding
 from ...transformer.transformer import Transformer
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 @dataclass
@@ -26,7 +27,7 @@ class ImageSelfAttention(nn.Module):
     def __init__(self, cfg: ImageSelfAttentionCfg, d_in: int, d_out: int):
         super().__init__()
         pe = PositionalEncoding(cfg.num_octaves)
-        self.positional_encoding = nn.Sequential(pe, nn.Linear(pe.d_out(2), cfg.d_token))
+        self.positional_encoding = nn.Sequential(pe, Linear(pe.d_out(2), cfg.d_token))
         self.patch_embedder = nn.Sequential(nn.Conv2d(d_in, cfg.d_token, cfg.patch_size, cfg.patch_size), nn.ReLU())
         self.transformer = Transformer(cfg.d_token, cfg.num_layers, cfg.num_heads, cfg.d_dot, cfg.d_mlp)
         self.resampler = nn.ConvTranspose2d(cfg.d_token, d_out, cfg.patch_size, cfg.patch_size)

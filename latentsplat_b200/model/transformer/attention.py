@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import torch
 from torch import nn
+from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
 class Attention(nn.Module):
@@ -17,11 +18,11 @@ class Attention(nn.Module):
         self.scale = dim_head ** -0.5
         self.attend = nn.Softmax(dim=-1)
         if selfatt:
-            self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
+            self.to_qkv = Linear(dim, inner_dim * 3, bias=False)
         else:
-            self.to_q = nn.Linear(dim, inner_dim, bias=False)
-            self.to_kv = nn.Linear(kv_dim, inner_dim * 2, bias=False)
-        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout)) if project_out else nn.Identity()
+            self.to_q = Linear(dim, inner_dim, bias=False)
+            self.to_kv = Linear(kv_dim, inner_dim * 2, bias=False)
+        self.to_out = nn.Sequential(Linear(inner_dim, dim), nn.Dropout(dropout)) if project_out else nn.Identity()
 
     def forward(self, x, z=None):
         if z is None:
