@@ -354,6 +354,8 @@ def run_full(args, cfg):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=device)
     from latentsplat_b200 import _build, _capi
     _build.build()
@@ -634,6 +636,8 @@ def run_ours(args, cfg):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=device)
 
     from latentsplat_b200 import _build, _capi

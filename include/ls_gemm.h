@@ -50,6 +50,15 @@ typedef struct LsGemmArgs {
 
 LS_API int ls_gemm_tf32(const LsGemmArgs* args, void* stream /* cudaStream_t */);
 
+/* Fused single-query multi-head attention: replaces the chunk / rearrange / bmm / softmax / bmm sequence of
+ * src/model/transformer/attention.py:54-70 for the epipolar cross-attention (one query per ray, S <= 32 sampled
+ * key/value tokens, epipolar_transformer.py:127-135).  q (R, H*D), kv (R, S, 2*H*D) = [K | V] as produced by to_kv,
+ * out (R, H*D), p (R, H, S) softmax probabilities kept for backward.  D must be 128. */
+LS_API int ls_sq_attention_forward(const float* q, const float* kv, float* out, float* p, int32_t R, int32_t H, int32_t S,
+                                   int32_t D, float scale, void* stream);
+LS_API int ls_sq_attention_backward(const float* q, const float* kv, const float* p, const float* dout, float* dq,
+                                    float* dkv, int32_t R, int32_t H, int32_t S, int32_t D, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,7 +72,7 @@ STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL 
 BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
 ABI_VERSION = 1
 EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
-           "ls_gemm_tf32")
+           "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward")
 
 _lib = None
 
@@ -104,6 +104,10 @@ def load() -> C.CDLL:
                                        C.c_int32, C.c_void_p]
     lib.ls_gemm_tf32.restype = C.c_int
     lib.ls_gemm_tf32.argtypes = [C.POINTER(LsGemmArgs), C.c_void_p]
+    lib.ls_sq_attention_forward.restype = C.c_int
+    lib.ls_sq_attention_forward.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
+    lib.ls_sq_attention_backward.restype = C.c_int
+    lib.ls_sq_attention_backward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -1,0 +1,120 @@
+// ls_attn.cu -- fused single-query multi-head attention (epipolar cross-attention), forward and backward.
+//
+// Replaces, for the epipolar transformer's cross-attention (one query token per ray, S = 32 key/value tokens sampled
+// on the epipolar line; /root/reference/src/model/transformer/attention.py:54-70 called from
+// epipolar_transformer.py:127-135), the eager sequence  chunk -> rearrange (2 transposed copies of the 4.3 GB kv
+// tensor) -> bmm(q, k^T) -> softmax -> bmm(attn, v) -> rearrange.  Here each warp owns one (ray, head): it streams the
+// head's K rows once (coalesced float4 per lane), reduces the 32 scores with shuffles, soft-maxes them in registers and
+// streams the V rows once.  HBM traffic = the kv tensor read exactly once per pass (+ written once in backward).
+//
+// Layouts (all fp32, row-major):  q (R, H*D);  kv (R, S, 2*H*D) with K = columns [0, H*D), V = [H*D, 2*H*D), head h at
+// [h*D, (h+1)*D) -- exactly what `to_kv(z).chunk(2, -1)` + "b n (h d) -> b h n d" index;  out (R, H*D);
+// p (R, H, S) softmax probabilities saved for backward.   D must be 128 (4 floats per lane), S <= 32.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ls_gemm.h"
+#include "ls_host.h"
+
+namespace lsa {
+
+constexpr int D = 128;
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+__global__ void __launch_bounds__(256) k_sq_attn_fwd(const float* __restrict__ q, const float* __restrict__ kv,
+                                                     float* __restrict__ out, float* __restrict__ p, int R, int H, int S,
+                                                     float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (ray, head)
+    if (w >= (long long)R * H) return;
+    const int r = (int)(w / H), h = (int)(w % H);
+    const int HD = H * D;
+    const float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * HD + h * D + 4 * lane);
+    const float* kbase = kv + (size_t)r * S * 2 * HD + h * D + 4 * lane;
+    float my_score = -INFINITY;                       // lane j keeps score j
+    for (int j = 0; j < S; ++j) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kbase + (size_t)j * 2 * HD);
+        const float s = warp_sum(dot4(q4, k4)) * scale;
+        if (lane == j) my_score = s;
+    }
+    const float m = warp_max(my_score);
+    const float e = lane < S ? __expf(my_score - m) : 0.f;
+    const float prob = e / warp_sum(e);
+    if (lane < S) p[((size_t)r * H + h) * S + lane] = prob;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* vbase = kbase + HD;
+    for (int j = 0; j < S; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, prob, j);
+        const float4 v4 = *reinterpret_cast<const float4*>(vbase + (size_t)j * 2 * HD);
+        acc.x = fmaf(pj, v4.x, acc.x); acc.y = fmaf(pj, v4.y, acc.y); acc.z = fmaf(pj, v4.z, acc.z); acc.w = fmaf(pj, v4.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + (size_t)r * HD + h * D + 4 * lane) = acc;
+}
+
+__global__ void __launch_bounds__(256) k_sq_attn_bwd(const float* __restrict__ q, const float* __restrict__ kv,
+                                                     const float* __restrict__ p, const float* __restrict__ dout,
+                                                     float* __restrict__ dq, float* __restrict__ dkv, int R, int H, int S,
+                                                     float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (long long)R * H) return;
+    const int r = (int)(w / H), h = (int)(w % H);
+    const int HD = H * D;
+    const size_t qoff = (size_t)r * HD + h * D + 4 * lane;
+    const float4 q4 = *reinterpret_cast<const float4*>(q + qoff);
+    const float4 g4 = *reinterpret_cast<const float4*>(dout + qoff);
+    const size_t kvoff = (size_t)r * S * 2 * HD + h * D + 4 * lane;
+    const float prob = lane < S ? p[((size_t)r * H + h) * S + lane] : 0.f;
+    // dp_j = dout . v_j ; dv_j = p_j dout
+    float my_dp = 0.f;
+    for (int j = 0; j < S; ++j) {
+        const float4 v4 = *reinterpret_cast<const float4*>(kv + kvoff + HD + (size_t)j * 2 * HD);
+        const float dp = warp_sum(dot4(g4, v4));
+        if (lane == j) my_dp = dp;
+        const float pj = __shfl_sync(0xffffffffu, prob, j);
+        *reinterpret_cast<float4*>(dkv + kvoff + HD + (size_t)j * 2 * HD) = make_float4(pj * g4.x, pj * g4.y, pj * g4.z, pj * g4.w);
+    }
+    const float ds = prob * (my_dp - warp_sum(prob * my_dp)) * scale;     // d score_j (scale folded in)
+    float4 dq4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < S; ++j) {
+        const float dsj = __shfl_sync(0xffffffffu, ds, j);
+        const float4 k4 = *reinterpret_cast<const float4*>(kv + kvoff + (size_t)j * 2 * HD);
+        dq4.x = fmaf(dsj, k4.x, dq4.x); dq4.y = fmaf(dsj, k4.y, dq4.y); dq4.z = fmaf(dsj, k4.z, dq4.z); dq4.w = fmaf(dsj, k4.w, dq4.w);
+        *reinterpret_cast<float4*>(dkv + kvoff + (size_t)j * 2 * HD) = make_float4(dsj * q4.x, dsj * q4.y, dsj * q4.z, dsj * q4.w);
+    }
+    *reinterpret_cast<float4*>(dq + qoff) = dq4;
+}
+
+}  // namespace lsa
+
+extern "C" LS_API int ls_sq_attention_forward(const float* q, const float* kv, float* out, float* p, int32_t R, int32_t H,
+                                              int32_t S, int32_t Dh, float scale, void* stream) {
+    if (Dh != lsa::D) return ls_fail("single-query attention: head dim %d != 128", Dh);
+    if (S < 1 || S > 32) return ls_fail("single-query attention: S=%d not in 1..32", S);
+    if (R <= 0 || H <= 0) return 0;
+    const long long warps = (long long)R * H;
+    lsa::k_sq_attn_fwd<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(q, kv, out, p, R, H, S, scale);
+    return ls_check_cuda("k_sq_attn_fwd");
+}
+
+extern "C" LS_API int ls_sq_attention_backward(const float* q, const float* kv, const float* p, const float* dout, float* dq,
+                                               float* dkv, int32_t R, int32_t H, int32_t S, int32_t Dh, float scale,
+                                               void* stream) {
+    if (Dh != lsa::D) return ls_fail("single-query attention: head dim %d != 128", Dh);
+    if (S < 1 || S > 32) return ls_fail("single-query attention: S=%d not in 1..32", S);
+    if (R <= 0 || H <= 0) return 0;
+    const long long warps = (long long)R * H;
+    lsa::k_sq_attn_bwd<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(q, kv, p, dout, dq, dkv, R, H, S, scale);
+    return ls_check_cuda("k_sq_attn_bwd");
+}

@@ -38,7 +38,12 @@ class Attention(nn.Module):
     def forward(self, x):
         B, N, C = x.shape
         qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
+        if x.is_cuda and ATTENTION_BF16:
+            # library flash-attention on bf16 copies of q/k/v (fp32 SDPA lands on an sm_80 SIMT kernel: 30 ms/step)
+            q, k, v = (t.to(torch.bfloat16) for t in (qkv[0], qkv[1], qkv[2]))
+            x = F.scaled_dot_product_attention(q, k, v, scale=self.scale).to(qkv.dtype)
+        else:
+            x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
         return self.proj(x.transpose(1, 2).reshape(B, N, C))
 
 
@@ -64,6 +69,8 @@ class PatchEmbed(nn.Module):
     def forward(self, x):
         return self.proj(x).flatten(2).transpose(1, 2)
 
+
+ATTENTION_BF16 = True     # DINO self-attention core in bf16 flash-attention on CUDA (q/k/v projections stay TF32/fp32)
 
 CONFIGS = {"dino_vits16": (16, 384, 12, 6), "dino_vits8": (8, 384, 12, 6),
            "dino_vitb16": (16, 768, 12, 12), "dino_vitb8": (8, 768, 12, 12)}

@@ -6,6 +6,8 @@ from __future__ import annotations
 
 import torch
 from torch import nn
+
+from latentsplat_b200 import attention as fused
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
@@ -29,7 +31,12 @@ class Attention(nn.Module):
             q, k, v = self.to_qkv(x).chunk(3, dim=-1)
         else:
             q = self.to_q(x)
-            k, v = self.to_kv(z).chunk(2, dim=-1)
+            kv = self.to_kv(z)
+            # epipolar cross-attention: one query per ray -> fused sm_100a kernel (no chunk/rearrange copies of kv,
+            # no tiny batched GEMMs); falls back to the explicit path when something hooks `attend` (visualiser)
+            if x.shape[1] == 1 and not self.attend._forward_hooks and fused.supported(q[:, 0], kv, self.heads):
+                return self.to_out(fused.single_query_attention(q[:, 0], kv, self.heads, self.scale)[:, None])
+            k, v = kv.chunk(2, dim=-1)
         split = lambda t: t.unflatten(-1, (self.heads, -1)).transpose(1, 2)      # b n (h d) -> b h n d
         q, k, v = split(q), split(k), split(v)
         dots = torch.matmul(q, k.transpose(-1, -2)) * self.scale

@@ -89,3 +89,34 @@ def test_linear_layer_forward_backward_matches_torch(cuda):
     # fused ReLU path
     y2 = gemm.linear(x, lin.weight, lin.bias, act="relu")
     assert (y2.double() - yr.relu()).abs().max().item() <= 6e-3 * float(yr.detach().abs().max())
+
+
+def test_fused_single_query_attention_matches_reference_math(cuda):
+    """ls_sq_attention_* == the explicit softmax(q k^T d^-1/2) v of attention.py:64-68, forward and backward."""
+    from latentsplat_b200.attention import single_query_attention
+    R, H, S, D = 777, 4, 32, 128
+    g = torch.Generator(cuda).manual_seed(3)
+    q = torch.randn(R, H * D, device=cuda, generator=g, requires_grad=True)
+    kv = torch.randn(R, S, 2 * H * D, device=cuda, generator=g, requires_grad=True)
+    w = torch.randn(R, H * D, device=cuda, generator=g)
+    out = single_query_attention(q, kv, H, D ** -0.5)
+    (out * w).sum().backward()
+    gq, gkv = q.grad.clone(), kv.grad.clone()
+    q.grad = kv.grad = None
+    qd, kvd = q.double(), kv.double()
+    k, v = kvd.chunk(2, dim=-1)
+    split = lambda t: t.unflatten(-1, (H, D)).transpose(1, 2)            # (R, H, n, D)
+    dots = torch.matmul(split(qd[:, None]), split(k).transpose(-1, -2)) * D ** -0.5
+    ref = torch.matmul(dots.softmax(dim=-1), split(v)).transpose(1, 2).flatten(-2)[:, 0]
+    (ref * w.double()).sum().backward()
+    assert (out.double() - ref).abs().max().item() < 1e-5
+    assert (gq.double() - q.grad.double()).abs().max().item() < 1e-5
+    assert (gkv.double() - kv.grad.double()).abs().max().item() < 1e-5
+    # ragged S (< 32)
+    kv2 = torch.randn(50, 7, 2 * H * D, device=cuda, generator=g)
+    q2 = torch.randn(50, H * D, device=cuda, generator=g)
+    o2 = single_query_attention(q2, kv2, H, 0.1)
+    k2, v2 = kv2.double().chunk(2, dim=-1)
+    d2 = torch.matmul(split(q2.double()[:, None]), split(k2).transpose(-1, -2)) * 0.1
+    r2 = torch.matmul(d2.softmax(dim=-1), split(v2)).transpose(1, 2).flatten(-2)[:, 0]
+    assert (o2.double() - r2).abs().max().item() < 1e-5
