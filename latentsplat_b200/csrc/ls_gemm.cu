@@ -31,13 +31,14 @@
 
 namespace lsg {
 
-constexpr int BM = 128, BN = 128, BK = 32;   // BK fp32 = 128 B = one swizzle row
+constexpr int BM = 128, BK = 32;              // BK fp32 = 128 B = one swizzle row; BN (128 | 256) is a template parameter
 constexpr int UMMA_K = 8;                    // 32 B of tf32 per instruction
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int A_BYTES = BM * BK * 4;
+__host__ __device__ constexpr int stage_bytes(int bn) { return A_BYTES + bn * BK * 4; }
 constexpr int kThreads = 256;
 constexpr int PITCH = 36;                                   // floats; 144-B rows: conflict-free float4 access
 constexpr int PATCH_BYTES = 4 * 32 * PITCH * 4;              // one 32 x 32 transpose patch per epilogue warp
-constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + PATCH_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/; }
+constexpr int smem_bytes(int stages, int bn) { return stages * stage_bytes(bn) + PATCH_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,6 +101,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return lo | (hi << 32);
 }
 
+// Explicit shared-memory accesses: through a generic pointer the compiler emits generic LD/ST (ncu: ST.E.128 /
+// long-scoreboard waits) and, unable to prove that the patch does not alias C, serialises every load behind the
+// previous global store -- 64 dependent round trips per tile.
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == LS_ACT_RELU) return fmaxf(v, 0.f);
     if (act == LS_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
@@ -114,11 +127,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // then K-split, so that concurrently running CTAs share A row panels in L2).  The TMA ring runs ahead across tiles,
 // the accumulator is double buffered in TMEM (2 x 128 columns) so that the epilogue of tile i overlaps the main loop
 // of tile i+1.
-template <bool A_MN, bool B_MN, int STAGES>
+template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
             const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic,
             int tiles_m, int tiles_n, int splits) {
+    constexpr int STAGE_BYTES = stage_bytes(BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                    // 4 x 32 x 36 floats
@@ -220,7 +234,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // different rows per store instruction; each warp therefore transposes its 32 x 32 chunk through a private
         // 4.5 KB shared-memory patch and stores 4 rows x 128 contiguous bytes per instruction.
         const int q = warp - 4;                  // TMEM lane quarter == warp % 4
-        float* patch = patches + q * 32 * PITCH;
+        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
         uint32_t local = 0;
@@ -239,8 +253,8 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(patch + lane * PITCH + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
                 __syncwarp();
                 const int col = col0 + sub_c;
                 float b4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -248,11 +262,13 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                     for (int t = 0; t < 4; ++t) if (col + t < N) b4[t] = bias[col + t];
                 }
+                float4 rows4[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int rr = 4 * i + sub_r;
-                    const int row = tile_m * BM + q * 32 + rr;
-                    const float4 v4 = *reinterpret_cast<const float4*>(patch + rr * PITCH + sub_c);
+                    const int row = tile_m * BM + q * 32 + 4 * i + sub_r;
+                    const float4 v4 = rows4[i];
                     float v[4] = {apply_act(v4.x + b4[0], act), apply_act(v4.y + b4[1], act), apply_act(v4.z + b4[2], act),
                                   apply_act(v4.w + b4[3], act)};
                     if (row < M) {
@@ -319,13 +335,13 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer,
     return 0;
 }
 
-template <bool A_MN, bool B_MN, int STAGES>
+template <bool A_MN, bool B_MN, int BN, int STAGES>
 int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
              cudaStream_t stream) {
     static bool configured = false;
-    constexpr int smem = smem_bytes(STAGES);
+    constexpr int smem = smem_bytes(STAGES, BN);
     if (!configured) {
-        if (cudaFuncSetAttribute(k_gemm_tf32<A_MN, B_MN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_gemm_tf32<A_MN, B_MN, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return ls_check_cuda("gemm smem attribute");
         configured = true;
     }
@@ -338,16 +354,31 @@ int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, 
         if (num_sms <= 0) num_sms = 148;
     }
     const int ctas = n_items < num_sms ? n_items : num_sms;
-    k_gemm_tf32<A_MN, B_MN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K,
+    k_gemm_tf32<A_MN, B_MN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K,
                                                                        (long long)a->ldc, a->act, kb_per_split, atomic,
                                                                        (int)grid.x, (int)grid.y, (int)grid.z);
     return ls_check_cuda("k_gemm_tf32");
 }
 
 template <bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
+int launch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
            cudaStream_t stream) {
-    return launch_s<A_MN, B_MN, 6>(ma, mb, a, grid, kb_per_split, atomic, stream);   // 6 x 32 KB ring + patches = 211 KB
+    // 128 x 128 tiles: 6 x 32 KB ring; 128 x 256 tiles: 4 x 48 KB ring (+ 18 KB transpose patches) ~ 211 KB
+    return bn == 256 ? launch_s<A_MN, B_MN, 256, 4>(ma, mb, a, grid, kb_per_split, atomic, stream)
+                     : launch_s<A_MN, B_MN, 128, 6>(ma, mb, a, grid, kb_per_split, atomic, stream);
+}
+
+// fp32 operands make the 128 x 128 tile shared-memory bound (32 KB written by TMA and 32 KB read by the tensor core
+// per 256 MMA cycles = 256 B/cycle against 128 B/cycle of smem bandwidth, ncu: tensor pipe 40 %); a 128 x 256 tile
+// moves 48 KB per 512 cycles.  Narrow outputs keep the square tile.
+int pick_bn(int N) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("LS_GEMM_BN");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 128 || forced == 256) return forced;
+    return N > 128 ? 256 : 128;
 }
 }  // namespace
 
@@ -369,13 +400,14 @@ extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
         if (cudaMemset2DAsync(a->C, a->ldc * sizeof(float), 0, (size_t)a->N * sizeof(float), (size_t)a->M, stream) != cudaSuccess)
             return ls_check_cuda("gemm memset");
     }
+    const int BN = pick_bn(a->N);
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     if (a->a_mn_major ? make_map(&ma, a->A, a->M, a->K, a->lda, 32, sw_mn) : make_map(&ma, a->A, a->K, a->M, a->lda, BM, sw_k)) return -1;
-    if (a->b_mn_major ? make_map(&mb, a->B, a->N, a->K, a->ldb, 32, sw_mn) : make_map(&mb, a->B, a->K, a->N, a->ldb, BN, sw_k)) return -1;
+    if (a->b_mn_major ? make_map(&mb, a->B, a->N, a->K, a->ldb, 32, sw_mn) : make_map(&mb, a->B, a->K, a->N, a->ldb, (uint32_t)BN, sw_k)) return -1;
     dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN, split);
-    if (a->a_mn_major) return a->b_mn_major ? launch<true, true>(ma, mb, a, grid, kb_per_split, atomic, stream)
-                                            : launch<true, false>(ma, mb, a, grid, kb_per_split, atomic, stream);
-    return a->b_mn_major ? launch<false, true>(ma, mb, a, grid, kb_per_split, atomic, stream)
-                         : launch<false, false>(ma, mb, a, grid, kb_per_split, atomic, stream);
+    if (a->a_mn_major) return a->b_mn_major ? launch<true, true>(BN, ma, mb, a, grid, kb_per_split, atomic, stream)
+                                            : launch<true, false>(BN, ma, mb, a, grid, kb_per_split, atomic, stream);
+    return a->b_mn_major ? launch<false, true>(BN, ma, mb, a, grid, kb_per_split, atomic, stream)
+                         : launch<false, false>(BN, ma, mb, a, grid, kb_per_split, atomic, stream);
 }

@@ -46,4 +46,8 @@ for n, v in times.items():
 for h in hs: h.remove()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+ka = sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)
+tot = sum(e.self_device_time_total for e in ka)
+print(f"Self CUDA total {tot/1e3:.1f} ms")
+for e in ka[:45]:
+    print(f"{e.self_device_time_total/1e3:9.2f} ms {100*e.self_device_time_total/tot:5.1f}% {e.count:5d}x  {e.key[:110]}")
