@@ -46,8 +46,9 @@ def workload_name(cfg) -> str:
     if cfg.get("workload", "splat") == "full":
         return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views 256x256, "
                 f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
-                "views -> VAE kl-f8 decoder with skips; fwd+bwd+fused Adam, fp32 (TF32 convs); rasterizer = our sm_100a "
-                "kernels, encoder/VAE GEMM+conv = cuDNN/cuBLAS library calls this round")
+                "views -> VAE kl-f8 decoder with skips; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
+                "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar single-query attention; library: cuDNN convolutions (TF32), "
+                "norms/elementwise (torch), DINO attention core (bf16 flash SDPA)")
     return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views 256x256, "
             f"G={cfg['G']} feature Gaussians/scene (colour SH deg {cfg['color_sh_degree']} + C={cfg['C']} feature SH "
             f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA fwd+bwd with scalar loss heads; "
@@ -362,6 +363,7 @@ def run_full(args, cfg):
     _capi.load()
     from latentsplat_b200.runtime import GraphedStep
 
+    torch.backends.cudnn.benchmark = True                  # let cuDNN pick its fastest (TF32) conv algorithms
     pipe, params = build_pipeline(device, seed=0)          # identical replicas on every rank
     n_params = sum(p.numel() for p in params)
     # one flat gradient buffer (views as .grad): a single NCCL all-reduce per step, zeroed inside the graph
@@ -411,8 +413,11 @@ def run_full(args, cfg):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for _ in range(2):
-            fwd_bwd(dev_flat)
+        from latentsplat_b200 import _capi as capi
+        fwd_bwd(dev_flat)
+        n0 = capi.KERNEL_LAUNCHES[0]
+        fwd_bwd(dev_flat)
+        gpu_launches = capi.KERNEL_LAUNCHES[0] - n0          # OUR kernels per step (rasterizer, GEMMs, fused attention)
         capacity = pipe.decoder.calibrate_raster_capacity(slack=1.5)
         num_rendered = pipe.decoder.last_raster.num_rendered
         n_eager = max(3, args.steps // 4)
@@ -464,9 +469,12 @@ def run_full(args, cfg):
         h2d = sum(v.numel() * v.element_size() for v in pinned.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
             "data": "synthetic",
-            "config": {"workload": workload_name(cfg), "global_batch": world * cfg["B"], "views_per_step_per_gpu": views_per_step,
+            "config": {"workload": workload_name(cfg), "global_batch": world * cfg["B"],
+                       "precision": "fp32 weights/activations in HBM; Linear layers = tcgen05 kind::tf32 (ours); convolutions = "
+                                    "cuDNN TF32 (torch default, as the reference); DINO attention core = bf16 flash SDPA (library); "
+                                    "rasterizer fp32", "views_per_step_per_gpu": views_per_step,
                        "gaussians_per_scene": 2 * H * W * 3, "num_rendered_per_step": num_rendered,
                        "parameters_updated": n_params, "parallelism": f"dp{world}",
                        "l2": "flushed between timed steps (256 MiB write), flush outside the per-step CUDA events",
@@ -475,7 +483,7 @@ def run_full(args, cfg):
                                     f"when n_gpus > 1; rasterizer sync-free ({capacity} key slots, overflow flag checked)",
                        "eager_exact_ms_per_step": eager_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": 7, "clocks": clocks, "roofline": roofline, "stages": stages,
+            "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "stages": stages,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -530,15 +538,46 @@ def full_stage_profile(pipe, dev_flat, cfg, fwd_bwd):
     stages = {k: {"ms": ms[k], "GBps": nbytes[k] / (ms[k] / 1000) / 1e9, "frac": nbytes[k] / (ms[k] / 1000) / 1e9 / peak}
               for k in ms}
     dom = max(ms, key=ms.get)
+    raster_roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                       "frac": stages[dom]["frac"], "num_rendered": n, "algorithmic_bytes_per_launch": nbytes[dom],
+                       "kernel_ms": ms[dom], "note": "blend kernels are instruction-issue bound (DESIGN.md section 4)"}
+    stages["raster_roofline"] = raster_roofline
+
+    # Dominant kernel of OUR code in the full step: the tcgen05 TF32 GEMM (all Linear layers; ~20 ms of the step vs
+    # ~4 ms of rasterizer kernels).  Timed live on its largest instance, the DINO MLP up-projection.
+    from latentsplat_b200.gemm import gemm_tf32
+    M, N, K = cfg["B"] * 2 * ((H // 8) * (W // 8) + 1), 3072, 768
+    A, Bm, out = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda"), torch.empty(M, N, device="cuda")
+    for _ in range(3):
+        gemm_tf32(A, Bm, M=M, N=N, K=K, out=out)
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gemm_tf32(A, Bm, M=M, N=N, K=K, out=out); e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    g_ms = sum(times) / len(times)
+    flops = 2.0 * M * N * K
+    tf32_peak, tf32_src = tf32_peak_tflops()
     traffic = None
     prof = ROOT / "profiles" / "r01_ncu_traffic.json"
     if prof.exists():
-        traffic = json.loads(prof.read_text()).get(dom + "_full", {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "num_rendered": n,
-                "algorithmic_bytes_per_launch": nbytes[dom], "kernel_ms": ms[dom],
-                "note": "dominant kernel of OUR code (rasterizer); the step itself is dominated by library conv/GEMM kernels"}
+        traffic = json.loads(prof.read_text()).get("gemm_dino_qkv", {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": f"k_gemm_tf32 (DINO fc1 {M}x{N}x{K}, TMA + tcgen05.mma kind::tf32)",
+                "achieved": flops / (g_ms / 1000) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": flops / (g_ms / 1000) / 1e12 / tf32_peak, "traffic": traffic, "peak_source": tf32_src,
+                "algorithmic_flops_per_launch": flops, "kernel_ms": g_ms,
+                "note": "dominant kernel of OUR code in this step; cuDNN convolutions (library) are the largest share overall"}
     return roofline, stages
+
+
+def tf32_peak_tflops():
+    """TF32 dense peak = half the bf16 rate; bf16 measured by the driver (cuBLAS, burst) in MEASURED_PEAKS.json."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["bf16_tflops"]) / 2, "measured bf16_tflops / 2 (MEASURED_PEAKS.json; TF32 runs at half the bf16 rate)"
+    return 1590.0 / 2, "fallback 1.59 PFLOP/s bf16 / 2 (B200_PROFILING.md)"
 
 
 def cpu_baseline_full(cfg, min_seconds=10.0, max_steps=1, threads=0):

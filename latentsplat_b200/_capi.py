@@ -75,6 +75,7 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward")
 
 _lib = None
+KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
 
 
 def lib_path() -> Path:

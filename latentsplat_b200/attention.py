@@ -19,6 +19,7 @@ class _SingleQueryAttention(torch.autograd.Function):
             _capi.check(_capi.load().ls_sq_attention_forward(q.data_ptr(), kv.data_ptr(), out.data_ptr(), p.data_ptr(), R,
                                                              heads, S, HD // heads, scale,
                                                              torch.cuda.current_stream().cuda_stream), "ls_sq_attention_forward")
+        _capi.KERNEL_LAUNCHES[0] += 1
         ctx.save_for_backward(q, kv, p)
         ctx.cfg = (heads, scale)
         return out
@@ -35,6 +36,7 @@ class _SingleQueryAttention(torch.autograd.Function):
             _capi.check(_capi.load().ls_sq_attention_backward(q.data_ptr(), kv.data_ptr(), p.data_ptr(), dout.data_ptr(),
                                                               dq.data_ptr(), dkv.data_ptr(), R, heads, S, HD // heads, scale,
                                                               torch.cuda.current_stream().cuda_stream), "ls_sq_attention_backward")
+        _capi.KERNEL_LAUNCHES[0] += 1
         return dq, dkv, None, None
 
 

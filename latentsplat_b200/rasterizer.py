@@ -135,6 +135,8 @@ class RasterCall:
         with torch.cuda.device(self.device):
             _capi.check(self.lib.ls_raster_forward(C.byref(self.scene), C.byref(st), C.byref(im), stages,
                                                    self._stream()), f"ls_raster_forward(stages={stages})")
+        # preprocess + scan | scatter | sort | blend
+        _capi.KERNEL_LAUNCHES[0] += 2 * bool(stages & 1) + bool(stages & 2) + bool(stages & 4) + bool(stages & 8)
 
     def size_keys(self) -> int:
         """The one host sync of a step: exact size of the key lists (the lineage syncs once per VIEW for
@@ -175,6 +177,7 @@ class RasterCall:
         with torch.cuda.device(self.device):
             _capi.check(self.lib.ls_raster_backward(C.byref(self.scene), C.byref(st), C.byref(grads), stages,
                                                     self._stream()), f"ls_raster_backward(stages={stages})")
+        _capi.KERNEL_LAUNCHES[0] += bool(stages & 1) + bool(stages & 2)
 
 
 class _Rasterize(torch.autograd.Function):
