@@ -367,11 +367,9 @@ def run_full(args, cfg):
     pipe, params = build_pipeline(device, seed=0)          # identical replicas on every rank
     n_params = sum(p.numel() for p in params)
     # one flat gradient buffer (views as .grad): a single NCCL all-reduce per step, zeroed inside the graph
-    flat_grad = torch.zeros(n_params, device=device)
-    off = 0
-    for p in params:
-        p.grad = flat_grad[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    from latentsplat_b200.parallel import FlatGradients
+    fgrads = FlatGradients(params)
+    flat_grad = fgrads.flat
     opt = torch.optim.Adam(params, lr=1.5e-5, fused=True, capturable=True)
 
     batch = make_full_batch(cfg, rank)
@@ -431,9 +429,7 @@ def run_full(args, cfg):
 
     def step():
         r = g_fb.replay()
-        if world > 1:
-            dist.all_reduce(flat_grad)
-            flat_grad.div_(world)
+        fgrads.all_reduce_mean()               # no-op at world size 1
         g_opt.replay()
         return r
 
