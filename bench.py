@@ -46,7 +46,7 @@ def workload_name(cfg) -> str:
     if cfg.get("workload", "splat") == "full":
         return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views 256x256, "
                 f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
-                "views -> VAE kl-f8 decoder with skips; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
+                "views -> VAE kl-f8 decoder with skips -> PatchGAN logits; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
                 "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar single-query attention; library: cuDNN convolutions (TF32), "
                 "norms/elementwise (torch), DINO attention core (bf16 flash SDPA)")
     return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views 256x256, "
@@ -320,9 +320,12 @@ def unflatten_batch(flat):
 
 
 def full_loss(out, target_image):
-    """10 mse(rendered colour) + l1(decoded image): the active nll terms of config/experiment/re10k.yaml
-    (lpips / GAN terms need third-party weights and are out of scope)."""
-    return 10.0 * ((out.render.color - target_image) ** 2).mean() + (out.image - target_image).abs().mean()
+    """10 mse(rendered colour) + l1(decoded image) + 0.5 * hinge generator term on the PatchGAN logits: the nll /
+    generator terms of config/experiment/re10k.yaml (lpips needs third-party VGG weights: out of scope)."""
+    loss = 10.0 * ((out.render.color - target_image) ** 2).mean() + (out.image - target_image).abs().mean()
+    if out.logits_fake is not None:
+        loss = loss - 0.5 * out.logits_fake.mean()
+    return loss
 
 
 def build_pipeline(device, seed=0):
@@ -330,15 +333,17 @@ def build_pipeline(device, seed=0):
     from latentsplat_b200.configs import build_modules
     from latentsplat_b200.pipeline import RenderPipeline
     torch.manual_seed(seed)
-    ae, enc, dec, _ = build_modules(with_discriminator=False)
+    ae, enc, dec, disc = build_modules(with_discriminator=True)
     # un-zero the skip convs so that the skip path carries gradient like a trained model's
     for c in ae.skip_convs:
         torch.nn.init.normal_(c.weight, std=0.02)
-    pipe = RenderPipeline(ae, enc, dec, None).to(device)
+    for q in disc.parameters():          # generator step: the discriminator is applied, not updated (model_wrapper.py:412-440)
+        q.requires_grad_(False)
+    pipe = RenderPipeline(ae, enc, dec, disc).to(device)
     # only the VAE *decoder* side is on the path (autoencoder.encode is never called)
     params = [p for n, p in pipe.named_parameters()
               if not (n.startswith("autoencoder.model.encoder") or n.startswith("autoencoder.model.quant_conv"))
-              and not n.startswith("autoencoder.skip_convs.4")]
+              and not n.startswith("autoencoder.skip_convs.4") and not n.startswith("discriminator.")]
     return pipe, params
 
 
@@ -381,7 +386,7 @@ def run_full(args, cfg):
 
     def fwd_bwd(inp):
         flat_grad.zero_()
-        out = pipe(unflatten_batch(inp), global_step=0)
+        out = pipe(unflatten_batch(inp), global_step=0, discriminate=True)
         loss = full_loss(out, inp["target.image"])
         loss.backward()
         return {"loss": loss.detach()}
@@ -588,16 +593,18 @@ def cpu_baseline_full(cfg, min_seconds=10.0, max_steps=1, threads=0):
     oracle.build()
     OracleGaussianRasterizer.parallel_backward = True
     torch.manual_seed(0)
-    ae, enc, _, _ = build_modules(with_discriminator=False)
+    ae, enc, _, disc = build_modules(with_discriminator=True)
     for c in ae.skip_convs:
         torch.nn.init.normal_(c.weight, std=0.02)
-    pipe = RenderPipeline(ae, enc, DecoderSplattingCPU(n_threads=threads), None)
+    for q in disc.parameters():
+        q.requires_grad_(False)
+    pipe = RenderPipeline(ae, enc, DecoderSplattingCPU(n_threads=threads), disc)
     small = dict(cfg, B=1, V_t=1)
     batch = make_full_batch(small, 0)
     steps, t0 = 0, time.perf_counter()
     while True:
         pipe.zero_grad(set_to_none=True)
-        out = pipe(batch, global_step=0)
+        out = pipe(batch, global_step=0, discriminate=True)
         full_loss(out, batch["target"]["image"]).backward()
         steps += 1
         el = time.perf_counter() - t0
@@ -812,7 +819,10 @@ def main():
     ap.add_argument("--gaussians", type=int, default=CFG["G"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--workload", default="full", choices=["full", "splat"])
+    ap.add_argument("--resolution", type=int, default=256, help="image side (BASELINE configs[4] stress: 512)")
     args = ap.parse_args()
+    global H, W
+    H = W = args.resolution
     cfg = dict(CFG, V_t=args.target_views, G=args.gaussians, B=args.batch, workload=args.workload)
     if args.impl == "reference":
         run_reference(args, cfg)

@@ -12,7 +12,7 @@ if len(sys.argv) > 1 and sys.argv[1] == 'tf32':
 def step():
     for p in params: p.grad = None
     with record_function("FWD"):
-        out = pipe(bench.unflatten_batch(flat), 0)
+        out = pipe(bench.unflatten_batch(flat), 0, discriminate=True)
         loss = bench.full_loss(out, flat['target.image'])
     with record_function("BWD"):
         loss.backward()
@@ -39,7 +39,7 @@ for n, m in mods.items():
     a, b = hook(n); hs += [m.register_forward_pre_hook(a), m.register_forward_hook(b)]
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
 for p in params: p.grad = None
-e0.record(); out = pipe(bench.unflatten_batch(flat), 0); loss = bench.full_loss(out, flat['target.image']); e1.record(); loss.backward(); e2.record()
+e0.record(); out = pipe(bench.unflatten_batch(flat), 0, discriminate=True); loss = bench.full_loss(out, flat['target.image']); e1.record(); loss.backward(); e2.record()
 torch.cuda.synchronize()
 print(f"FWD {e0.elapsed_time(e1):.1f} ms  BWD {e1.elapsed_time(e2):.1f} ms")
 for n, v in times.items():
