@@ -59,6 +59,16 @@ LS_API int ls_sq_attention_forward(const float* q, const float* kv, float* out, 
 LS_API int ls_sq_attention_backward(const float* q, const float* kv, const float* p, const float* dout, float* dq,
                                     float* dkv, int32_t R, int32_t H, int32_t S, int32_t D, float scale, void* stream);
 
+/* Weight-absorbed form of the same attention: with one query per ray and bias-free to_q / to_kv,
+ *   score = (W_k,h^T q_h) . z_j   and   out_h = W_v,h (sum_j p_{h,j} z_j),
+ * so the kv tensor (S * 2*H*D floats per ray) is never materialised.  qt (R, H, 128) absorbed queries, z (R, S, 128) raw
+ * samples, zbar (R, H, 128) probability-weighted sample means, p (R, H, S).  The per-head 128x128 GEMMs around these
+ * kernels (q -> qt, zbar -> out, and their gradients) are ls_gemm_tf32 calls made by the caller. */
+LS_API int ls_absorbed_attention_forward(const float* qt, const float* z, float* zbar, float* p, int32_t R, int32_t H,
+                                         int32_t S, int32_t Dz, float scale, void* stream);
+LS_API int ls_absorbed_attention_backward(const float* qt, const float* z, const float* p, const float* dzbar, float* dqt,
+                                          float* dz, int32_t R, int32_t H, int32_t S, int32_t Dz, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,7 +72,8 @@ STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL 
 BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
 ABI_VERSION = 1
 EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
-           "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward")
+           "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
+           "ls_absorbed_attention_forward", "ls_absorbed_attention_backward")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -109,6 +110,10 @@ def load() -> C.CDLL:
     lib.ls_sq_attention_forward.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
     lib.ls_sq_attention_backward.restype = C.c_int
     lib.ls_sq_attention_backward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
+    lib.ls_absorbed_attention_forward.restype = C.c_int
+    lib.ls_absorbed_attention_forward.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
+    lib.ls_absorbed_attention_backward.restype = C.c_int
+    lib.ls_absorbed_attention_backward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -96,7 +96,137 @@ __global__ void __launch_bounds__(256) k_sq_attn_bwd(const float* __restrict__ q
     *reinterpret_cast<float4*>(dq + qoff) = dq4;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-absorbed variant.  With one query per ray and bias-free projections,
+//     score_{h,j} = q_h . (W_k,h z_j) = (W_k,h^T q_h) . z_j          out_h = sum_j p_{h,j} W_v,h z_j = W_v,h (sum_j p_{h,j} z_j)
+// so the 1 048 576 x 128 -> 1024 `to_kv` GEMM (137 GMAC and a 4.3 GB kv tensor per layer, epipolar_transformer.py:127-135
+// + attention.py:60-61) is never formed: the kernels below attend over the raw 128-wide samples z with absorbed queries
+// qt_h = W_k,h^T q_h and return zbar_h = sum_j p_{h,j} z_j; the (tiny) per-head GEMMs around them run on ls_gemm_tf32.
+// One warp per ray; all heads share each z row, which is read from HBM exactly once per pass.
+constexpr int kMaxHeads = 8;
+
+__global__ void __launch_bounds__(256) k_absorbed_attn_fwd(const float* __restrict__ qt, const float* __restrict__ z,
+                                                           float* __restrict__ zbar, float* __restrict__ p, int R, int H,
+                                                           int S, float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    float4 q4[kMaxHeads];
+    float score[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+        score[h] = -INFINITY;
+        if (h < H) q4[h] = *reinterpret_cast<const float4*>(qt + ((size_t)r * H + h) * D + 4 * lane);
+    }
+    const float* zr = z + (size_t)r * S * D + 4 * lane;
+    for (int j = 0; j < S; ++j) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+            if (h < H) {
+                const float s = warp_sum(dot4(q4[h], z4)) * scale;
+                if (lane == j) score[h] = s;
+            }
+    }
+    float prob[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h)
+        if (h < H) {
+            const float m = warp_max(score[h]);
+            const float e = lane < S ? __expf(score[h] - m) : 0.f;
+            prob[h] = e / warp_sum(e);
+            if (lane < S) p[((size_t)r * H + h) * S + lane] = prob[h];
+        }
+    float4 acc[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < S; ++j) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+            if (h < H) {
+                const float pj = __shfl_sync(0xffffffffu, prob[h], j);
+                acc[h].x = fmaf(pj, z4.x, acc[h].x); acc[h].y = fmaf(pj, z4.y, acc[h].y);
+                acc[h].z = fmaf(pj, z4.z, acc[h].z); acc[h].w = fmaf(pj, z4.w, acc[h].w);
+            }
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h)
+        if (h < H) *reinterpret_cast<float4*>(zbar + ((size_t)r * H + h) * D + 4 * lane) = acc[h];
+}
+
+__global__ void __launch_bounds__(256) k_absorbed_attn_bwd(const float* __restrict__ qt, const float* __restrict__ z,
+                                                           const float* __restrict__ p, const float* __restrict__ dzbar,
+                                                           float* __restrict__ dqt, float* __restrict__ dz, int R, int H,
+                                                           int S, float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    float4 q4[kMaxHeads], g4[kMaxHeads], dq4[kMaxHeads];
+    float prob[kMaxHeads], dp[kMaxHeads], ds[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+        dp[h] = 0.f; prob[h] = 0.f; dq4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h < H) {
+            q4[h] = *reinterpret_cast<const float4*>(qt + ((size_t)r * H + h) * D + 4 * lane);
+            g4[h] = *reinterpret_cast<const float4*>(dzbar + ((size_t)r * H + h) * D + 4 * lane);
+            if (lane < S) prob[h] = p[((size_t)r * H + h) * S + lane];
+        }
+    }
+    const float* zr = z + (size_t)r * S * D + 4 * lane;
+    for (int j = 0; j < S; ++j) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+            if (h < H) {
+                const float v = warp_sum(dot4(g4[h], z4));
+                if (lane == j) dp[h] = v;
+            }
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h)
+        if (h < H) ds[h] = prob[h] * (dp[h] - warp_sum(prob[h] * dp[h])) * scale;
+    float* dzr = dz + (size_t)r * S * D + 4 * lane;
+    for (int j = 0; j < S; ++j) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+            if (h < H) {
+                const float pj = __shfl_sync(0xffffffffu, prob[h], j);
+                const float dsj = __shfl_sync(0xffffffffu, ds[h], j);
+                o.x += pj * g4[h].x + dsj * q4[h].x; o.y += pj * g4[h].y + dsj * q4[h].y;
+                o.z += pj * g4[h].z + dsj * q4[h].z; o.w += pj * g4[h].w + dsj * q4[h].w;
+                dq4[h].x = fmaf(dsj, z4.x, dq4[h].x); dq4[h].y = fmaf(dsj, z4.y, dq4[h].y);
+                dq4[h].z = fmaf(dsj, z4.z, dq4[h].z); dq4[h].w = fmaf(dsj, z4.w, dq4[h].w);
+            }
+        *reinterpret_cast<float4*>(dzr + (size_t)j * D) = o;
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h)
+        if (h < H) *reinterpret_cast<float4*>(dqt + ((size_t)r * H + h) * D + 4 * lane) = dq4[h];
+}
+
 }  // namespace lsa
+
+extern "C" LS_API int ls_absorbed_attention_forward(const float* qt, const float* z, float* zbar, float* p, int32_t R, int32_t H,
+                                                    int32_t S, int32_t Dz, float scale, void* stream) {
+    if (Dz != lsa::D) return ls_fail("absorbed attention: sample width %d != 128", Dz);
+    if (S < 1 || S > 32 || H < 1 || H > lsa::kMaxHeads) return ls_fail("absorbed attention: S=%d (1..32) H=%d (1..8)", S, H);
+    if (R <= 0) return 0;
+    lsa::k_absorbed_attn_fwd<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, zbar, p, R, H, S, scale);
+    return ls_check_cuda("k_absorbed_attn_fwd");
+}
+
+extern "C" LS_API int ls_absorbed_attention_backward(const float* qt, const float* z, const float* p, const float* dzbar,
+                                                     float* dqt, float* dz, int32_t R, int32_t H, int32_t S, int32_t Dz,
+                                                     float scale, void* stream) {
+    if (Dz != lsa::D) return ls_fail("absorbed attention: sample width %d != 128", Dz);
+    if (S < 1 || S > 32 || H < 1 || H > lsa::kMaxHeads) return ls_fail("absorbed attention: S=%d (1..32) H=%d (1..8)", S, H);
+    if (R <= 0) return 0;
+    lsa::k_absorbed_attn_bwd<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, p, dzbar, dqt, dz, R, H, S, scale);
+    return ls_check_cuda("k_absorbed_attn_bwd");
+}
 
 extern "C" LS_API int ls_sq_attention_forward(const float* q, const float* kv, float* out, float* p, int32_t R, int32_t H,
                                               int32_t S, int32_t Dh, float scale, void* stream) {

@@ -31,10 +31,14 @@ class Attention(nn.Module):
             q, k, v = self.to_qkv(x).chunk(3, dim=-1)
         else:
             q = self.to_q(x)
+            # Epipolar cross-attention: one query per ray.  (1) weight-absorbed form: to_kv is folded into the query and
+            # the output projection of the attended samples, the 4.3 GB kv tensor is never formed; (2) else the fused
+            # single-query kernel on kv; (3) else (hooks on `attend` for the visualiser, CPU, odd shapes) the explicit path.
+            plain = x.shape[1] == 1 and not self.attend._forward_hooks and self.to_kv.bias is None
+            if plain and fused.ABSORB and fused.absorbed_supported(q[:, 0], z, self.to_kv.weight, self.heads):
+                return self.to_out(fused.absorbed_cross_attention(q[:, 0], z, self.to_kv.weight, self.heads, self.scale)[:, None])
             kv = self.to_kv(z)
-            # epipolar cross-attention: one query per ray -> fused sm_100a kernel (no chunk/rearrange copies of kv,
-            # no tiny batched GEMMs); falls back to the explicit path when something hooks `attend` (visualiser)
-            if x.shape[1] == 1 and not self.attend._forward_hooks and fused.supported(q[:, 0], kv, self.heads):
+            if plain and fused.supported(q[:, 0], kv, self.heads):
                 return self.to_out(fused.single_query_attention(q[:, 0], kv, self.heads, self.scale)[:, None])
             k, v = kv.chunk(2, dim=-1)
         split = lambda t: t.unflatten(-1, (self.heads, -1)).transpose(1, 2)      # b n (h d) -> b h n d

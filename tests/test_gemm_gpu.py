@@ -120,3 +120,30 @@ def test_fused_single_query_attention_matches_reference_math(cuda):
     d2 = torch.matmul(split(q2.double()[:, None]), split(k2).transpose(-1, -2)) * 0.1
     r2 = torch.matmul(d2.softmax(dim=-1), split(v2)).transpose(1, 2).flatten(-2)[:, 0]
     assert (o2.double() - r2).abs().max().item() < 1e-5
+
+
+def test_absorbed_cross_attention_equals_explicit_attention(cuda):
+    """Folding to_kv into the query / output side is exact algebra: compare with softmax(q (W_k z)^T) (W_v z) in float64,
+    forward and all three gradients (q, z, W_kv)."""
+    from latentsplat_b200.attention import absorbed_cross_attention
+    R, H, S, D = 1500, 4, 32, 128
+    g = torch.Generator(cuda).manual_seed(4)
+    q = torch.randn(R, H * D, device=cuda, generator=g, requires_grad=True)
+    z = torch.randn(R, S, 128, device=cuda, generator=g, requires_grad=True)
+    w = (torch.randn(2 * H * D, 128, device=cuda, generator=g) / 128 ** 0.5).requires_grad_(True)
+    wt = torch.randn(R, H * D, device=cuda, generator=g)
+    out = absorbed_cross_attention(q, z, w, H, D ** -0.5)
+    (out * wt).sum().backward()
+    got = [out.detach().double(), q.grad.double(), z.grad.double(), w.grad.double()]
+    q.grad = z.grad = w.grad = None
+    qd, zd, wd = q.double(), z.double(), w.double()
+    k, v = (zd @ wd.T).chunk(2, dim=-1)
+    split = lambda t: t.unflatten(-1, (H, D)).transpose(1, 2)
+    dots = torch.matmul(split(qd[:, None]), split(k).transpose(-1, -2)) * D ** -0.5
+    ref = torch.matmul(dots.softmax(dim=-1), split(v)).transpose(1, 2).flatten(-2)[:, 0]
+    (ref * wt.double()).sum().backward()
+    want = [ref.detach(), q.grad.double(), z.grad.double(), w.grad.double()]
+    for a, b, name in zip(got, want, ("out", "dq", "dz", "dW_kv")):
+        err = (a - b).abs().max().item()
+        assert err <= 2e-2 * b.abs().max().item(), f"{name}: {err:.3e} vs {b.abs().max().item():.3e}"     # TF32 GEMMs
+        assert (a - b).abs().mean().item() <= 2e-3 * b.abs().mean().item() + 1e-6, name
