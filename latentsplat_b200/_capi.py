@@ -65,6 +65,11 @@ class LsGemmArgs(C.Structure):
     ]
 
 
+class LsEpipolarGather(C.Structure):     # include/ls_epipolar.h
+    _fields_ = [(n, C.c_int32) for n in ("rows", "samples", "images", "height", "width", "channels", "encoding_width")] + \
+               [(n, C.c_void_p) for n in ("xy", "depth", "image", "valid")]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
@@ -73,7 +78,8 @@ BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
 ABI_VERSION = 1
 EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
-           "ls_absorbed_attention_forward", "ls_absorbed_attention_backward")
+           "ls_absorbed_attention_forward", "ls_absorbed_attention_backward",
+           "ls_epipolar_gather_forward", "ls_epipolar_gather_backward")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -114,6 +120,10 @@ def load() -> C.CDLL:
     lib.ls_absorbed_attention_forward.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
     lib.ls_absorbed_attention_backward.restype = C.c_int
     lib.ls_absorbed_attention_backward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_float, C.c_void_p]
+    lib.ls_epipolar_gather_forward.restype = C.c_int
+    lib.ls_epipolar_gather_forward.argtypes = [C.POINTER(LsEpipolarGather)] + [C.c_void_p] * 5
+    lib.ls_epipolar_gather_backward.restype = C.c_int
+    lib.ls_epipolar_gather_backward.argtypes = [C.POINTER(LsEpipolarGather)] + [C.c_void_p] * 5
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

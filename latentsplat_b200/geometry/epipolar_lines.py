@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 from torch import Tensor
 
-from .projection import get_world_rays, homogenize_points, homogenize_vectors, intersect_rays, project_camera_space
+from .projection import get_world_rays, homogenize_points, homogenize_vectors, intersect_rays, matvec, project_camera_space
 
 
 def _is_in_bounds(xy: Tensor, epsilon: float = 1e-6) -> Tensor:
@@ -68,8 +68,8 @@ def project_rays(origins: Tensor, directions: Tensor, extrinsics: Tensor, intrin
     """World rays -> the image-space segment they trace in the camera (extrinsics, intrinsics)
     (epipolar_lines.py:157-251).  Returns t_min, t_max, xy_min, xy_max, overlaps_image."""
     world_to_cam = torch.linalg.inv_ex(extrinsics, check_errors=False).inverse
-    origins = torch.einsum("...ij,...j->...i", world_to_cam, homogenize_points(origins))[..., :3]
-    directions = torch.einsum("...ij,...j->...i", world_to_cam, homogenize_vectors(directions))[..., :3]
+    origins = matvec(world_to_cam, homogenize_points(origins))[..., :3]
+    directions = matvec(world_to_cam, homogenize_vectors(directions))[..., :3]
 
     frame = (_intersect_image_coordinate(intrinsics, origins, directions, 0, 0.0),
              _intersect_image_coordinate(intrinsics, origins, directions, 0, 1.0),

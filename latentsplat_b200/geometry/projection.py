@@ -20,8 +20,15 @@ def homogenize_vectors(vectors: Tensor) -> Tensor:
     return torch.cat([vectors, torch.zeros_like(vectors[..., :1])], dim=-1)
 
 
+def matvec(matrix: Tensor, vector: Tensor) -> Tensor:
+    """einsum("...ij,...j->...i") written as broadcast multiply + sum over the (3 or 4 wide) last axis: on CUDA the
+    einsum lands on a batched GEMM of ~1 M tiny matrices (1.8 ms per call at the bench shape), this on one fused-size
+    elementwise pass."""
+    return (matrix * vector[..., None, :]).sum(dim=-1)
+
+
 def transform_rigid(homogeneous_coordinates: Tensor, transformation: Tensor) -> Tensor:
-    return torch.einsum("...ij,...j->...i", transformation, homogeneous_coordinates)
+    return matvec(transformation, homogeneous_coordinates)
 
 
 def transform_cam2world(homogeneous_coordinates: Tensor, extrinsics: Tensor) -> Tensor:
@@ -37,7 +44,7 @@ def project_camera_space(points: Tensor, intrinsics: Tensor, epsilon: float = to
     """Pinhole projection of camera-space points to normalised image coordinates (projection.py:50-59)."""
     points = points / (points[..., -1:] + epsilon)
     points = points.nan_to_num(posinf=infinity, neginf=-infinity)
-    points = torch.einsum("...ij,...j->...i", intrinsics, points)
+    points = matvec(intrinsics, points)
     return points[..., :-1]
 
 
@@ -50,7 +57,7 @@ def project(points: Tensor, extrinsics: Tensor, intrinsics: Tensor,
 def unproject(coordinates: Tensor, z: Tensor, intrinsics: Tensor) -> Tensor:
     """Normalised image coordinates + depth -> camera-space points (projection.py:79-95)."""
     inv = torch.linalg.inv_ex(intrinsics, check_errors=False).inverse
-    rays = torch.einsum("...ij,...j->...i", inv, homogenize_points(coordinates))
+    rays = matvec(inv, homogenize_points(coordinates))
     return rays * z[..., None]
 
 

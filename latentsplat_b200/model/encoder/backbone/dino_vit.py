@@ -27,6 +27,42 @@ class Mlp(nn.Module):
         return self.fc2(self.act(self.fc1(x)))
 
 
+class _Bf16AttentionCore(torch.autograd.Function):
+    """softmax(q k^T scale) v on ONE bf16 copy of the packed fp32 qkv projection, through the library flash kernel.
+
+    Keeps the casts / layout shuffles around the library call to the minimum: forward = one fp32->bf16 cast of
+    (B, N, 3C) + one bf16->fp32 cast of the output; backward = one cast of the incoming gradient + three strided
+    cast-copies of dq, dk, dv straight into the packed (B, N, 3, H, D) gradient (autograd's own route through
+    permute / unbind / .to() costs a zero-fill and an add per tensor on top of that)."""
+
+    @staticmethod
+    def forward(ctx, qkv: Tensor, heads: int, scale: float) -> Tensor:
+        B, N, C3 = qkv.shape
+        D = C3 // 3 // heads
+        packed = qkv.to(torch.bfloat16).view(B, N, 3, heads, D)
+        q, k, v = (packed[:, :, i].transpose(1, 2) for i in range(3))                 # (B, H, N, D) strided views
+        if ctx.needs_input_grad[0]:
+            q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
+            with torch.enable_grad():
+                out = F.scaled_dot_product_attention(q, k, v, scale=scale)
+            ctx.inner = (q, k, v, out)
+        else:
+            out = F.scaled_dot_product_attention(q, k, v, scale=scale)
+        return out.detach().transpose(1, 2).reshape(B, N, heads * D).to(qkv.dtype)
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        q, k, v, out = ctx.inner
+        ctx.inner = None
+        B, H, N, D = q.shape
+        g = grad.to(torch.bfloat16).view(B, N, H, D).transpose(1, 2)
+        dq, dk, dv = torch.autograd.grad(out, (q, k, v), g)
+        packed = torch.empty((B, N, 3, H, D), dtype=grad.dtype, device=grad.device)
+        for i, d in enumerate((dq, dk, dv)):
+            packed[:, :, i].copy_(d.transpose(1, 2))
+        return packed.view(B, N, 3 * H * D), None, None
+
+
 class Attention(nn.Module):
     def __init__(self, dim: int, num_heads: int):
         super().__init__()
@@ -37,13 +73,12 @@ class Attention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        qkv = self.qkv(x)
         if x.is_cuda and ATTENTION_BF16:
-            # library flash-attention on bf16 copies of q/k/v (fp32 SDPA lands on an sm_80 SIMT kernel: 30 ms/step)
-            q, k, v = (t.to(torch.bfloat16) for t in (qkv[0], qkv[1], qkv[2]))
-            x = F.scaled_dot_product_attention(q, k, v, scale=self.scale).to(qkv.dtype)
-        else:
-            x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
+            # library flash-attention on a bf16 copy of q/k/v (fp32 SDPA lands on an sm_80 SIMT kernel: 30 ms/step)
+            return self.proj(_Bf16AttentionCore.apply(qkv, self.num_heads, self.scale))
+        qkv = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
         return self.proj(x.transpose(1, 2).reshape(B, N, C))
 
 

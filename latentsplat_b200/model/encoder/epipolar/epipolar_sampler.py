@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 from dataclasses import dataclass
+from typing import Optional
 
 import torch
 import torch.nn.functional as F
@@ -15,7 +16,7 @@ from ....misc.heterogeneous_pairings import generate_heterogeneous_index, genera
 
 @dataclass
 class EpipolarSampling:
-    features: Tensor        # (batch, view, other_view, ray, sample, channel)
+    features: Optional[Tensor]   # (batch, view, other_view, ray, sample, channel); None when the caller gathers (fused path)
     valid: Tensor           # (batch, view, other_view, ray) bool
     xy_ray: Tensor          # (batch, view, ray, 2)
     xy_sample: Tensor       # (batch, view, other_view, ray, sample, 2)
@@ -35,7 +36,10 @@ class EpipolarSampler(nn.Module):
         self.register_buffer("transpose_v", t_v, persistent=False)
         self.register_buffer("transpose_ov", t_ov, persistent=False)
 
-    def forward(self, images: Tensor, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor) -> EpipolarSampling:
+    def forward(self, images: Tensor, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                gather: bool = True) -> EpipolarSampling:
+        """`gather=False` returns the sampling geometry only (`features=None`): the caller fuses the bilinear gather, the
+        overlap mask and the depth encoding into one kernel (latentsplat_b200.epipolar_gather) using `image_index`."""
         b, v, c, h, w = images.shape
         device = images.device
         xy_ray, origins, directions = self.generate_image_rays(images, extrinsics, intrinsics)
@@ -48,6 +52,12 @@ class EpipolarSampler(nn.Module):
         xy_min = (projection["xy_min"].nan_to_num(posinf=0, neginf=0) * overlaps[..., None])[..., None, :]
         xy_max = (projection["xy_max"].nan_to_num(posinf=0, neginf=0) * overlaps[..., None])[..., None, :]
         xy_sample = xy_min + sample_depth * (xy_max - xy_min)
+        half_span = 0.5 / s
+        if not gather:
+            return EpipolarSampling(features=None, valid=overlaps, xy_ray=xy_ray, xy_sample=xy_sample,
+                                    xy_sample_near=xy_min + (sample_depth - half_span) * (xy_max - xy_min),
+                                    xy_sample_far=xy_min + (sample_depth + half_span) * (xy_max - xy_min),
+                                    origins=origins, directions=directions)
 
         # Before the "transpose", dim 1 is the view the ray is cast from; sampling needs the view drawn from.
         samples = self.transpose(xy_sample)
@@ -58,7 +68,6 @@ class EpipolarSampler(nn.Module):
         samples = self.transpose(samples)
         samples = samples * overlaps[..., None, None]                              # zero out invalid samples
 
-        half_span = 0.5 / s
         return EpipolarSampling(features=samples, valid=overlaps, xy_ray=xy_ray, xy_sample=xy_sample,
                                 xy_sample_near=xy_min + (sample_depth - half_span) * (xy_max - xy_min),
                                 xy_sample_far=xy_min + (sample_depth + half_span) * (xy_max - xy_min),
@@ -71,6 +80,17 @@ class EpipolarSampler(nn.Module):
         xy = xy.reshape(h * w, 2)
         origins, directions = get_world_rays(xy, extrinsics[:, :, None], intrinsics[:, :, None])
         return xy[None, None].expand(b, v, -1, -1), origins, directions
+
+    def image_index(self, b: int, rays: int) -> Tensor:
+        """(b * v * (v-1) * rays) int32: flattened (scene * views + other view) feature map each epipolar line lies in --
+        what the two `transpose` shuffles around grid_sample express (:96-110)."""
+        key = (b, rays)
+        if getattr(self, "_image_index_key", None) != key or self._image_index.device != self.index_v.device:
+            v = self.index_v.shape[0]
+            idx = torch.arange(b, device=self.index_v.device)[:, None, None] * v + self.index_v[None]        # (b, v, ov)
+            self._image_index = idx[..., None].expand(b, v, v - 1, rays).reshape(-1).to(torch.int32).contiguous()
+            self._image_index_key = key
+        return self._image_index
 
     def transpose(self, x: Tensor) -> Tensor:
         b, v, ov = x.shape[:3]

@@ -21,6 +21,7 @@ from .conversions import depth_to_relative_disparity
 from .epipolar_sampler import EpipolarSampler, EpipolarSampling
 from .image_self_attention import ImageSelfAttention, ImageSelfAttentionCfg
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200 import epipolar_gather as fused_gather
 
 
 @dataclass
@@ -75,7 +76,10 @@ class EpipolarTransformer(nn.Module):
             features = self.downscaler(features.flatten(0, 1)).unflatten(0, (b, v))
         hd, wd = h // self.cfg.downscale, w // self.cfg.downscale
 
-        sampling: EpipolarSampling = self.epipolar_sampler(features, extrinsics, intrinsics, near, far)
+        encoding = self.depth_encoding[1] if self.cfg.num_octaves > 0 else None
+        fused = fused_gather.supported(features, c, self.cfg.num_samples, None if encoding is None else encoding.weight)
+        sampling: EpipolarSampling = self.epipolar_sampler(features, extrinsics, intrinsics, near, far, gather=not fused)
+        depths = None
         if self.cfg.num_octaves > 0:
             collect = self.epipolar_sampler.collect
             depths = get_depth(sampling.origins[:, :, None, :, None], sampling.directions[:, :, None, :, None],
@@ -84,14 +88,24 @@ class EpipolarTransformer(nn.Module):
             # clip: context views may be extremely close together or oriented the same way (:113-116)
             depths = depths.maximum(near[..., None, None, None]).minimum(far[..., None, None, None])
             depths = depth_to_relative_disparity(depths, near[..., None, None, None], far[..., None, None, None])
-            q = sampling.features + self.depth_encoding(depths[..., None])
-        else:
+            if not fused:
+                q = sampling.features + self.depth_encoding(depths[..., None])
+        elif not fused:
             q = sampling.features
 
         # NB the reference's names: `kv` are the per-pixel query tokens x, `q` the sampled key/value tokens z.
-        kv = features.permute(0, 1, 3, 4, 2).reshape(b * v * hd * wd, 1, c)
-        assert q.shape[2] == 1, "the reference's rearrange 'b v () r s c' admits exactly one other view"
-        z = q.reshape(b * v * hd * wd, -1, c)                     # b v () r s c -> (b v r) s c
+        channels_last = features.permute(0, 1, 3, 4, 2).contiguous()          # (b, v, hd, wd, c): query tokens AND gather source
+        kv = channels_last.reshape(b * v * hd * wd, 1, c)
+        assert v == 2, "the reference's rearrange 'b v () r s c' admits exactly one other view"
+        if fused:
+            # one sm_100a kernel: bilinear gather on the epipolar line in the other view * overlap mask + depth encoding
+            z = fused_gather.epipolar_gather(
+                channels_last.reshape(b * v, hd, wd, c), sampling.xy_sample.reshape(b * v * hd * wd, -1, 2),
+                None if depths is None else depths.expand(sampling.xy_sample.shape[:-1]).reshape(b * v * hd * wd, -1),
+                self.epipolar_sampler.image_index(b, hd * wd), sampling.valid.reshape(-1).to(features.dtype),
+                None if encoding is None else encoding.weight, None if encoding is None else encoding.bias)
+        else:
+            z = q.reshape(b * v * hd * wd, -1, c)                 # b v () r s c -> (b v r) s c
         features = self.transformer(kv, z, b=b, v=v, h=hd, w=wd)
         features = features.reshape(b, v, hd, wd, c).permute(0, 1, 4, 2, 3)
 

@@ -31,7 +31,13 @@ class FlatGradients:
         self.flat = torch.zeros(self.numel, device=dev, dtype=dtype)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # same strides as the parameter (dense layouts only, e.g. contiguous or channels_last) -- fused optimizers
+            # require param / grad layouts to match
+            seg = self.flat[off:off + p.numel()]
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            if not dense:
+                raise ValueError("FlatGradients needs dense (contiguous or channels_last) parameters")
+            p.grad = seg.as_strided(p.shape, p.stride())
             off += p.numel()
 
     def zero(self) -> None:

@@ -147,3 +147,99 @@ def test_absorbed_cross_attention_equals_explicit_attention(cuda):
         err = (a - b).abs().max().item()
         assert err <= 2e-2 * b.abs().max().item(), f"{name}: {err:.3e} vs {b.abs().max().item():.3e}"     # TF32 GEMMs
         assert (a - b).abs().mean().item() <= 2e-3 * b.abs().mean().item() + 1e-6, name
+
+
+@pytest.mark.parametrize("with_encoding", [True, False])
+def test_epipolar_gather_matches_grid_sample_path(cuda, with_encoding):
+    """ls_epipolar_gather_* == index -> F.grid_sample(bilinear, zeros, align_corners=False) -> mask (+ Linear(PE(depth)))
+    (epipolar_sampler.py:96-112, epipolar_transformer.py:121-122), forward and the three gradients."""
+    import torch.nn.functional as F
+    from latentsplat_b200.epipolar_gather import epipolar_gather
+    from latentsplat_b200.model.encodings.positional_encoding import PositionalEncoding
+    g = torch.Generator(cuda).manual_seed(11)
+    images, H, W, rows, S = 6, 16, 12, 700, 32
+    feat = torch.randn(images, H, W, 128, device=cuda, generator=g, requires_grad=True)
+    xy = torch.rand(rows, S, 2, device=cuda, generator=g) * 1.4 - 0.2           # some samples fall outside the image
+    xy[5, 3] = 0.0
+    depth = torch.rand(rows, S, device=cuda, generator=g)
+    image = torch.randint(0, images, (rows,), device=cuda, generator=g).to(torch.int32)
+    valid = (torch.rand(rows, device=cuda, generator=g) > 0.2).float()
+    pe = PositionalEncoding(10).to(cuda)
+    weight = (torch.randn(128, 20, device=cuda, generator=g) * 0.3).requires_grad_(True) if with_encoding else None
+    bias = torch.randn(128, device=cuda, generator=g).requires_grad_(True) if with_encoding else None
+    wt = torch.randn(rows, S, 128, device=cuda, generator=g)
+
+    z = epipolar_gather(feat, xy, depth if with_encoding else None, image, valid, weight, bias)
+    (z * wt).sum().backward()
+    got = [z.detach(), feat.grad.clone()] + ([weight.grad.clone(), bias.grad.clone()] if with_encoding else [])
+    feat.grad = None
+    if with_encoding:
+        weight.grad = bias.grad = None
+
+    nchw = feat.permute(0, 3, 1, 2)[image.long()]                                # (rows, C, H, W)
+    ref = F.grid_sample(nchw, (2 * xy - 1)[:, :, None], mode="bilinear", padding_mode="zeros", align_corners=False)
+    ref = ref[..., 0].transpose(1, 2) * valid[:, None, None]
+    if with_encoding:
+        ref = ref + F.linear(pe(depth[..., None]), weight, bias)
+    (ref * wt).sum().backward()
+    want = [ref.detach(), feat.grad] + ([weight.grad, bias.grad] if with_encoding else [])
+    for a, b, name in zip(got, want, ("z", "dfeat", "dW", "db")):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-4 * scale + 1e-5, f"{name}: {(a - b).abs().max().item():.3e} of {scale:.3e}"
+
+
+def test_epipolar_transformer_fused_gather_equals_explicit_path(cuda):
+    """The whole module with the fused gather == the explicit PyTorch sequence (same weights, same inputs)."""
+    from latentsplat_b200 import epipolar_gather as eg
+    from latentsplat_b200.configs import build_modules
+    from helpers import camera
+    torch.manual_seed(0)
+    _, enc, _, _ = build_modules(with_discriminator=True)
+    et = enc.epipolar_transformer.to(cuda)
+    b, v, h, w = 1, 2, 32, 32
+    feats = torch.randn(b, v, 128, h, w, device=cuda)
+    ex = torch.eye(4, device=cuda).repeat(b, v, 1, 1)
+    ex[:, 1, 0, 3] = 0.3
+    ex[:, 1, 2, 3] = 0.05
+    intr = torch.tensor([[0.9, 0, 0.5], [0, 0.9, 0.5], [0, 0, 1.0]], device=cuda).repeat(b, v, 1, 1)
+    near, far = torch.full((b, v), 0.5, device=cuda), torch.full((b, v), 50.0, device=cuda)
+    outs = []
+    for flag in (True, False):
+        eg.ENABLED = flag
+        try:
+            f = feats.clone().requires_grad_(True)
+            y, _ = et(f, ex, intr, near, far)
+            y.square().mean().backward()
+            outs.append((y.detach(), f.grad.clone(), et.depth_encoding[1].weight.grad.clone()))
+            et.zero_grad(set_to_none=True)
+        finally:
+            eg.ENABLED = True
+    for a, b_, name in zip(outs[0], outs[1], ("features", "d input", "d depth_encoding.weight")):
+        err, scale = (a - b_).abs().max().item(), b_.abs().max().item()
+        assert err <= 2e-2 * scale, f"{name}: {err:.3e} of {scale:.3e}"              # TF32 GEMMs on both sides
+        assert (a - b_).abs().mean().item() <= 3e-3 * b_.abs().mean().item() + 1e-7, name
+
+
+def test_dino_bf16_attention_core_matches_fp32_path(cuda):
+    """_Bf16AttentionCore (one packed bf16 copy -> library flash kernel -> packed gradient) against the plain fp32
+    SDPA route of the same block, forward and gradients."""
+    from latentsplat_b200.model.encoder.backbone import dino_vit
+    torch.manual_seed(0)
+    attn = dino_vit.Attention(384, 6).to(cuda)
+    x = torch.randn(3, 197, 384, device=cuda)
+    res = []
+    for flag in (True, False):
+        dino_vit.ATTENTION_BF16 = flag
+        try:
+            xi = x.clone().requires_grad_(True)
+            y = attn(xi)
+            (y * torch.linspace(-1, 1, 384, device=cuda)).sum().backward()
+            res.append((y.detach(), xi.grad.clone(), attn.qkv.weight.grad.clone()))
+            attn.zero_grad(set_to_none=True)
+        finally:
+            dino_vit.ATTENTION_BF16 = True
+    with torch.no_grad():
+        assert torch.isfinite(attn(x)).all()                                     # no-grad path builds no inner graph
+    for a, b, name in zip(res[0], res[1], ("out", "dx", "dWqkv")):
+        err, scale = (a - b).abs().max().item(), b.abs().max().item()
+        assert err <= 3e-2 * scale, f"{name}: {err:.3e} of {scale:.3e}"                # bf16 q/k/v/p
