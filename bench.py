@@ -340,7 +340,10 @@ def build_pipeline(device, seed=0):
     for q in disc.parameters():          # generator step: the discriminator is applied, not updated (model_wrapper.py:412-440)
         q.requires_grad_(False)
     pipe = RenderPipeline(ae, enc, dec, disc).to(device)
-    if os.environ.get("LS_CHANNELS_LAST", "0") == "1":      # experiment switch: NHWC weights/activations for the conv nets
+    cl = os.environ.get("LS_CHANNELS_LAST", "")             # experiment switch: NHWC conv weights/activations
+    if "enc" in cl:
+        pipe.encoder.to(memory_format=torch.channels_last)
+    if "vae" in cl:
         pipe.autoencoder.to(memory_format=torch.channels_last)
         pipe.discriminator.to(memory_format=torch.channels_last)
     # only the VAE *decoder* side is on the path (autoencoder.encode is never called)

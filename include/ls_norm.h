@@ -1,0 +1,43 @@
+/*
+ * ls_norm.h -- C ABI of the fused GroupNorm (+ SiLU) of the VAE decoder, NCHW fp32.
+ *
+ * What it replaces in the reference (Chrixtar/latentsplat): the `GroupNorm(32, C, eps=1e-6) -> SiLU` pairs of the
+ * diffusers VAE decoder the reference wraps (src/model/autoencoder/autoencoder_kl.py:93-124: ResnetBlock2D.norm1/norm2 +
+ * nonlinearity, Decoder.conv_norm_out + conv_act) and the activation-free GroupNorm of the mid-block attention.
+ *
+ *   y = act( (x - mean_g) * rstd_g * gamma_c + beta_c ),   statistics over (C/G channels x H x W) per image
+ *
+ * Conventions as ls_raster.h: device pointers, caller-owned buffers, work enqueued on `stream`, no sync, 0 / negative
+ * return + ls_last_error().  x / y / dy / dx 16-byte aligned, H*W a multiple of 4.
+ */
+#ifndef LS_NORM_H
+#define LS_NORM_H
+
+#include <stdint.h>
+
+#include "ls_raster.h" /* LS_API, ls_last_error */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LsGroupNorm {
+    int32_t N, C, G;      /* images, channels, groups (C % G == 0)                                             */
+    int32_t act;          /* 0: none, 1: SiLU                                                                  */
+    int64_t HW;           /* H * W                                                                             */
+    float eps;
+    const float* x;       /* (N, C, H, W)                                                                      */
+    const float* gamma;   /* (C)                                                                               */
+    const float* beta;    /* (C)                                                                               */
+    double* stats;        /* (N, G, 2): sum, sum of squares -- written by forward, read by backward            */
+} LsGroupNorm;
+
+LS_API int ls_groupnorm_forward(const LsGroupNorm* args, float* y, void* stream /* cudaStream_t */);
+/* dy (N,C,H,W) -> dx (N,C,H,W); sums (N, C, 2) receives per-(image, channel) { sum ds, sum ds*xhat } with
+ * ds = dy * act'(u): d beta_c = sum_n sums[n,c,0], d gamma_c = sum_n sums[n,c,1] (left to the caller: N*C values). */
+LS_API int ls_groupnorm_backward(const LsGroupNorm* args, const float* dy, float* dx, double* sums, void* stream /* cudaStream_t */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS_NORM_H */

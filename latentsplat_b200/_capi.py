@@ -70,6 +70,11 @@ class LsEpipolarGather(C.Structure):     # include/ls_epipolar.h
                [(n, C.c_void_p) for n in ("xy", "depth", "image", "valid")]
 
 
+class LsGroupNorm(C.Structure):          # include/ls_norm.h
+    _fields_ = [("N", C.c_int32), ("C", C.c_int32), ("G", C.c_int32), ("act", C.c_int32), ("HW", C.c_int64), ("eps", C.c_float),
+                ("x", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("stats", C.c_void_p)]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
@@ -79,7 +84,7 @@ ABI_VERSION = 1
 EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
            "ls_absorbed_attention_forward", "ls_absorbed_attention_backward",
-           "ls_epipolar_gather_forward", "ls_epipolar_gather_backward")
+           "ls_epipolar_gather_forward", "ls_epipolar_gather_backward", "ls_groupnorm_forward", "ls_groupnorm_backward")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -124,6 +129,10 @@ def load() -> C.CDLL:
     lib.ls_epipolar_gather_forward.argtypes = [C.POINTER(LsEpipolarGather)] + [C.c_void_p] * 5
     lib.ls_epipolar_gather_backward.restype = C.c_int
     lib.ls_epipolar_gather_backward.argtypes = [C.POINTER(LsEpipolarGather)] + [C.c_void_p] * 5
+    lib.ls_groupnorm_forward.restype = C.c_int
+    lib.ls_groupnorm_forward.argtypes = [C.POINTER(LsGroupNorm), C.c_void_p, C.c_void_p]
+    lib.ls_groupnorm_backward.restype = C.c_int
+    lib.ls_groupnorm_backward.argtypes = [C.POINTER(LsGroupNorm)] + [C.c_void_p] * 4
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -1,0 +1,245 @@
+// ls_norm.cu -- GroupNorm (+ fused SiLU) for NCHW fp32 activations, forward and backward.
+//
+// What it replaces: every `nonlinearity(norm(x))` of the VAE decoder the reference takes from diffusers
+// (/root/reference/src/model/autoencoder/autoencoder_kl.py:93-124 -> diffusers ResnetBlock2D / UNetMidBlock2D /
+// Decoder.conv_norm_out: GroupNorm(32, C, eps=1e-6, affine) followed by SiLU; the attention block's GroupNorm has no
+// activation).  torch runs it as RowwiseMoments (one block per (image, group) row -- 128 blocks for a 134 MB tensor, so
+// latency- not bandwidth-bound) + an elementwise affine pass + a separate SiLU pass, and three more passes backward.
+//
+// Here:   forward  = stats pass (rows split over enough blocks to fill 148 SMs, fp32 partials combined in fp64 atomics)
+//                    + one apply pass  y = silu(a_c x + b_c)                     -> 2 reads + 1 write of x
+//         backward = per-(image, channel) sums of ds and ds * xhat (ds = dy * silu'(u), u recomputed)
+//                    + one apply pass  dx = rstd (gamma ds - (P + xhat Q) / L)    -> 4 reads + 1 write
+// HBM-bound; algorithmic bytes = 12 (fwd) / 20 (bwd) per element.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ls_host.h"
+#include "ls_norm.h"
+
+namespace lsn {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of two values; result valid in thread 0
+__device__ __forceinline__ void block_sum2(float& a, float& b) {
+    __shared__ float sa[kThreads / 32], sb[kThreads / 32];
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sa[w] = a; sb[w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = l < kThreads / 32 ? sa[l] : 0.f;
+        b = l < kThreads / 32 ? sb[l] : 0.f;
+        a = warp_sum(a);
+        b = warp_sum(b);
+    }
+}
+
+__device__ __forceinline__ void mean_rstd(const double* __restrict__ stats, int row, double inv_len, float eps, float& mean,
+                                          float& rstd) {
+    const double m = stats[2 * row] * inv_len;
+    double var = stats[2 * row + 1] * inv_len - m * m;
+    var = var > 0.0 ? var : 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---- forward -------------------------------------------------------------------------------------------------------
+// grid (splits, N*G): block (s, row) reduces elements [s*chunk, (s+1)*chunk) of the row (chunk multiple of 4)
+__global__ void __launch_bounds__(kThreads) k_gn_stats(const float* __restrict__ x, double* __restrict__ stats, long long len,
+                                                       long long chunk) {
+    const long long row = blockIdx.y;
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > len) hi = len;
+    const float4* p = reinterpret_cast<const float4*>(x + row * len + lo);
+    const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;
+    float s = 0.f, ss = 0.f;
+    for (long long i = threadIdx.x; i < n4; i += kThreads) {
+        const float4 v = __ldg(p + i);
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+    }
+    block_sum2(s, ss);
+    if (threadIdx.x == 0 && n4 > 0) {
+        atomicAdd(&stats[2 * row], (double)s);
+        atomicAdd(&stats[2 * row + 1], (double)ss);
+    }
+}
+
+__device__ __forceinline__ float silu(float u) { return u / (1.f + __expf(-u)); }
+
+// grid (splits, N*C): one (image, channel) plane of HW elements per blockIdx.y
+template <int ACT>
+__global__ void __launch_bounds__(kThreads) k_gn_apply(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const double* __restrict__ stats,
+                                                       float* __restrict__ y, int C, int G, long long HW, long long chunk, float eps) {
+    const int plane = blockIdx.y, n = plane / C, c = plane % C, cpg = C / G;
+    float mean, rstd;
+    mean_rstd(stats, n * G + c / cpg, 1.0 / ((double)cpg * (double)HW), eps, mean, rstd);
+    const float a = rstd * gamma[c], b = beta[c] - mean * a;
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > HW) hi = HW;
+    const float4* p = reinterpret_cast<const float4*>(x + (long long)plane * HW + lo);
+    float4* q = reinterpret_cast<float4*>(y + (long long)plane * HW + lo);
+    const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;
+    for (long long i = threadIdx.x; i < n4; i += kThreads) {
+        float4 v = __ldg(p + i);
+        v.x = fmaf(a, v.x, b); v.y = fmaf(a, v.y, b); v.z = fmaf(a, v.z, b); v.w = fmaf(a, v.w, b);
+        if (ACT) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
+        q[i] = v;
+    }
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float dact(float u, float g) {
+    if (!ACT) return g;
+    const float sg = 1.f / (1.f + __expf(-u));
+    return g * sg * fmaf(u, 1.f - sg, 1.f);
+}
+
+// per (image, channel): sums[plane] = { sum ds, sum ds * xhat }
+template <int ACT>
+__global__ void __launch_bounds__(kThreads) k_gn_bwd_sums(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const double* __restrict__ stats, double* __restrict__ sums, int C, int G,
+                                                          long long HW, long long chunk, float eps) {
+    const int plane = blockIdx.y, n = plane / C, c = plane % C, cpg = C / G;
+    float mean, rstd;
+    mean_rstd(stats, n * G + c / cpg, 1.0 / ((double)cpg * (double)HW), eps, mean, rstd);
+    const float gm = gamma[c], bt = beta[c];
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > HW) hi = HW;
+    const float4* p = reinterpret_cast<const float4*>(x + (long long)plane * HW + lo);
+    const float4* g = reinterpret_cast<const float4*>(dy + (long long)plane * HW + lo);
+    const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;
+    float s0 = 0.f, s1 = 0.f;
+    for (long long i = threadIdx.x; i < n4; i += kThreads) {
+        const float4 v = __ldg(p + i), d = __ldg(g + i);
+        const float xs[4] = {v.x, v.y, v.z, v.w}, ds_[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xh = (xs[k] - mean) * rstd;
+            const float ds = dact<ACT>(fmaf(xh, gm, bt), ds_[k]);
+            s0 += ds;
+            s1 = fmaf(ds, xh, s1);
+        }
+    }
+    block_sum2(s0, s1);
+    if (threadIdx.x == 0 && n4 > 0) {
+        atomicAdd(&sums[2 * plane], (double)s0);
+        atomicAdd(&sums[2 * plane + 1], (double)s1);
+    }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kThreads) k_gn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const double* __restrict__ stats, const double* __restrict__ sums,
+                                                           float* __restrict__ dx, int C, int G, long long HW, long long chunk,
+                                                           float eps) {
+    const int plane = blockIdx.y, n = plane / C, c = plane % C, cpg = C / G, grp = c / cpg;
+    float mean, rstd;
+    const double inv_len = 1.0 / ((double)cpg * (double)HW);
+    mean_rstd(stats, n * G + grp, inv_len, eps, mean, rstd);
+    double P = 0.0, Q = 0.0;                          // sum over the group's channels of gamma * {sum ds, sum ds xhat}
+    for (int k = 0; k < cpg; ++k) {
+        const int cc = grp * cpg + k;
+        const double gk = (double)gamma[cc];
+        P += gk * sums[2 * (n * C + cc)];
+        Q += gk * sums[2 * (n * C + cc) + 1];
+    }
+    const float pm = (float)(P * inv_len), qm = (float)(Q * inv_len);
+    const float gm = gamma[c], bt = beta[c];
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > HW) hi = HW;
+    const float4* p = reinterpret_cast<const float4*>(x + (long long)plane * HW + lo);
+    const float4* g = reinterpret_cast<const float4*>(dy + (long long)plane * HW + lo);
+    float4* o = reinterpret_cast<float4*>(dx + (long long)plane * HW + lo);
+    const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;
+    for (long long i = threadIdx.x; i < n4; i += kThreads) {
+        const float4 v = __ldg(p + i), d = __ldg(g + i);
+        const float xs[4] = {v.x, v.y, v.z, v.w}, ds_[4] = {d.x, d.y, d.z, d.w};
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xh = (xs[k] - mean) * rstd;
+            const float ds = dact<ACT>(fmaf(xh, gm, bt), ds_[k]);
+            r[k] = rstd * (fmaf(gm, ds, -pm) - xh * qm);
+        }
+        o[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+static int check(const LsGroupNorm* a) {
+    if (!a) return ls_fail("groupnorm: args is NULL");
+    if (a->N < 0 || a->C < 1 || a->G < 1 || a->HW < 1 || a->C % a->G) return ls_fail("groupnorm: bad sizes N=%d C=%d G=%d HW=%lld", a->N, a->C, a->G, (long long)a->HW);
+    if (a->HW % 4) return ls_fail("groupnorm: H*W=%lld must be a multiple of 4 (16-byte vector access)", (long long)a->HW);
+    if (a->act != 0 && a->act != 1) return ls_fail("groupnorm: act=%d (0 none, 1 SiLU)", a->act);
+    if (a->N > 0 && (!a->x || !a->gamma || !a->beta || !a->stats)) return ls_fail("groupnorm: NULL x / gamma / beta / stats");
+    if ((long long)a->N * a->C > 65535LL) return ls_fail("groupnorm: N*C=%lld exceeds the launch grid (65535 planes)", (long long)a->N * a->C);
+    return 0;
+}
+
+// split a row of `len` elements (multiple of 4) over enough blocks that rows*splits ~ 8 blocks per SM
+static void pick_split(long long rows, long long len, int* splits, long long* chunk) {
+    long long want = (148LL * 8 + rows - 1) / rows;
+    const long long max_split = (len + 4095) / 4096;          // at least 4096 elements (16 per thread) per block
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    long long c = (len + want - 1) / want;
+    c = (c + 3) & ~3LL;
+    *chunk = c;
+    *splits = (int)((len + c - 1) / c);
+}
+
+}  // namespace lsn
+
+extern "C" LS_API int ls_groupnorm_forward(const LsGroupNorm* a, float* y, void* stream) {
+    if (int e = lsn::check(a)) return e;
+    if (a->N == 0) return 0;
+    if (!y) return ls_fail("groupnorm forward: y is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long rows = (long long)a->N * a->G, len = (long long)(a->C / a->G) * a->HW;
+    if (cudaMemsetAsync(a->stats, 0, sizeof(double) * 2 * rows, s) != cudaSuccess) return ls_check_cuda("groupnorm memset");
+    int splits; long long chunk;
+    lsn::pick_split(rows, len, &splits, &chunk);
+    lsn::k_gn_stats<<<dim3(splits, (unsigned)rows), lsn::kThreads, 0, s>>>(a->x, a->stats, len, chunk);
+    const long long planes = (long long)a->N * a->C;
+    lsn::pick_split(planes, a->HW, &splits, &chunk);
+    if (a->act) lsn::k_gn_apply<1><<<dim3(splits, (unsigned)planes), lsn::kThreads, 0, s>>>(a->x, a->gamma, a->beta, a->stats, y, a->C, a->G, a->HW, chunk, a->eps);
+    else lsn::k_gn_apply<0><<<dim3(splits, (unsigned)planes), lsn::kThreads, 0, s>>>(a->x, a->gamma, a->beta, a->stats, y, a->C, a->G, a->HW, chunk, a->eps);
+    return ls_check_cuda("groupnorm forward");
+}
+
+extern "C" LS_API int ls_groupnorm_backward(const LsGroupNorm* a, const float* dy, float* dx, double* sums, void* stream) {
+    if (int e = lsn::check(a)) return e;
+    if (a->N == 0) return 0;
+    if (!dy || !dx || !sums) return ls_fail("groupnorm backward: NULL dy / dx / sums");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long planes = (long long)a->N * a->C;
+    if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * planes, s) != cudaSuccess) return ls_check_cuda("groupnorm memset");
+    int splits; long long chunk;
+    lsn::pick_split(planes, a->HW, &splits, &chunk);
+    const dim3 grid(splits, (unsigned)planes);
+    if (a->act) {
+        lsn::k_gn_bwd_sums<1><<<grid, lsn::kThreads, 0, s>>>(a->x, dy, a->gamma, a->beta, a->stats, sums, a->C, a->G, a->HW, chunk, a->eps);
+        lsn::k_gn_bwd_apply<1><<<grid, lsn::kThreads, 0, s>>>(a->x, dy, a->gamma, a->beta, a->stats, sums, dx, a->C, a->G, a->HW, chunk, a->eps);
+    } else {
+        lsn::k_gn_bwd_sums<0><<<grid, lsn::kThreads, 0, s>>>(a->x, dy, a->gamma, a->beta, a->stats, sums, a->C, a->G, a->HW, chunk, a->eps);
+        lsn::k_gn_bwd_apply<0><<<grid, lsn::kThreads, 0, s>>>(a->x, dy, a->gamma, a->beta, a->stats, sums, dx, a->C, a->G, a->HW, chunk, a->eps);
+    }
+    return ls_check_cuda("groupnorm backward");
+}

@@ -73,7 +73,7 @@ class AutoencoderKL(Autoencoder[AutoencoderKLCfg]):
             if self.cfg.skip_connections:
                 z = z + self.skip_convs[i](interpolate(skip_z, size=z.shape[-2:], mode="bilinear", align_corners=True))
             z = up_block(z)
-        return decoder.conv_out(decoder.conv_act(decoder.conv_norm_out(z)))
+        return decoder.conv_out(decoder.conv_norm_out(z))      # conv_act (SiLU) is fused into conv_norm_out (vae_kl.py)
 
     def decode(self, z: Tensor, skip_z: Optional[Tensor] = None) -> Tensor:
         batch_dims = z.shape[:-3]

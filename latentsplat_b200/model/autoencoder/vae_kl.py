@@ -14,22 +14,23 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200.norm import GroupNorm  # nn.GroupNorm with the following SiLU fused in (sm_100a kernels on CUDA)
 
 
 class ResnetBlock2D(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, groups: int = 32, eps: float = 1e-6):
         super().__init__()
-        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.norm1 = GroupNorm(groups, in_channels, eps=eps, affine=True, act="silu")      # norm + nonlinearity
         self.conv1 = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
-        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.norm2 = GroupNorm(groups, out_channels, eps=eps, affine=True, act="silu")
         self.dropout = nn.Dropout(0.0)
         self.conv2 = nn.Conv2d(out_channels, out_channels, 3, 1, 1)
         self.nonlinearity = nn.SiLU()
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1, 1, 0) if in_channels != out_channels else None
 
     def forward(self, x: Tensor) -> Tensor:
-        h = self.conv1(self.nonlinearity(self.norm1(x)))
-        h = self.conv2(self.dropout(self.nonlinearity(self.norm2(h))))
+        h = self.conv1(self.norm1(x))                       # diffusers: conv1(nonlinearity(norm1(x))), SiLU fused into the norm
+        h = self.conv2(self.dropout(self.norm2(h)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -40,7 +41,7 @@ class Attention(nn.Module):
 
     def __init__(self, channels: int, groups: int = 32, eps: float = 1e-6):
         super().__init__()
-        self.group_norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
+        self.group_norm = GroupNorm(groups, channels, eps=eps, affine=True)
         self.to_q = Linear(channels, channels)
         self.to_k = Linear(channels, channels)
         self.to_v = Linear(channels, channels)
@@ -124,7 +125,7 @@ class Encoder(nn.Module):
             inp, out = out, ch
             self.down_blocks.append(DownEncoderBlock2D(inp, out, layers_per_block, i != len(block_out_channels) - 1, groups))
         self.mid_block = UNetMidBlock2D(block_out_channels[-1], groups)
-        self.conv_norm_out = nn.GroupNorm(groups, block_out_channels[-1], eps=1e-6)
+        self.conv_norm_out = GroupNorm(groups, block_out_channels[-1], eps=1e-6, act="silu")
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(block_out_channels[-1], 2 * latent_channels, 3, padding=1)
 
@@ -133,7 +134,7 @@ class Encoder(nn.Module):
         for blk in self.down_blocks:
             x = blk(x)
         x = self.mid_block(x)
-        return self.conv_out(self.conv_act(self.conv_norm_out(x)))
+        return self.conv_out(self.conv_norm_out(x))        # conv_act (SiLU) is fused into conv_norm_out
 
 
 class Decoder(nn.Module):
@@ -147,7 +148,7 @@ class Decoder(nn.Module):
         for i, ch in enumerate(rev):
             inp, out = out, ch
             self.up_blocks.append(UpDecoderBlock2D(inp, out, layers_per_block + 1, i != len(rev) - 1, groups))
-        self.conv_norm_out = nn.GroupNorm(groups, block_out_channels[0], eps=1e-6)
+        self.conv_norm_out = GroupNorm(groups, block_out_channels[0], eps=1e-6, act="silu")
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(block_out_channels[0], out_channels, 3, padding=1)
 
@@ -155,7 +156,7 @@ class Decoder(nn.Module):
         z = self.mid_block(self.conv_in(z))
         for blk in self.up_blocks:
             z = blk(z)
-        return self.conv_out(self.conv_act(self.conv_norm_out(z)))
+        return self.conv_out(self.conv_norm_out(z))        # conv_act (SiLU) is fused into conv_norm_out
 
 
 class AutoencoderKLModel(nn.Module):

@@ -1,0 +1,71 @@
+"""GroupNorm (+ SiLU) on our sm_100a kernels (libls_raster.so, include/ls_norm.h).
+
+`GroupNorm` is a drop-in `nn.GroupNorm` (same parameters, so diffusers / latentSplat checkpoints load) with an `act`
+attribute ("none" | "silu"): the VAE decoder's `nonlinearity(norm(x))` pairs become one call.  CUDA fp32 NCHW tensors
+take the fused kernels; anything else (CPU host-logic tests) takes `F.group_norm` (+ `F.silu`)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import _capi
+
+ENABLED = True      # set False for A/B comparisons against torch's GroupNorm + SiLU
+
+
+class _GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, groups: int, eps: float, act: int):
+        x = x.contiguous()
+        N, Cn = x.shape[:2]
+        hw = x[0, 0].numel()
+        stats = torch.empty((N, groups, 2), dtype=torch.float64, device=x.device)
+        y = torch.empty_like(x)
+        a = _capi.LsGroupNorm(N, Cn, groups, act, hw, eps, x.data_ptr(), weight.data_ptr(), bias.data_ptr(), stats.data_ptr())
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.load().ls_groupnorm_forward(C.byref(a), y.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "ls_groupnorm_forward")
+        _capi.KERNEL_LAUNCHES[0] += 2
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.cfg = (groups, eps, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, weight, bias, stats = ctx.saved_tensors
+        groups, eps, act = ctx.cfg
+        dy = dy.contiguous()
+        N, Cn = x.shape[:2]
+        sums = torch.empty((N, Cn, 2), dtype=torch.float64, device=x.device)
+        dx = torch.empty_like(x)
+        a = _capi.LsGroupNorm(N, Cn, groups, act, x[0, 0].numel(), eps, x.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                              stats.data_ptr())
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.load().ls_groupnorm_backward(C.byref(a), dy.data_ptr(), dx.data_ptr(), sums.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream), "ls_groupnorm_backward")
+        _capi.KERNEL_LAUNCHES[0] += 2
+        per_channel = sums.sum(dim=0).to(torch.float32)            # (C, 2): d beta, d gamma
+        return dx, per_channel[:, 1].contiguous(), per_channel[:, 0].contiguous(), None, None, None
+
+
+def group_norm(x: Tensor, groups: int, weight: Tensor, bias: Tensor, eps: float, act: str = "none") -> Tensor:
+    if (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x[0, 0].numel() % 4 == 0
+            and weight is not None and bias is not None and x.shape[0] * x.shape[1] <= 65535):
+        return _GroupNormFn.apply(x, weight, bias, groups, eps, 1 if act == "silu" else 0)
+    y = F.group_norm(x, groups, weight, bias, eps)
+    return F.silu(y) if act == "silu" else y
+
+
+class GroupNorm(nn.GroupNorm):
+    """nn.GroupNorm with an optional fused activation (`act="silu"`); parameters `weight`, `bias` as nn.GroupNorm."""
+
+    def __init__(self, num_groups: int, num_channels: int, eps: float = 1e-5, affine: bool = True, act: str = "none"):
+        super().__init__(num_groups, num_channels, eps=eps, affine=affine)
+        assert act in ("none", "silu")
+        self.act = act
+
+    def forward(self, input: Tensor) -> Tensor:
+        return group_norm(input, self.num_groups, self.weight, self.bias, self.eps, self.act)

@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def test_library_exports_every_declared_symbol(lib):
     header = (ROOT / "include" / "ls_raster.h").read_text()
-    both = header + (ROOT / "include" / "ls_gemm.h").read_text() + (ROOT / "include" / "ls_epipolar.h").read_text()
+    both = header + (ROOT / "include" / "ls_gemm.h").read_text() + (ROOT / "include" / "ls_epipolar.h").read_text() + (ROOT / "include" / "ls_norm.h").read_text()
     declared = set(re.findall(r"LS_API\s+[\w\s\*]+?\b(ls_\w+)\s*\(", both))
     from latentsplat_b200 import _capi
     assert declared == set(_capi.EXPORTS), declared
@@ -24,9 +24,9 @@ def test_struct_layouts_match_the_header():
     """Field order of the ctypes mirrors == field order in the header (names), a cheap drift detector."""
     from latentsplat_b200 import _capi
     header = (ROOT / "include" / "ls_raster.h").read_text()
-    header += (ROOT / "include" / "ls_gemm.h").read_text() + (ROOT / "include" / "ls_epipolar.h").read_text()
+    header += (ROOT / "include" / "ls_gemm.h").read_text() + (ROOT / "include" / "ls_epipolar.h").read_text() + (ROOT / "include" / "ls_norm.h").read_text()
     for name in ("LsRasterScene", "LsRasterState", "LsRasterImages", "LsRasterGrads", "LsRasterSizes", "LsGemmArgs",
-                 "LsEpipolarGather"):
+                 "LsEpipolarGather", "LsGroupNorm"):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

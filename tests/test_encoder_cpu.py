@@ -173,7 +173,8 @@ def test_vae_parameter_inventory_and_skip_injection():
             h = h + ae.skip_convs[i](torch.nn.functional.interpolate(skip.flatten(0, 1), size=h.shape[-2:],
                                                                      mode="bilinear", align_corners=True))
             h = up(h)
-        h = (d.conv_out(torch.nn.functional.silu(d.conv_norm_out(h))) + 1) / 2
+        Fn = torch.nn.functional          # conv_norm_out carries the SiLU (fused module): restate both explicitly here
+        h = (d.conv_out(Fn.silu(Fn.group_norm(h, 32, d.conv_norm_out.weight, d.conv_norm_out.bias, 1e-6))) + 1) / 2
         torch.testing.assert_close(c.flatten(0, 1), h)
     post = ae.encode(torch.rand(1, 2, 3, 32, 32))
     assert post.mean.shape == (1, 2, 4, 4, 4) and float(post.logvar.max()) <= 20

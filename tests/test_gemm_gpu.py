@@ -243,3 +243,26 @@ def test_dino_bf16_attention_core_matches_fp32_path(cuda):
     for a, b, name in zip(res[0], res[1], ("out", "dx", "dWqkv")):
         err, scale = (a - b).abs().max().item(), b.abs().max().item()
         assert err <= 3e-2 * scale, f"{name}: {err:.3e} of {scale:.3e}"                # bf16 q/k/v/p
+
+
+@pytest.mark.parametrize("shape,act", [((4, 128, 64, 64), "silu"), ((2, 512, 16, 16), "silu"), ((3, 64, 40, 36), "none"),
+                                       ((2, 256, 1024), "none")])
+def test_groupnorm_silu_matches_torch(cuda, shape, act):
+    """ls_groupnorm_* == F.silu(F.group_norm(x, 32, w, b, 1e-6)) forward and dx / dgamma / dbeta (float64 reference)."""
+    import torch.nn.functional as F
+    from latentsplat_b200.norm import group_norm
+    g = torch.Generator(cuda).manual_seed(7)
+    x = (torch.randn(shape, device=cuda, generator=g) * 2 + 3).requires_grad_(True)        # non-zero mean: tests the fp64 combine
+    w = (torch.rand(shape[1], device=cuda, generator=g) + 0.5).requires_grad_(True)
+    b = torch.randn(shape[1], device=cuda, generator=g).requires_grad_(True)
+    wt = torch.randn(shape, device=cuda, generator=g)
+    y = group_norm(x, 32, w, b, 1e-6, act)
+    (y * wt).sum().backward()
+    got = [y.detach().double(), x.grad.double(), w.grad.double(), b.grad.double()]
+    x.grad = w.grad = b.grad = None
+    ref = F.group_norm(x.double(), 32, w.double(), b.double(), 1e-6)
+    ref = F.silu(ref) if act == "silu" else ref
+    (ref * wt.double()).sum().backward()
+    want = [ref.detach(), x.grad.double(), w.grad.double(), b.grad.double()]
+    for a, r, name in zip(got, want, ("y", "dx", "dgamma", "dbeta")):
+        assert (a - r).abs().max().item() <= 2e-5 * r.abs().max().item() + 1e-6, f"{name}: {(a - r).abs().max().item():.3e}"
