@@ -37,6 +37,15 @@ LS_API int ls_groupnorm_forward(const LsGroupNorm* args, float* y, void* stream 
  * ds = dy * act'(u): d beta_c = sum_n sums[n,c,0], d gamma_c = sum_n sums[n,c,1] (left to the caller: N*C values). */
 LS_API int ls_groupnorm_backward(const LsGroupNorm* args, const float* dy, float* dx, double* sums, void* stream /* cudaStream_t */);
 
+/* LayerNorm over the last dimension (C a multiple of 128, <= 1024), rows x C row-major fp32: nn.LayerNorm of the DINO
+ * ViT blocks (the backbone behind src/model/encoder/backbone/backbone_dino.py:33) and of the epipolar transformer's
+ * PreNorm (src/model/transformer/pre_norm.py:28-35).  mean_rstd (rows, 2) is written by forward and read by backward;
+ * backward ACCUMULATES into dgamma / dbeta (C each; the caller zero-fills them). */
+LS_API int ls_layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
+                                int64_t rows, int32_t C, float eps, void* stream /* cudaStream_t */);
+LS_API int ls_layernorm_backward(const float* x, const float* dy, const float* gamma, const float* mean_rstd, float* dx,
+                                 float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

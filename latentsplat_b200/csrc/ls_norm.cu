@@ -183,6 +183,130 @@ __global__ void __launch_bounds__(kThreads) k_gn_bwd_apply(const float* __restri
     }
 }
 
+// ---- LayerNorm over the last dimension ---------------------------------------------------------------------------
+// One warp per row (C = 128 * VPL floats: VPL float4 per lane held in registers), rows strided over a persistent grid.
+// Replaces nn.LayerNorm in the DINO ViT blocks (C = 768, 8200 token rows, 25 calls per step) and in the epipolar
+// transformer's PreNorm (C = 128, 32 768 rays): torch spends 0.8 ms forward + 2.3 ms backward per step on them
+// (vectorized_layer_norm + layer_norm_grad_input + GammaBetaBackward); here forward is one read + one write, backward
+// two reads + one write, with d gamma / d beta kept in registers across the warp's rows and flushed once per block.
+constexpr int kMaxVPL = 8;
+
+template <int VPL>
+__global__ void __launch_bounds__(kThreads) k_ln_fwd(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ y,
+                                                     float* __restrict__ mean_rstd_out, long long rows, float eps) {
+    constexpr int Cw = VPL * 128;
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 g[VPL], b[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        g[k] = *reinterpret_cast<const float4*>(gamma + k * 128 + 4 * lane);
+        b[k] = *reinterpret_cast<const float4*>(beta + k * 128 + 4 * lane);
+    }
+    for (long long r = warp; r < rows; r += warps) {
+        const float* xr = x + r * Cw + 4 * lane;
+        float4 v[VPL];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            v[k] = __ldg(reinterpret_cast<const float4*>(xr + k * 128));
+            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+        const float mean = warp_sum(s) * (1.f / Cw);
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            v[k].x -= mean; v[k].y -= mean; v[k].z -= mean; v[k].w -= mean;
+            q = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, fmaf(v[k].z, v[k].z, fmaf(v[k].w, v[k].w, q))));
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / Cw) + eps);
+        float* yr = y + r * Cw + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            float4 o;
+            o.x = fmaf(v[k].x * rstd, g[k].x, b[k].x); o.y = fmaf(v[k].y * rstd, g[k].y, b[k].y);
+            o.z = fmaf(v[k].z * rstd, g[k].z, b[k].z); o.w = fmaf(v[k].w * rstd, g[k].w, b[k].w);
+            *reinterpret_cast<float4*>(yr + k * 128) = o;
+        }
+        if (lane == 0) *reinterpret_cast<float2*>(mean_rstd_out + 2 * r) = make_float2(mean, rstd);
+    }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(kThreads) k_ln_bwd(const float* __restrict__ x, const float* __restrict__ dy,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean_rstd_in,
+                                                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     long long rows) {
+    constexpr int Cw = VPL * 128;
+    __shared__ float s_g[Cw], s_b[Cw];
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 g[VPL], ag[VPL], ab[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        g[k] = *reinterpret_cast<const float4*>(gamma + k * 128 + 4 * lane);
+        ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long r = warp; r < rows; r += warps) {
+        const float2 mr = *reinterpret_cast<const float2*>(mean_rstd_in + 2 * r);
+        const float* xr = x + r * Cw + 4 * lane;
+        const float* gr = dy + r * Cw + 4 * lane;
+        float4 xh[VPL], gg[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k * 128));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(gr + k * 128));
+            xh[k] = make_float4((v.x - mr.x) * mr.y, (v.y - mr.x) * mr.y, (v.z - mr.x) * mr.y, (v.w - mr.x) * mr.y);
+            ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+            ag[k].x = fmaf(d.x, xh[k].x, ag[k].x); ag[k].y = fmaf(d.y, xh[k].y, ag[k].y);
+            ag[k].z = fmaf(d.z, xh[k].z, ag[k].z); ag[k].w = fmaf(d.w, xh[k].w, ag[k].w);
+            gg[k] = make_float4(d.x * g[k].x, d.y * g[k].y, d.z * g[k].z, d.w * g[k].w);
+            s1 += (gg[k].x + gg[k].y) + (gg[k].z + gg[k].w);
+            s2 = fmaf(gg[k].x, xh[k].x, fmaf(gg[k].y, xh[k].y, fmaf(gg[k].z, xh[k].z, fmaf(gg[k].w, xh[k].w, s2))));
+        }
+        const float m1 = warp_sum(s1) * (1.f / Cw), m2 = warp_sum(s2) * (1.f / Cw);
+        float* or_ = dx + r * Cw + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            float4 o;
+            o.x = mr.y * (gg[k].x - m1 - xh[k].x * m2); o.y = mr.y * (gg[k].y - m1 - xh[k].y * m2);
+            o.z = mr.y * (gg[k].z - m1 - xh[k].z * m2); o.w = mr.y * (gg[k].w - m1 - xh[k].w * m2);
+            *reinterpret_cast<float4*>(or_ + k * 128) = o;
+        }
+    }
+    for (int i = threadIdx.x; i < Cw; i += blockDim.x) { s_g[i] = 0.f; s_b[i] = 0.f; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int c = k * 128 + 4 * lane;
+        atomicAdd(&s_g[c + 0], ag[k].x); atomicAdd(&s_g[c + 1], ag[k].y); atomicAdd(&s_g[c + 2], ag[k].z); atomicAdd(&s_g[c + 3], ag[k].w);
+        atomicAdd(&s_b[c + 0], ab[k].x); atomicAdd(&s_b[c + 1], ab[k].y); atomicAdd(&s_b[c + 2], ab[k].z); atomicAdd(&s_b[c + 3], ab[k].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cw; i += blockDim.x) { atomicAdd(&dgamma[i], s_g[i]); atomicAdd(&dbeta[i], s_b[i]); }
+}
+
+static int ln_grid(long long rows) {
+    const long long want = (rows + kThreads / 32 - 1) / (kThreads / 32);
+    const long long cap = 148 * 4;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+template <int VPL>
+static void ln_launch_fwd(const float* x, const float* g, const float* b, float* y, float* mr, long long rows, float eps, cudaStream_t s) {
+    k_ln_fwd<VPL><<<ln_grid(rows), kThreads, 0, s>>>(x, g, b, y, mr, rows, eps);
+}
+template <int VPL>
+static void ln_launch_bwd(const float* x, const float* dy, const float* g, const float* mr, float* dx, float* dg, float* db,
+                          long long rows, cudaStream_t s) {
+    k_ln_bwd<VPL><<<ln_grid(rows), kThreads, 0, s>>>(x, dy, g, mr, dx, dg, db, rows);
+}
+
 static int check(const LsGroupNorm* a) {
     if (!a) return ls_fail("groupnorm: args is NULL");
     if (a->N < 0 || a->C < 1 || a->G < 1 || a->HW < 1 || a->C % a->G) return ls_fail("groupnorm: bad sizes N=%d C=%d G=%d HW=%lld", a->N, a->C, a->G, (long long)a->HW);
@@ -242,4 +366,44 @@ extern "C" LS_API int ls_groupnorm_backward(const LsGroupNorm* a, const float* d
         lsn::k_gn_bwd_apply<0><<<grid, lsn::kThreads, 0, s>>>(a->x, dy, a->gamma, a->beta, a->stats, sums, dx, a->C, a->G, a->HW, chunk, a->eps);
     }
     return ls_check_cuda("groupnorm backward");
+}
+
+extern "C" LS_API int ls_layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
+                                           int64_t rows, int32_t C, float eps, void* stream) {
+    if (C < 128 || C % 128 || C / 128 > lsn::kMaxVPL) return ls_fail("layernorm: C=%d must be a multiple of 128 up to 1024", C);
+    if (rows < 0) return ls_fail("layernorm: rows < 0");
+    if (rows == 0) return 0;
+    if (!x || !gamma || !beta || !y || !mean_rstd) return ls_fail("layernorm forward: NULL pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (C / 128) {
+        case 1: lsn::ln_launch_fwd<1>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        case 2: lsn::ln_launch_fwd<2>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        case 3: lsn::ln_launch_fwd<3>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        case 4: lsn::ln_launch_fwd<4>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        case 5: lsn::ln_launch_fwd<5>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        case 6: lsn::ln_launch_fwd<6>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        case 7: lsn::ln_launch_fwd<7>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+        default: lsn::ln_launch_fwd<8>(x, gamma, beta, y, mean_rstd, rows, eps, s); break;
+    }
+    return ls_check_cuda("k_ln_fwd");
+}
+
+extern "C" LS_API int ls_layernorm_backward(const float* x, const float* dy, const float* gamma, const float* mean_rstd, float* dx,
+                                            float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream) {
+    if (C < 128 || C % 128 || C / 128 > lsn::kMaxVPL) return ls_fail("layernorm: C=%d must be a multiple of 128 up to 1024", C);
+    if (rows < 0) return ls_fail("layernorm: rows < 0");
+    if (rows == 0) return 0;
+    if (!x || !dy || !gamma || !mean_rstd || !dx || !dgamma || !dbeta) return ls_fail("layernorm backward: NULL pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (C / 128) {
+        case 1: lsn::ln_launch_bwd<1>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        case 2: lsn::ln_launch_bwd<2>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        case 3: lsn::ln_launch_bwd<3>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        case 4: lsn::ln_launch_bwd<4>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        case 5: lsn::ln_launch_bwd<5>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        case 6: lsn::ln_launch_bwd<6>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        case 7: lsn::ln_launch_bwd<7>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+        default: lsn::ln_launch_bwd<8>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
+    }
+    return ls_check_cuda("k_ln_bwd");
 }

@@ -110,7 +110,7 @@ def intersect_rays(origins_x: Tensor, directions_x: Tensor, origins_y: Tensor, d
     nx = dx[..., :, None] * dx[..., None, :] - eye
     ny = dy[..., :, None] * dy[..., None, :] - eye
     lhs = nx + ny
-    rhs = torch.einsum("...ij,...j->...i", nx, ox) + torch.einsum("...ij,...j->...i", ny, oy)
+    rhs = matvec(nx, ox) + matvec(ny, oy)
     # keep the solve finite on the parallel entries (their result is overwritten below)
     lhs = torch.where(parallel[..., None, None], -eye, lhs)
     result = _solve3_sym(lhs, rhs)

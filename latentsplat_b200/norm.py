@@ -69,3 +69,54 @@ class GroupNorm(nn.GroupNorm):
 
     def forward(self, input: Tensor) -> Tensor:
         return group_norm(input, self.num_groups, self.weight, self.bias, self.eps, self.act)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, eps: float):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        rows, Cn = x2.shape
+        y = torch.empty_like(x2)
+        mean_rstd = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.load().ls_layernorm_forward(x2.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                                          mean_rstd.data_ptr(), rows, Cn, eps,
+                                                          torch.cuda.current_stream().cuda_stream), "ls_layernorm_forward")
+        _capi.KERNEL_LAUNCHES[0] += 1
+        ctx.save_for_backward(x2, weight, mean_rstd)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, weight, mean_rstd = ctx.saved_tensors
+        rows, Cn = x2.shape
+        dy2 = dy.reshape(rows, Cn).contiguous()
+        dx = torch.empty_like(x2)
+        dgb = torch.zeros((2, Cn), dtype=torch.float32, device=x2.device)
+        with torch.cuda.device(x2.device):
+            _capi.check(_capi.load().ls_layernorm_backward(x2.data_ptr(), dy2.data_ptr(), weight.data_ptr(), mean_rstd.data_ptr(),
+                                                           dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), rows, Cn,
+                                                           torch.cuda.current_stream().cuda_stream), "ls_layernorm_backward")
+        _capi.KERNEL_LAUNCHES[0] += 1
+        return dx.view(dy.shape), dgb[0], dgb[1], None
+
+
+def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tensor:
+    Cn = x.shape[-1]
+    if (ENABLED and x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None
+            and Cn % 128 == 0 and Cn <= 1024 and x.numel() > 0):
+        return _LayerNormFn.apply(x, weight, bias, eps)
+    return F.layer_norm(x, (Cn,), weight, bias, eps)
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm over the last dimension on our kernel when CUDA fp32 and C % 128 == 0 (parameters as nn.LayerNorm)."""
+
+    def forward(self, input: Tensor) -> Tensor:
+        if len(self.normalized_shape) != 1:
+            return super().forward(input)
+        return layer_norm(input, self.weight, self.bias, self.eps)

@@ -266,3 +266,24 @@ def test_groupnorm_silu_matches_torch(cuda, shape, act):
     want = [ref.detach(), x.grad.double(), w.grad.double(), b.grad.double()]
     for a, r, name in zip(got, want, ("y", "dx", "dgamma", "dbeta")):
         assert (a - r).abs().max().item() <= 2e-5 * r.abs().max().item() + 1e-6, f"{name}: {(a - r).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("shape", [(8, 1025, 768), (4099, 1, 128), (37, 384)])
+def test_layernorm_matches_torch(cuda, shape):
+    """ls_layernorm_* == F.layer_norm (float64 reference), forward and dx / dgamma / dbeta."""
+    import torch.nn.functional as F
+    from latentsplat_b200.norm import layer_norm
+    g = torch.Generator(cuda).manual_seed(9)
+    x = (torch.randn(shape, device=cuda, generator=g) * 1.5 + 2).requires_grad_(True)
+    w = (torch.rand(shape[-1], device=cuda, generator=g) + 0.5).requires_grad_(True)
+    b = torch.randn(shape[-1], device=cuda, generator=g).requires_grad_(True)
+    wt = torch.randn(shape, device=cuda, generator=g)
+    y = layer_norm(x, w, b, 1e-6)
+    (y * wt).sum().backward()
+    got = [y.detach().double(), x.grad.double(), w.grad.double(), b.grad.double()]
+    x.grad = w.grad = b.grad = None
+    ref = F.layer_norm(x.double(), shape[-1:], w.double(), b.double(), 1e-6)
+    (ref * wt.double()).sum().backward()
+    want = [ref.detach(), x.grad.double(), w.grad.double(), b.grad.double()]
+    for a, r, name in zip(got, want, ("y", "dx", "dgamma", "dbeta")):
+        assert (a - r).abs().max().item() <= 2e-5 * r.abs().max().item() + 1e-6, f"{name}: {(a - r).abs().max().item():.3e}"
