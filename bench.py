@@ -47,8 +47,9 @@ def workload_name(cfg) -> str:
         return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views 256x256, "
                 f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
                 "views -> VAE kl-f8 decoder with skips -> PatchGAN logits; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
-                "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar single-query attention; library: cuDNN convolutions (TF32), "
-                "norms/elementwise (torch), DINO attention core (bf16 flash SDPA)")
+                "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar gather + depth encoding, weight-absorbed epipolar cross-attention, "
+                "GroupNorm+SiLU, LayerNorm; library: cuDNN convolutions (TF32), DINO / VAE-mid attention cores (bf16 flash / "
+                "mem-efficient SDPA), remaining elementwise glue (torch)")
     return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views 256x256, "
             f"G={cfg['G']} feature Gaussians/scene (colour SH deg {cfg['color_sh_degree']} + C={cfg['C']} feature SH "
             f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA fwd+bwd with scalar loss heads; "
@@ -430,6 +431,8 @@ def run_full(args, cfg):
         capacity = pipe.decoder.calibrate_raster_capacity(slack=1.5)
         num_rendered = pipe.decoder.last_raster.num_rendered
         n_eager = max(3, args.steps // 4)
+        opt_step()                                            # untimed: Adam state allocation, fused-kernel selection
+        fwd_bwd(dev_flat)
         eager_ms, _ = timed_loop(lambda: (fwd_bwd(dev_flat), opt_step()), n_eager)
         eager_ms /= n_eager
     torch.cuda.current_stream().wait_stream(side)
