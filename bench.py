@@ -453,6 +453,13 @@ def run_full(args, cfg):
 
     for _ in range(warm):
         step(); step_e2e()
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        dev_ms, wall_ms = timed_loop(step, args.steps)
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiler_range": True, "steps": args.steps, "ms_per_step_under_profiler": dev_ms / args.steps}), flush=True)
+        return
     with ClockSampler(local_rank) as clk:
         dev_ms, wall_ms = timed_loop(step, args.steps)
         e2e_ms, _ = timed_loop(step_e2e, args.steps)
@@ -752,6 +759,13 @@ def run_ours(args, cfg):
     for _ in range(warm):
         step.replay()
         run_e2e()
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        dev_ms, wall_ms = timed_loop(lambda: step.replay(), args.steps)
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiler_range": True, "steps": args.steps, "ms_per_step_under_profiler": dev_ms / args.steps}), flush=True)
+        return
     with ClockSampler(local_rank) as clk:
         dev_ms, wall_ms = timed_loop(lambda: step.replay(), args.steps)
         e2e_ms, _ = timed_loop(run_e2e, args.steps)
@@ -829,6 +843,9 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--workload", default="full", choices=["full", "splat"])
     ap.add_argument("--resolution", type=int, default=256, help="image side (BASELINE configs[4] stress: 512)")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="for `ncu --profile-from-start off`: bracket the timed device steps with cudaProfilerStart/Stop and "
+                         "skip the e2e / stage / CPU-baseline legs (numbers printed by such a run are not bench values)")
     args = ap.parse_args()
     global H, W
     H = W = args.resolution

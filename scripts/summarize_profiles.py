@@ -28,9 +28,10 @@ if launches.exists():
         a[0] += 1
         a[1] += t
     tot = sum(a[1] for a in agg.values())
-    ours = sum(a[1] for k, a in agg.items() if "ls::" in k)
-    md = [f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3` (gpu__time_duration.sum, --clock-control none)",
-          "", f"{len(rows)} launches, {tot / 1e3:.2f} ms GPU time in total; our kernels (`ls::*`) = {100 * ours / tot:.1f} % of it.",
+    import re
+    ours = sum(a[1] for k, a in agg.items() if re.search(r"\bls[a-z]?::", k))
+    md = [f"# {tag}: ncu launch list of the timed region of `python bench.py` (cudaProfilerStart/Stop range; gpu__time_duration.sum, --clock-control none)",
+          "", f"{len(rows)} launches, {tot / 1e3:.2f} ms GPU time in total; our kernels (`ls::*`, `lsg::*`, `lsa::*`, `lse::*`, `lsn::*`) = {100 * ours / tot:.1f} % of it.",
           "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
           "| share | total µs | launches | avg µs | grid | block | kernel |", "|---:|---:|---:|---:|---|---|---|"]
     for k, (n, t, g, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
