@@ -44,8 +44,33 @@ class GaussianAdapter(nn.Module):
                 mask[l * l:(l + 1) ** 2] = 0.1 * 0.25 ** l
             self.register_buffer(name, mask, persistent=False)
 
+    def harmonics_transform(self, c2w_rotations: Tensor) -> Tensor:
+        """(…, 3, 3) camera-to-world rotations -> (…, d_in, d_in) matrix T with  T @ raw  ==  raw with its colour and
+        feature SH blocks masked (:44-61) and rotated into world space (:104-105), everything else untouched.
+        Masking and rotation are linear in the raw network output, so the encoder folds T into the weights of the
+        `to_gaussians` Linear (one effective weight per context view) and calls `forward(..., harmonics_ready=True)`:
+        the two mask multiplies, the per-degree batched rotations over millions of coefficient vectors, their `cat`s
+        and all of their backward passes disappear into a GEMM that runs anyway."""
+        lead = c2w_rotations.shape[:-2]
+        t = torch.zeros((*lead, self.d_in, self.d_in), dtype=c2w_rotations.dtype, device=c2w_rotations.device)
+        torch.diagonal(t[..., :7, :7], dim1=-2, dim2=-1).fill_(1.0)      # scales, rotation: untouched (no H2D: capturable)
+        offset = 7
+        for degree, mask, channels, width in ((self.cfg.color_sh_degree, self.color_sh_mask, 3, self.d_color_sh),
+                                              (self.cfg.feature_sh_degree, self.feature_sh_mask, self.n_feature_channels,
+                                               self.d_feature_sh)):
+            mats = sh_rotation_matrices(c2w_rotations, degree)
+            block = torch.zeros((*lead, width, width), dtype=t.dtype, device=t.device)
+            for l, m in enumerate(mats):
+                block[..., l * l:(l + 1) ** 2, l * l:(l + 1) ** 2] = m
+            block = block * mask                                   # D diag(mask): scale column j by mask[j]
+            for ch in range(channels):
+                t[..., offset:offset + width, offset:offset + width] = block
+                offset += width
+        return t
+
     def forward(self, extrinsics: Tensor, intrinsics: Tensor, coordinates: Tensor, depths: Tensor, opacities: Tensor,
-                raw_gaussians: Tensor, image_shape: tuple[int, int], eps: float = 1e-8) -> Gaussians:
+                raw_gaussians: Tensor, image_shape: tuple[int, int], eps: float = 1e-8,
+                harmonics_ready: bool = False) -> Gaussians:
         device = extrinsics.device
         scales, rotations, color_sh, feature_sh = raw_gaussians.split(
             (3, 4, 3 * self.d_color_sh, self.n_feature_channels * self.d_feature_sh), dim=-1)
@@ -60,8 +85,9 @@ class GaussianAdapter(nn.Module):
 
         color_sh = color_sh.unflatten(-1, (3, self.d_color_sh))
         feature_sh = feature_sh.unflatten(-1, (self.n_feature_channels, self.d_feature_sh))
-        color_sh = color_sh * self.color_sh_mask
-        feature_sh = feature_sh * self.feature_sh_mask
+        if not harmonics_ready:
+            color_sh = color_sh * self.color_sh_mask
+            feature_sh = feature_sh * self.feature_sh_mask
 
         # world-space covariance C (R S S^T R^T) C^T = (C R S)(C R S)^T, without batched 3x3 GEMMs
         c2w_rotations = extrinsics[..., :3, :3]
@@ -71,13 +97,15 @@ class GaussianAdapter(nn.Module):
         origins, directions = get_world_rays(coordinates, extrinsics, intrinsics)
         means = origins + directions * depths[..., None]
 
+        if not harmonics_ready:
+            # rotate once per ray, THEN broadcast over the samples of the ray (the reference broadcasts first, :92-93,
+            # and rotates spp x as many coefficient vectors)
+            color_sh = self._rotate(color_sh, c2w_rotations, self.cfg.color_sh_degree)
+            feature_sh = self._rotate(feature_sh, c2w_rotations, self.cfg.feature_sh_degree)
         return Gaussians(means=means, covariances=covariances,
-                         # rotate once per ray, THEN broadcast over the samples of the ray (the reference
-                         # broadcasts first, :92-93, and rotates spp x as many coefficient vectors)
-                         color_harmonics=self._rotate(color_sh, c2w_rotations, self.cfg.color_sh_degree)
-                         .broadcast_to((*opacities.shape, 3, self.d_color_sh)),
-                         feature_harmonics=self._rotate(feature_sh, c2w_rotations, self.cfg.feature_sh_degree)
-                         .broadcast_to((*opacities.shape, self.n_feature_channels, self.d_feature_sh)),
+                         color_harmonics=color_sh.broadcast_to((*opacities.shape, 3, self.d_color_sh)),
+                         feature_harmonics=feature_sh.broadcast_to((*opacities.shape, self.n_feature_channels,
+                                                                    self.d_feature_sh)),
                          opacities=opacities,
                          scales=scales,                                             # camera space (ply export only)
                          rotations=rotations.broadcast_to((*scales.shape[:-1], 4)))

@@ -28,7 +28,7 @@ from .encoder import Encoder
 from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
 from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
 from .shims import apply_bounds_shim, apply_patch_shim
-from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200.gemm import Linear, linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
 
 
 @dataclass
@@ -57,6 +57,9 @@ class EncoderEpipolarCfg:
     use_transmittance: bool
     visualizer: Optional[dict] = None        # EncoderVisualizerEpipolarCfg in the reference (out of scope)
     num_context_views: int = 2               # get_cfg().dataset.view_sampler.num_context_views in the reference
+
+
+FOLD_HARMONICS = True     # fold SH masking + camera-to-world SH rotation into the to_gaussians weights (set False for A/B)
 
 
 class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
@@ -97,6 +100,28 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         x = self.backbone(images)
         return self.backbone_projection(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
 
+    def _gaussian_head(self, features: Tensor, c2w_rotations: Tensor) -> Tensor:
+        """to_gaussians(features) (:97-103) -- with the SH masking and the camera-to-world SH rotation of the Gaussian
+        adapter (gaussian_adapter.py:44-61, 104-105) folded into the Linear: both are linear maps T_view of the raw
+        output, so  T_v (W x + b) = (T_v W) x + T_v b  and each context view gets its own effective weight."""
+        if not FOLD_HARMONICS:
+            return self.to_gaussians(features)
+        act, lin = self.to_gaussians[0], self.to_gaussians[1]
+        b, v = features.shape[:2]
+        srf, d = self.cfg.num_surfaces, 2 + self.gaussian_adapter.d_in
+        t = torch.zeros((b, v, srf * d, srf * d), dtype=features.dtype, device=features.device)
+        t_adapter = self.gaussian_adapter.harmonics_transform(c2w_rotations)                    # (b, v, d_in, d_in)
+        for k in range(srf):
+            o = k * d
+            t[:, :, o, o] = 1.0
+            t[:, :, o + 1, o + 1] = 1.0
+            t[:, :, o + 2:o + d, o + 2:o + d] = t_adapter
+        weight = t @ lin.weight                                                                 # (b, v, srf*d, d_feature)
+        bias = (t @ lin.bias[:, None])[..., 0]
+        x = act(features)
+        rows = [linear(x[i, j], weight[i, j], bias[i, j]) for i in range(b) for j in range(v)]
+        return torch.stack(rows).unflatten(0, (b, v))
+
     def forward(self, context: dict, global_step: int, features: Optional[Tensor] = None,
                 deterministic: bool = False, visualization_dump: Optional[dict] = None) -> VariationalGaussians:
         b, v = context["image"].shape[:2]
@@ -119,14 +144,15 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
 
         xy_ray, _ = sample_image_grid((h, w), device)
         xy_ray = xy_ray.reshape(h * w, 1, 2)
-        gaussians = self.to_gaussians(features).unflatten(-1, (self.cfg.num_surfaces, -1))   # ... (srf c) -> ... srf c
+        gaussians = self._gaussian_head(features, context["extrinsics"][..., :3, :3])
+        gaussians = gaussians.unflatten(-1, (self.cfg.num_surfaces, -1))                       # ... (srf c) -> ... srf c
         offset_xy = gaussians[..., :2].sigmoid()
         pixel_size = device_constant((1 / w, 1 / h), device)
         xy_ray = xy_ray + (offset_xy - 0.5) * pixel_size
         gpp = self.cfg.gaussians_per_pixel
         g = self.gaussian_adapter(context["extrinsics"][:, :, None, None, None], context["intrinsics"][:, :, None, None, None],
                                   xy_ray[..., None, :], depths, self.map_pdf_to_opacity(densities, global_step) / gpp,
-                                  gaussians[..., None, 2:], (h, w))
+                                  gaussians[..., None, 2:], (h, w), harmonics_ready=FOLD_HARMONICS)
 
         if visualization_dump is not None:
             visualization_dump["depth"] = depths.unflatten(2, (h, w))
