@@ -180,4 +180,40 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- warp-cooperative staging of per-Gaussian coefficient rows ---------------------------------------------------
+// A thread per Gaussian reading its own 300-B SH row makes every warp-level load touch 32 different sectors for 128
+// useful bytes (the preprocess kernels then sit at 12-35 % of HBM bandwidth, L2->L1 sector traffic bound).  Instead the
+// warp moves a chunk of `len` <= kStagePitch consecutive floats of each of its 32 consecutive rows with lanes running
+// over the FLAT (row, element) index -- consecutive lanes touch consecutive addresses inside a row piece -- through a
+// small per-warp shared buffer (32 x 25 floats; pitch 25 is odd, so the per-lane row reads are conflict-free).
+constexpr int kStagePitch = 25;
+
+__device__ __forceinline__ void stage_load(float* __restrict__ buf, const float* __restrict__ base, int row_len, int c0,
+                                           int len, int nrows, int lane) {
+    const uint32_t magic = (65536u + (uint32_t)len - 1u) / (uint32_t)len;     // f / len for f < 800, len <= 25
+    const int total = 32 * len;
+    for (int f = lane; f < total; f += 32) {
+        const int g = (int)(((uint32_t)f * magic) >> 16), e = f - g * len;
+        if (g < nrows) buf[g * kStagePitch + e] = __ldg(base + (size_t)g * row_len + c0 + e);
+    }
+    __syncwarp();
+}
+
+// rows whose bit is clear in row_mask are left untouched (their destination was zero-filled by the caller)
+__device__ __forceinline__ void stage_store(const float* __restrict__ buf, float* __restrict__ base, int row_len, int c0,
+                                            int len, uint32_t row_mask, bool atomic, int lane) {
+    __syncwarp();
+    const uint32_t magic = (65536u + (uint32_t)len - 1u) / (uint32_t)len;
+    const int total = 32 * len;
+    for (int f = lane; f < total; f += 32) {
+        const int g = (int)(((uint32_t)f * magic) >> 16), e = f - g * len;
+        if ((row_mask >> g) & 1u) {
+            float* dst = base + (size_t)g * row_len + c0 + e;
+            const float v = buf[g * kStagePitch + e];
+            if (atomic) atomicAdd(dst, v); else *dst = v;
+        }
+    }
+    __syncwarp();
+}
+
 }  // namespace ls

@@ -228,30 +228,39 @@ __device__ __forceinline__ void accum(float* dst, float v, bool atomic) {
 
 __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, const LsRasterState st,
                                                         const LsRasterGrads gr) {
+    __shared__ float s_stage[8][32 * kStagePitch];
     const int v = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sc.G) return;
+    const int lane = threadIdx.x & 31;
+    float* stage = s_stage[threadIdx.x >> 5];
+    float* mine = stage + lane * kStagePitch;
+    const int i0 = i - lane, nrows = min(32, sc.G - i0);       // this warp's 32 consecutive Gaussians
     const size_t vi = (size_t)v * sc.G + i;
-    if (st.radii[vi] <= 0) return;
+    // lanes never return early: the SH rows and their gradients move warp-cooperatively (stage_load / stage_store)
+    const bool alive = i < sc.G && st.radii[vi] > 0;
+    const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+    if (alive_mask == 0u) return;                               // warp-uniform
     const int s_idx = v / sc.views_per_scene;
     const size_t si = (size_t)s_idx * sc.G + i;
+    const size_t si0 = (size_t)s_idx * sc.G + i0;
     const bool at = sc.views_per_scene > 1;
 
+    float p[3] = {0.f, 0.f, 0.f}, dmean[3] = {0.f, 0.f, 0.f};
+    const float scale = sc.scene_scale ? sc.scene_scale[v] : 1.0f;
+    const float* __restrict__ r = gr.dL_drecord + vi * gr.grad_stride;       // dereferenced by alive lanes only
+    if (alive) {
     const float* __restrict__ vm = sc.viewmatrix + 16 * v;
     const float* __restrict__ pm = sc.projmatrix + 16 * v;
-    const float scale = sc.scene_scale ? sc.scene_scale[v] : 1.0f;
     const float scale2 = scale * scale;
     const float tanx = sc.tanfov[2 * v], tany = sc.tanfov[2 * v + 1];
     const float fx = div_((float)sc.W, mul_(2.0f, tanx)), fy = div_((float)sc.H, mul_(2.0f, tany));
-    const float p[3] = {mul_(sc.means3D[3 * si], scale), mul_(sc.means3D[3 * si + 1], scale),
-                        mul_(sc.means3D[3 * si + 2], scale)};
+    p[0] = mul_(sc.means3D[3 * si], scale); p[1] = mul_(sc.means3D[3 * si + 1], scale); p[2] = mul_(sc.means3D[3 * si + 2], scale);
     float cv[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) cv[k] = mul_(sc.cov3D[6 * si + k], scale * scale);
     Cov2D q;
     cov2d(p, fx, fy, tanx, tany, cv, vm, q);
 
-    const float* __restrict__ r = gr.dL_drecord + vi * gr.grad_stride;
     const float g2x = r[0], g2y = r[1], gcx = r[2], gcy = r[3], gcz = r[4], gop = r[5], gdep = r[6];
 
     // conic = inverse(cov2D)
@@ -294,7 +303,6 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
     dt[1] = q.ymul * -fy * tz2 * dJ12;
     dt[2] = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2.f * fx * q.t[0]) * tz3 * dJ02 + (2.f * fy * q.t[1]) * tz3 * dJ12;
     dt[2] += gdep;  // depth channel = row 2 of the view transform
-    float dmean[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) dmean[j] = vm[4 * j + 0] * dt[0] + vm[4 * j + 1] * dt[1] + vm[4 * j + 2] * dt[2];
 
@@ -315,6 +323,8 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
         gr.dL_dmeans2D[3 * vi + 2] = 0.f;
     }
 
+    }   // alive (geometry)
+
     // colour / feature inputs
     const int ncol = n_color(sc.color_mode);
     const bool need_dir = sc.color_mode == LS_COLOR_SH || sc.feature_mode == LS_FEATURE_SH;
@@ -322,7 +332,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
     float ddir[3] = {0.f, 0.f, 0.f};
     float basis[25];
     float dbasis[25][3];
-    if (need_dir) {
+    if (need_dir && alive) {
         const float* cp = sc.campos + 3 * v;
         const float d0 = p[0] - cp[0], d1 = p[1] - cp[1], d2 = p[2] - cp[2];
         inv = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
@@ -332,43 +342,76 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
         sh_basis<true>(deg, u[0], u[1], u[2], basis, dbasis);
     }
     if (sc.color_mode == LS_COLOR_PRECOMP) {
+        if (alive) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) accum(gr.dL_dcolor_in + 3 * si + ch, r[7 + ch], at);
+            for (int ch = 0; ch < 3; ++ch) accum(gr.dL_dcolor_in + 3 * si + ch, r[7 + ch], at);
+        }
     } else if (sc.color_mode == LS_COLOR_SH) {
         const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1);
-        const uint8_t cl = st.clamped[vi];
-        const float gc[3] = {(cl & 1) ? 0.f : r[7], (cl & 2) ? 0.f : r[8], (cl & 4) ? 0.f : r[9]};
-        const float* __restrict__ sh = sc.color + si * (size_t)(n * 3);
-        float* dsh = gr.dL_dcolor_in + si * (size_t)(n * 3);
-        for (int k = 0; k < n; ++k) {
-            float sg = 0.f;
+        float gc[3] = {0.f, 0.f, 0.f};
+        if (alive) {
+            const uint8_t cl = st.clamped[vi];
+            gc[0] = (cl & 1) ? 0.f : r[7]; gc[1] = (cl & 2) ? 0.f : r[8]; gc[2] = (cl & 4) ? 0.f : r[9];
+        }
+        const float* __restrict__ sh0 = sc.color + si0 * (size_t)(n * 3);          // the warp's 32 rows
+        float* dsh0 = gr.dL_dcolor_in + si0 * (size_t)(n * 3);
+        for (int k0 = 0; k0 < n; k0 += 5) {                                        // 5 coefficients (15 floats) per pass
+            const int cnt = min(5, n - k0);
+            stage_load(stage, sh0, n * 3, k0 * 3, cnt * 3, nrows, lane);
+            float out[15];
+            if (alive) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                accum(dsh + 3 * k + ch, basis[k] * gc[ch], at);
-                sg = fmaf(sh[3 * k + ch], gc[ch], sg);
+                for (int kk = 0; kk < 5; ++kk) {
+                    if (kk < cnt) {
+                        const int k = k0 + kk;
+                        float sg = 0.f;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            out[3 * kk + ch] = basis[k] * gc[ch];
+                            sg = fmaf(mine[3 * kk + ch], gc[ch], sg);
+                        }
+                        ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
+                        ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
+                        ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
+                    }
+                }
             }
-            ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
-            ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
-            ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
+            __syncwarp();                                                          // everyone has read its sh chunk
+            if (alive) {
+#pragma unroll
+                for (int e = 0; e < 15; ++e)
+                    if (e < 3 * cnt) mine[e] = out[e];
+            }
+            stage_store(stage, dsh0, n * 3, k0 * 3, cnt * 3, alive_mask, at, lane);
         }
     }
     if (sc.feature_mode == LS_FEATURE_PRECOMP) {
-        for (int ch = 0; ch < sc.C; ++ch) accum(gr.dL_dfeature_in + si * sc.C + ch, r[7 + ncol + ch], at);
+        if (alive)
+            for (int ch = 0; ch < sc.C; ++ch) accum(gr.dL_dfeature_in + si * sc.C + ch, r[7 + ncol + ch], at);
     } else if (sc.feature_mode == LS_FEATURE_SH) {
         const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1);
-        const float* __restrict__ fs = sc.feature + si * (size_t)(sc.C * n);
-        float* dfs = gr.dL_dfeature_in + si * (size_t)(sc.C * n);
-        for (int ch = 0; ch < sc.C; ++ch) {
-            const float gf = r[7 + ncol + ch];
-            for (int k = 0; k < n; ++k) {
-                accum(dfs + ch * n + k, basis[k] * gf, at);
-                const float sg = fs[ch * n + k] * gf;
-                ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
-                ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
-                ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
+        const float* __restrict__ fs0 = sc.feature + si0 * (size_t)(sc.C * n);
+        float* dfs0 = gr.dL_dfeature_in + si0 * (size_t)(sc.C * n);
+        const int cpc = max(1, kStagePitch / n);                                   // whole channels per pass
+        for (int c0 = 0; c0 < sc.C; c0 += cpc) {
+            const int nch = min(cpc, sc.C - c0);
+            stage_load(stage, fs0, sc.C * n, c0 * n, nch * n, nrows, lane);
+            if (alive) {
+                for (int cc = 0; cc < nch; ++cc) {
+                    const float gf = r[7 + ncol + c0 + cc];
+                    for (int k = 0; k < n; ++k) {
+                        const float sg = mine[cc * n + k] * gf;                    // read the coefficient ...
+                        mine[cc * n + k] = basis[k] * gf;                          // ... then overwrite its slot with its gradient
+                        ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
+                        ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
+                        ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
+                    }
+                }
             }
+            stage_store(stage, dfs0, sc.C * n, c0 * n, nch * n, alive_mask, at, lane);
         }
     }
+    if (!alive) return;                                        // no warp-level operation below this line
     if (need_dir) {
         const float dot = u[0] * ddir[0] + u[1] * ddir[1] + u[2] * ddir[2];
 #pragma unroll
