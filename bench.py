@@ -454,11 +454,15 @@ def run_full(args, cfg):
     for _ in range(warm):
         step(); step_e2e()
     if args.profiler_range:
+        # one launch list per timed step; "eager" replays the same kernels outside the CUDA graph (ncu 2025.2 aborts on
+        # cuDNN's batch-norm graph node of the PatchGAN when it profiles kernel nodes inside a graph replay)
+        fn = (lambda: (fwd_bwd(dev_flat), opt_step())) if args.profiler_range == "eager" else step
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        dev_ms, wall_ms = timed_loop(step, args.steps)
+        dev_ms, wall_ms = timed_loop(fn, args.steps)
         torch.cuda.cudart().cudaProfilerStop()
-        print(json.dumps({"profiler_range": True, "steps": args.steps, "ms_per_step_under_profiler": dev_ms / args.steps}), flush=True)
+        print(json.dumps({"profiler_range": args.profiler_range, "steps": args.steps,
+                          "ms_per_step_under_profiler": dev_ms / args.steps}), flush=True)
         return
     with ClockSampler(local_rank) as clk:
         dev_ms, wall_ms = timed_loop(step, args.steps)
@@ -843,7 +847,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--workload", default="full", choices=["full", "splat"])
     ap.add_argument("--resolution", type=int, default=256, help="image side (BASELINE configs[4] stress: 512)")
-    ap.add_argument("--profiler-range", action="store_true",
+    ap.add_argument("--profiler-range", nargs="?", const="graph", default=None, choices=["graph", "eager"],
                     help="for `ncu --profile-from-start off`: bracket the timed device steps with cudaProfilerStart/Stop and "
                          "skip the e2e / stage / CPU-baseline legs (numbers printed by such a run are not bench values)")
     args = ap.parse_args()

@@ -22,7 +22,12 @@ if launches.exists():
     rows = list(csv.DictReader(lines))
     agg = collections.OrderedDict()
     for x in rows:
-        t = float(x["Metric Value"].replace(",", ""))
+        try:
+            t = float(x["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        if t != t:          # nan: a launch ncu could not time
+            continue
         t = {"ns": t / 1e3, "us": t, "usecond": t, "ms": t * 1e3, "msecond": t * 1e3, "nsecond": t / 1e3}.get(x["Metric Unit"], t)
         a = agg.setdefault(x["Kernel Name"][:90], [0, 0.0, x["Grid Size"], x["Block Size"]])
         a[0] += 1
