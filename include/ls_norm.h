@@ -46,6 +46,13 @@ LS_API int ls_layernorm_forward(const float* x, const float* gamma, const float*
 LS_API int ls_layernorm_backward(const float* x, const float* dy, const float* gamma, const float* mean_rstd, float* dx,
                                  float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream /* cudaStream_t */);
 
+/* Per-channel bias of a convolution output, NCHW fp32: `Conv2d(..., bias=True)` everywhere on the path (VAE decoder,
+ * encoder refinement / feed-forward / skip convolutions, PatchGAN; e.g. src/model/encoder/epipolar/epipolar_transformer.py:
+ * 66-73, 155-170).  The convolution itself (cuDNN) runs bias-free; ls_conv_bias_add adds bias[c] to y IN PLACE,
+ * ls_conv_bias_grad ACCUMULATES sum_{n,h,w} dy into dbias[c] (the caller zero-fills dbias). */
+LS_API int ls_conv_bias_add(float* y, const float* bias, int64_t N, int32_t C, int64_t HW, void* stream /* cudaStream_t */);
+LS_API int ls_conv_bias_grad(const float* dy, float* dbias, int64_t N, int32_t C, int64_t HW, void* stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -307,6 +307,56 @@ static void ln_launch_bwd(const float* x, const float* dy, const float* g, const
     k_ln_bwd<VPL><<<ln_grid(rows), kThreads, 0, s>>>(x, dy, g, mr, dx, dg, db, rows);
 }
 
+// ---- per-channel bias of a convolution output (NCHW) and its gradient ---------------------------------------------
+// cuDNN's convolutions run bias-free here; torch would add the bias with a broadcasting (non-vectorised) elementwise
+// kernel and reduce its gradient with a strided reduce_kernel -- 6 ms + 5 ms of the step for ~1 G output elements.
+// k_bias_add: in place, one (image, channel) plane per blockIdx.y, float4 where H*W % 4 == 0.
+// k_plane_sum: per-plane block sums of dy, one float atomic per block into db[c].
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) k_bias_add(float* __restrict__ y, const float* __restrict__ bias, int C, long long HW,
+                                                       long long chunk) {
+    const int plane = blockIdx.y;
+    const float b = bias[plane % C];
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > HW) hi = HW;
+    float* p = y + (long long)plane * HW;
+    if (VEC == 4) {
+        float4* q = reinterpret_cast<float4*>(p + lo);
+        const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;
+        for (long long i = threadIdx.x; i < n4; i += kThreads) {
+            float4 v = q[i];
+            v.x += b; v.y += b; v.z += b; v.w += b;
+            q[i] = v;
+        }
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += kThreads) p[i] += b;
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) k_plane_sum(const float* __restrict__ dy, float* __restrict__ db, int C, long long HW,
+                                                        long long chunk) {
+    const int plane = blockIdx.y;
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > HW) hi = HW;
+    const float* p = dy + (long long)plane * HW;
+    float s = 0.f, unused = 0.f;
+    if (VEC == 4) {
+        const float4* q = reinterpret_cast<const float4*>(p + lo);
+        const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;
+        for (long long i = threadIdx.x; i < n4; i += kThreads) {
+            const float4 v = __ldg(q + i);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += kThreads) s += __ldg(p + i);
+    }
+    block_sum2(s, unused);
+    if (threadIdx.x == 0 && hi > lo) atomicAdd(&db[plane % C], s);
+}
+
 static int check(const LsGroupNorm* a) {
     if (!a) return ls_fail("groupnorm: args is NULL");
     if (a->N < 0 || a->C < 1 || a->G < 1 || a->HW < 1 || a->C % a->G) return ls_fail("groupnorm: bad sizes N=%d C=%d G=%d HW=%lld", a->N, a->C, a->G, (long long)a->HW);
@@ -406,4 +456,35 @@ extern "C" LS_API int ls_layernorm_backward(const float* x, const float* dy, con
         default: lsn::ln_launch_bwd<8>(x, dy, gamma, mean_rstd, dx, dgamma, dbeta, rows, s); break;
     }
     return ls_check_cuda("k_ln_bwd");
+}
+
+static int bias_args_ok(const void* a, const void* b, int64_t N, int32_t C, int64_t HW) {
+    if (N < 0 || C < 1 || HW < 1) return ls_fail("conv bias: bad sizes N=%lld C=%d HW=%lld", (long long)N, C, (long long)HW);
+    if (N * (int64_t)C > 65535) return ls_fail("conv bias: N*C=%lld exceeds the launch grid (65535 planes)", (long long)(N * C));
+    if (N > 0 && (!a || !b)) return ls_fail("conv bias: NULL pointer");
+    return 0;
+}
+
+extern "C" LS_API int ls_conv_bias_add(float* y, const float* bias, int64_t N, int32_t C, int64_t HW, void* stream) {
+    if (int e = bias_args_ok(y, bias, N, C, HW)) return e;
+    if (N == 0) return 0;
+    const long long planes = (long long)N * C;
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    int splits; long long chunk;
+    lsn::pick_split(planes, vec ? HW : ((HW + 3) & ~3LL), &splits, &chunk);
+    if (vec) lsn::k_bias_add<4><<<dim3(splits, (unsigned)planes), lsn::kThreads, 0, (cudaStream_t)stream>>>(y, bias, C, HW, chunk);
+    else lsn::k_bias_add<1><<<dim3(splits, (unsigned)planes), lsn::kThreads, 0, (cudaStream_t)stream>>>(y, bias, C, HW, chunk);
+    return ls_check_cuda("k_bias_add");
+}
+
+extern "C" LS_API int ls_conv_bias_grad(const float* dy, float* dbias, int64_t N, int32_t C, int64_t HW, void* stream) {
+    if (int e = bias_args_ok(dy, dbias, N, C, HW)) return e;
+    if (N == 0) return 0;
+    const long long planes = (long long)N * C;
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    int splits; long long chunk;
+    lsn::pick_split(planes, vec ? HW : ((HW + 3) & ~3LL), &splits, &chunk);
+    if (vec) lsn::k_plane_sum<4><<<dim3(splits, (unsigned)planes), lsn::kThreads, 0, (cudaStream_t)stream>>>(dy, dbias, C, HW, chunk);
+    else lsn::k_plane_sum<1><<<dim3(splits, (unsigned)planes), lsn::kThreads, 0, (cudaStream_t)stream>>>(dy, dbias, C, HW, chunk);
+    return ls_check_cuda("k_plane_sum");
 }

@@ -18,6 +18,7 @@ from torch.nn.functional import interpolate
 from ..diagonal_gaussian_distribution import DiagonalGaussianDistribution
 from .autoencoder import Autoencoder
 from .vae_kl import AutoencoderKLModel
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 PRETRAINED_AUTOENCODER_PATH = "pretrained/autoencoder"     # /root/reference/src/constants.py:1
 
@@ -55,7 +56,7 @@ class AutoencoderKL(Autoencoder[AutoencoderKLCfg]):
             self.model.load_state_dict(state_dict)
         if cfg.skip_connections:
             self.d_skip = self.d_latent + (d_skip_extra if cfg.skip_extra else 0)
-            mk = lambda d_out: (zero_module if cfg.skip_zero else (lambda m: m))(nn.Conv2d(self.d_skip, d_out, kernel_size=1))
+            mk = lambda d_out: (zero_module if cfg.skip_zero else (lambda m: m))(Conv2d(self.d_skip, d_out, kernel_size=1))
             self.skip_convs = nn.ModuleList([mk(cfg.block_out_channels[-1])] +
                                             [mk(d) for d in reversed(cfg.block_out_channels)])
 

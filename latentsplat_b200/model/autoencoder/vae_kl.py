@@ -15,18 +15,19 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200.norm import GroupNorm  # nn.GroupNorm with the following SiLU fused in (sm_100a kernels on CUDA)
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 
 class ResnetBlock2D(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, groups: int = 32, eps: float = 1e-6):
         super().__init__()
         self.norm1 = GroupNorm(groups, in_channels, eps=eps, affine=True, act="silu")      # norm + nonlinearity
-        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+        self.conv1 = Conv2d(in_channels, out_channels, 3, 1, 1)
         self.norm2 = GroupNorm(groups, out_channels, eps=eps, affine=True, act="silu")
         self.dropout = nn.Dropout(0.0)
-        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, 1, 1)
+        self.conv2 = Conv2d(out_channels, out_channels, 3, 1, 1)
         self.nonlinearity = nn.SiLU()
-        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1, 1, 0) if in_channels != out_channels else None
+        self.conv_shortcut = Conv2d(in_channels, out_channels, 1, 1, 0) if in_channels != out_channels else None
 
     def forward(self, x: Tensor) -> Tensor:
         h = self.conv1(self.norm1(x))                       # diffusers: conv1(nonlinearity(norm1(x))), SiLU fused into the norm
@@ -70,7 +71,7 @@ class UNetMidBlock2D(nn.Module):
 class Downsample2D(nn.Module):
     def __init__(self, channels: int):
         super().__init__()
-        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=0)
+        self.conv = Conv2d(channels, channels, 3, stride=2, padding=0)
 
     def forward(self, x: Tensor) -> Tensor:
         return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
@@ -79,7 +80,7 @@ class Downsample2D(nn.Module):
 class Upsample2D(nn.Module):
     def __init__(self, channels: int):
         super().__init__()
-        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+        self.conv = Conv2d(channels, channels, 3, padding=1)
 
     def forward(self, x: Tensor) -> Tensor:
         return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
@@ -118,7 +119,7 @@ class UpDecoderBlock2D(nn.Module):
 class Encoder(nn.Module):
     def __init__(self, in_channels: int, latent_channels: int, block_out_channels, layers_per_block: int, groups: int = 32):
         super().__init__()
-        self.conv_in = nn.Conv2d(in_channels, block_out_channels[0], 3, 1, 1)
+        self.conv_in = Conv2d(in_channels, block_out_channels[0], 3, 1, 1)
         self.down_blocks = nn.ModuleList()
         out = block_out_channels[0]
         for i, ch in enumerate(block_out_channels):
@@ -127,7 +128,7 @@ class Encoder(nn.Module):
         self.mid_block = UNetMidBlock2D(block_out_channels[-1], groups)
         self.conv_norm_out = GroupNorm(groups, block_out_channels[-1], eps=1e-6, act="silu")
         self.conv_act = nn.SiLU()
-        self.conv_out = nn.Conv2d(block_out_channels[-1], 2 * latent_channels, 3, padding=1)
+        self.conv_out = Conv2d(block_out_channels[-1], 2 * latent_channels, 3, padding=1)
 
     def forward(self, x: Tensor) -> Tensor:
         x = self.conv_in(x)
@@ -140,7 +141,7 @@ class Encoder(nn.Module):
 class Decoder(nn.Module):
     def __init__(self, latent_channels: int, out_channels: int, block_out_channels, layers_per_block: int, groups: int = 32):
         super().__init__()
-        self.conv_in = nn.Conv2d(latent_channels, block_out_channels[-1], 3, 1, 1)
+        self.conv_in = Conv2d(latent_channels, block_out_channels[-1], 3, 1, 1)
         self.mid_block = UNetMidBlock2D(block_out_channels[-1], groups)
         self.up_blocks = nn.ModuleList()
         rev = list(reversed(block_out_channels))
@@ -150,7 +151,7 @@ class Decoder(nn.Module):
             self.up_blocks.append(UpDecoderBlock2D(inp, out, layers_per_block + 1, i != len(rev) - 1, groups))
         self.conv_norm_out = GroupNorm(groups, block_out_channels[0], eps=1e-6, act="silu")
         self.conv_act = nn.SiLU()
-        self.conv_out = nn.Conv2d(block_out_channels[0], out_channels, 3, padding=1)
+        self.conv_out = Conv2d(block_out_channels[0], out_channels, 3, padding=1)
 
     def forward(self, z: Tensor) -> Tensor:
         z = self.mid_block(self.conv_in(z))
@@ -168,8 +169,8 @@ class AutoencoderKLModel(nn.Module):
         super().__init__()
         self.encoder = Encoder(in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups)
-        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
-        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        self.quant_conv = Conv2d(2 * latent_channels, 2 * latent_channels, 1)
+        self.post_quant_conv = Conv2d(latent_channels, latent_channels, 1)
 
     def encode_moments(self, x: Tensor) -> tuple[Tensor, Tensor]:
         mean, logvar = self.quant_conv(self.encoder(x)).chunk(2, dim=1)

@@ -11,6 +11,7 @@ import torch
 from torch import Tensor, nn
 
 from .discriminator import Discriminator
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 PRETRAINED_DISCRIMINATOR_PATH = "pretrained/discriminator"
 
@@ -34,7 +35,7 @@ class DiscriminatorPatchGan(Discriminator[DiscriminatorPatchGanCfg]):
         super().__init__(cfg)
         c = self.cfg
         act = lambda: nn.LeakyReLU(negative_slope=c.leaky_relu_neg_slope, inplace=True)
-        conv = lambda i, o, s, bias: nn.Conv2d(i, o, kernel_size=c.kernel_size, stride=s, padding=c.padding, bias=bias)
+        conv = lambda i, o, s, bias: Conv2d(i, o, kernel_size=c.kernel_size, stride=s, padding=c.padding, bias=bias)
         layers = [conv(d_in, c.base_dim, c.downscale_factor, True), act()]
         mult = 1
         for n in range(1, c.n_layers):

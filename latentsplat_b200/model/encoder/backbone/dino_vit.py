@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200.norm import LayerNorm  # nn.LayerNorm on our warp-per-row kernel on CUDA
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 
 class Mlp(nn.Module):
@@ -100,7 +101,7 @@ class PatchEmbed(nn.Module):
     def __init__(self, img_size: int, patch_size: int, in_chans: int, embed_dim: int):
         super().__init__()
         self.num_patches = (img_size // patch_size) ** 2
-        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.proj = Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
 
     def forward(self, x):
         return self.proj(x).flatten(2).transpose(1, 2)

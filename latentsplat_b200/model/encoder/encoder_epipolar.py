@@ -29,6 +29,7 @@ from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
 from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
 from .shims import apply_bounds_shim, apply_patch_shim
 from latentsplat_b200.gemm import Linear, linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 
 @dataclass
@@ -80,7 +81,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         self.to_gaussians = nn.Sequential(nn.ReLU(), Linear(cfg.d_feature,
                                                                cfg.num_surfaces * (2 + self.gaussian_adapter.d_in)))
         # the high-resolution skip only exists without downscaling (:104-111)
-        self.high_resolution_skip = nn.Sequential(nn.Conv2d(3, cfg.d_feature, 7, 1, 3), nn.ReLU()) \
+        self.high_resolution_skip = nn.Sequential(Conv2d(3, cfg.d_feature, 7, 1, 3), nn.ReLU()) \
             if scale_factor == 1 else None
 
     def map_pdf_to_opacity(self, pdf: Tensor, global_step: int) -> Tensor:

@@ -22,6 +22,7 @@ from .epipolar_sampler import EpipolarSampler, EpipolarSampling
 from .image_self_attention import ImageSelfAttention, ImageSelfAttentionCfg
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200 import epipolar_gather as fused_gather
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 
 @dataclass
@@ -41,8 +42,8 @@ class ConvFeedForward(nn.Module):
 
     def __init__(self, self_attention_cfg: ImageSelfAttentionCfg, d_in: int, d_hidden: int, dropout: float) -> None:
         super().__init__()
-        self.layers = nn.Sequential(nn.Conv2d(d_in, d_hidden, 7, 1, 3), nn.GELU(), nn.Dropout(dropout),
-                                    nn.Conv2d(d_hidden, d_in, 7, 1, 3), nn.Dropout(dropout))
+        self.layers = nn.Sequential(Conv2d(d_in, d_hidden, 7, 1, 3), nn.GELU(), nn.Dropout(dropout),
+                                    Conv2d(d_hidden, d_in, 7, 1, 3), nn.Dropout(dropout))
         self.self_attention = ImageSelfAttention(self_attention_cfg, d_in, d_in)
 
     def forward(self, x: Tensor, b: int, v: int, h: int, w: int) -> Tensor:
@@ -63,10 +64,10 @@ class EpipolarTransformer(nn.Module):
         self.transformer = Transformer(d_in, cfg.num_layers, cfg.num_heads, cfg.d_dot, cfg.d_mlp, selfatt=False,
                                        kv_dim=d_in, feed_forward_layer=partial(ConvFeedForward, cfg.self_attention))
         if cfg.downscale > 1:
-            self.downscaler = nn.Conv2d(d_in, d_in, cfg.downscale, cfg.downscale)
+            self.downscaler = Conv2d(d_in, d_in, cfg.downscale, cfg.downscale)
             self.upscaler = nn.ConvTranspose2d(d_in, d_in, cfg.downscale, cfg.downscale)
-            self.upscale_refinement = nn.Sequential(nn.Conv2d(d_in, d_in * 2, 7, 1, 3), nn.GELU(),
-                                                    nn.Conv2d(d_in * 2, d_in, 7, 1, 3))
+            self.upscale_refinement = nn.Sequential(Conv2d(d_in, d_in * 2, 7, 1, 3), nn.GELU(),
+                                                    Conv2d(d_in * 2, d_in, 7, 1, 3))
         else:
             self.downscaler = self.upscaler = self.upscale_refinement = None
 
