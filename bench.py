@@ -582,9 +582,9 @@ def full_stage_profile(pipe, dev_flat, cfg, fwd_bwd):
     flops = 2.0 * M * N * K
     tf32_peak, tf32_src = tf32_peak_tflops()
     traffic = None
-    prof = ROOT / "profiles" / "r01_ncu_traffic.json"
+    prof = ROOT / "profiles" / "r01_full_ncu_traffic.json"
     if prof.exists():
-        traffic = json.loads(prof.read_text()).get("gemm_dino_qkv", {}).get("dram_bytes_per_launch")
+        traffic = json.loads(prof.read_text()).get("gemm_dino_fc1", {}).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": f"k_gemm_tf32 (DINO fc1 {M}x{N}x{K}, TMA + tcgen05.mma kind::tf32)",
                 "achieved": flops / (g_ms / 1000) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": flops / (g_ms / 1000) / 1e12 / tf32_peak, "traffic": traffic, "peak_source": tf32_src,
@@ -799,7 +799,7 @@ def run_ours(args, cfg):
         dom = max(ms, key=ms.get)
         ach = nbytes[dom] / (ms[dom] / 1000) / 1e9
         traffic = None
-        prof = ROOT / "profiles" / "r01_ncu_traffic.json"
+        prof = ROOT / "profiles" / "r01_splat_ncu_traffic.json"
         if prof.exists():
             traffic = json.loads(prof.read_text()).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

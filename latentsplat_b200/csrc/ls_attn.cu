@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(256) k_sq_attn_bwd(const float* __restrict__ q
 // One warp per ray; all heads share each z row, which is read from HBM exactly once per pass.
 constexpr int kMaxHeads = 8;
 
+// kMaxHeads is a template parameter: the per-head register arrays (absorbed query, gradient, accumulators: 3 float4 + 3
+// scalars per head in backward) set the occupancy -- sized for 8 heads the backward kernel needs 136 registers (one block
+// per SM, 12 % warps active, 1.09 ms); sized for the 4 heads the model uses it fits three.
+template <int kMaxHeads>
 __global__ void __launch_bounds__(256) k_absorbed_attn_fwd(const float* __restrict__ qt, const float* __restrict__ z,
                                                            float* __restrict__ zbar, float* __restrict__ p, int R, int H,
                                                            int S, float scale) {
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(256) k_absorbed_attn_fwd(const float* __restri
         if (h < H) q4[h] = *reinterpret_cast<const float4*>(qt + ((size_t)r * H + h) * D + 4 * lane);
     }
     const float* zr = z + (size_t)r * S * D + 4 * lane;
+#pragma unroll 4
     for (int j = 0; j < S; ++j) {
         const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
 #pragma unroll
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(256) k_absorbed_attn_fwd(const float* __restri
     float4 acc[kMaxHeads];
 #pragma unroll
     for (int h = 0; h < kMaxHeads; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int j = 0; j < S; ++j) {
         const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
 #pragma unroll
@@ -155,7 +161,8 @@ __global__ void __launch_bounds__(256) k_absorbed_attn_fwd(const float* __restri
         if (h < H) *reinterpret_cast<float4*>(zbar + ((size_t)r * H + h) * D + 4 * lane) = acc[h];
 }
 
-__global__ void __launch_bounds__(256) k_absorbed_attn_bwd(const float* __restrict__ qt, const float* __restrict__ z,
+template <int kMaxHeads>
+__global__ void __launch_bounds__(256, kMaxHeads <= 4 ? 3 : 1) k_absorbed_attn_bwd(const float* __restrict__ qt, const float* __restrict__ z,
                                                            const float* __restrict__ p, const float* __restrict__ dzbar,
                                                            float* __restrict__ dqt, float* __restrict__ dz, int R, int H,
                                                            int S, float scale) {
@@ -174,6 +181,7 @@ __global__ void __launch_bounds__(256) k_absorbed_attn_bwd(const float* __restri
         }
     }
     const float* zr = z + (size_t)r * S * D + 4 * lane;
+#pragma unroll 2
     for (int j = 0; j < S; ++j) {
         const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
 #pragma unroll
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(256) k_absorbed_attn_bwd(const float* __restri
     for (int h = 0; h < kMaxHeads; ++h)
         if (h < H) ds[h] = prob[h] * (dp[h] - warp_sum(prob[h] * dp[h])) * scale;
     float* dzr = dz + (size_t)r * S * D + 4 * lane;
+#pragma unroll 2
     for (int j = 0; j < S; ++j) {
         const float4 z4 = *reinterpret_cast<const float4*>(zr + (size_t)j * D);
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -214,7 +223,8 @@ extern "C" LS_API int ls_absorbed_attention_forward(const float* qt, const float
     if (Dz != lsa::D) return ls_fail("absorbed attention: sample width %d != 128", Dz);
     if (S < 1 || S > 32 || H < 1 || H > lsa::kMaxHeads) return ls_fail("absorbed attention: S=%d (1..32) H=%d (1..8)", S, H);
     if (R <= 0) return 0;
-    lsa::k_absorbed_attn_fwd<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, zbar, p, R, H, S, scale);
+    if (H <= 4) lsa::k_absorbed_attn_fwd<4><<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, zbar, p, R, H, S, scale);
+    else lsa::k_absorbed_attn_fwd<8><<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, zbar, p, R, H, S, scale);
     return ls_check_cuda("k_absorbed_attn_fwd");
 }
 
@@ -224,7 +234,8 @@ extern "C" LS_API int ls_absorbed_attention_backward(const float* qt, const floa
     if (Dz != lsa::D) return ls_fail("absorbed attention: sample width %d != 128", Dz);
     if (S < 1 || S > 32 || H < 1 || H > lsa::kMaxHeads) return ls_fail("absorbed attention: S=%d (1..32) H=%d (1..8)", S, H);
     if (R <= 0) return 0;
-    lsa::k_absorbed_attn_bwd<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, p, dzbar, dqt, dz, R, H, S, scale);
+    if (H <= 4) lsa::k_absorbed_attn_bwd<4><<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, p, dzbar, dqt, dz, R, H, S, scale);
+    else lsa::k_absorbed_attn_bwd<8><<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(qt, z, p, dzbar, dqt, dz, R, H, S, scale);
     return ls_check_cuda("k_absorbed_attn_bwd");
 }
 
