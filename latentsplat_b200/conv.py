@@ -18,13 +18,14 @@ class _ConvBiasFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, stride, padding, dilation, groups: int):
         y = torch.ops.aten.convolution(x, weight, None, stride, padding, dilation, False, [0, 0], groups)
-        if not y.is_contiguous():
-            y = y.contiguous()
-        N, Cn = y.shape[:2]
-        with torch.cuda.device(x.device):
-            _capi.check(_capi.load().ls_conv_bias_add(y.data_ptr(), bias.data_ptr(), N, Cn, y[0, 0].numel(),
-                                                      torch.cuda.current_stream().cuda_stream), "ls_conv_bias_add")
-        _capi.KERNEL_LAUNCHES[0] += 1
+        if y.is_contiguous():
+            N, Cn = y.shape[:2]
+            with torch.cuda.device(x.device):
+                _capi.check(_capi.load().ls_conv_bias_add(y.data_ptr(), bias.data_ptr(), N, Cn, y[0, 0].numel(),
+                                                          torch.cuda.current_stream().cuda_stream), "ls_conv_bias_add")
+            _capi.KERNEL_LAUNCHES[0] += 1
+        else:       # channels-last output (the input arrived channels-last): the bias is the fastest-varying axis, torch's
+            y.add_(bias.view(1, -1, 1, 1))      # vectorised row-broadcast add is already right; never force a layout copy
         ctx.save_for_backward(x, weight)
         ctx.cfg = (stride, padding, dilation, groups)
         return y
@@ -33,11 +34,12 @@ class _ConvBiasFn(torch.autograd.Function):
     def backward(ctx, gy: Tensor):
         x, weight = ctx.saved_tensors
         stride, padding, dilation, groups = ctx.cfg
-        gy = gy.contiguous()
         gx, gw, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, stride, padding, dilation, False, [0, 0], groups,
                                                         [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         gb = None
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2] and not gy.is_contiguous():
+            gb = gy.sum(dim=(0, 2, 3))
+        elif ctx.needs_input_grad[2]:
             N, Cn = gy.shape[:2]
             gb = torch.zeros(Cn, dtype=torch.float32, device=gy.device)
             with torch.cuda.device(gy.device):

@@ -79,6 +79,46 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+class _GroupedLinearFn(torch.autograd.Function):
+    """y[g] = x[g] @ w[g]^T + b[g] for g groups with their own weights (x (G, M, K), w (G, N, K), b (G, N)): one autograd
+    node, G GEMM launches writing straight into slices of one output / one input-gradient tensor (slicing at the autograd
+    level would add a zero-fill + accumulate pass over the whole activation per group)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor):
+        G, M, K = x.shape
+        N = weight.shape[1]
+        y = torch.empty((G, M, N), dtype=torch.float32, device=x.device)
+        for g in range(G):
+            gemm_tf32(x[g], weight[g], M=M, N=N, K=K, bias=bias[g], out=y[g])
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x, weight = ctx.saved_tensors
+        G, M, K = x.shape
+        N = weight.shape[1]
+        gy = gy.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
+        for g in range(G):
+            if gx is not None:
+                gemm_tf32(gy[g], weight[g], M=M, N=K, K=N, b_mn=True, out=gx[g])
+            if gw is not None:
+                gemm_tf32(gy[g], x[g], M=N, N=K, K=M, a_mn=True, b_mn=True, out=gw[g])
+        gb = gy.sum(dim=1) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
+def grouped_linear(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """x (G, M, K), weight (G, N, K), bias (G, N) -> (G, M, N); CUDA fp32 on the tcgen05 GEMM, else a batched matmul."""
+    if (x.is_cuda and enabled and x.dtype == torch.float32 and x.shape[2] % 4 == 0 and weight.shape[1] % 4 == 0
+            and x.shape[1] > 0):
+        return _GroupedLinearFn.apply(x.contiguous(), weight.contiguous(), bias.contiguous())
+    return torch.baddbmm(bias[:, None], x, weight.transpose(1, 2))
+
+
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = "none") -> Tensor:
     """F.linear(+activation) on the tcgen05 GEMM when possible (CUDA fp32, TMA-compatible strides)."""
     if x.is_cuda and enabled and x.dtype == torch.float32 and weight.dtype == torch.float32 and act != "gelu":

@@ -28,7 +28,7 @@ from .encoder import Encoder
 from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
 from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
 from .shims import apply_bounds_shim, apply_patch_shim
-from latentsplat_b200.gemm import Linear, linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200.gemm import Linear, grouped_linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
 
 
@@ -119,9 +119,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
             t[:, :, o + 2:o + d, o + 2:o + d] = t_adapter
         weight = t @ lin.weight                                                                 # (b, v, srf*d, d_feature)
         bias = (t @ lin.bias[:, None])[..., 0]
-        x = act(features)
-        rows = [linear(x[i, j], weight[i, j], bias[i, j]) for i in range(b) for j in range(v)]
-        return torch.stack(rows).unflatten(0, (b, v))
+        return grouped_linear(act(features).flatten(0, 1), weight.flatten(0, 1), bias.flatten(0, 1)).unflatten(0, (b, v))
 
     def forward(self, context: dict, global_step: int, features: Optional[Tensor] = None,
                 deterministic: bool = False, visualization_dump: Optional[dict] = None) -> VariationalGaussians:

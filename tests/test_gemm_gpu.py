@@ -306,3 +306,22 @@ def test_conv2d_bias_kernels_match_nn_conv2d(cuda, shape, k, stride):
         res.append((y.detach(), xi.grad, m.weight.grad, m.bias.grad))
     for a, b, name in zip(res[0], res[1], ("y", "dx", "dW", "db")):
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-5, f"{name}: {(a - b).abs().max().item():.3e}"
+
+
+def test_grouped_linear_matches_baddbmm(cuda):
+    """gemm.grouped_linear (one autograd node, G GEMMs into slices) == baddbmm in float64: y, dx, dW, db."""
+    from latentsplat_b200.gemm import grouped_linear
+    g = torch.Generator(cuda).manual_seed(2)
+    x = torch.randn(3, 1000, 128, device=cuda, generator=g, requires_grad=True)
+    w = (torch.randn(3, 156, 128, device=cuda, generator=g) / 128 ** 0.5).requires_grad_(True)
+    b = torch.randn(3, 156, device=cuda, generator=g, requires_grad=True)
+    wt = torch.randn(3, 1000, 156, device=cuda, generator=g)
+    y = grouped_linear(x, w, b)
+    (y * wt).sum().backward()
+    got = [y.detach().double(), x.grad.double(), w.grad.double(), b.grad.double()]
+    x.grad = w.grad = b.grad = None
+    ref = torch.baddbmm(b.double()[:, None], x.double(), w.double().transpose(1, 2))
+    (ref * wt.double()).sum().backward()
+    want = [ref.detach(), x.grad.double(), w.grad.double(), b.grad.double()]
+    for a, r, name in zip(got, want, ("y", "dx", "dW", "db")):
+        assert (a - r).abs().max().item() <= 2e-2 * r.abs().max().item(), f"{name}: {(a - r).abs().max().item():.3e}"   # TF32
