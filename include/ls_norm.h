@@ -53,6 +53,10 @@ LS_API int ls_layernorm_backward(const float* x, const float* dy, const float* g
 LS_API int ls_conv_bias_add(float* y, const float* bias, int64_t N, int32_t C, int64_t HW, void* stream /* cudaStream_t */);
 LS_API int ls_conv_bias_grad(const float* dy, float* dbias, int64_t N, int32_t C, int64_t HW, void* stream /* cudaStream_t */);
 
+/* out[c] += sum_r x[r*ld + c] for a row-major (rows, cols) fp32 matrix: the bias gradient `dY.sum(0)` of every nn.Linear
+ * on the path (see ls_gemm.h for the list).  ACCUMULATES (the caller zero-fills out); x 16-byte aligned, ld % 4 == 0. */
+LS_API int ls_col_sum(const float* x, float* out, int64_t rows, int32_t cols, int64_t ld, void* stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

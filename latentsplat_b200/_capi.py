@@ -85,7 +85,7 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
            "ls_absorbed_attention_forward", "ls_absorbed_attention_backward",
            "ls_epipolar_gather_forward", "ls_epipolar_gather_backward", "ls_groupnorm_forward", "ls_groupnorm_backward",
-           "ls_layernorm_forward", "ls_layernorm_backward", "ls_conv_bias_add", "ls_conv_bias_grad")
+           "ls_layernorm_forward", "ls_layernorm_backward", "ls_conv_bias_add", "ls_conv_bias_grad", "ls_col_sum")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -141,6 +141,8 @@ def load() -> C.CDLL:
     for fn in (lib.ls_conv_bias_add, lib.ls_conv_bias_grad):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]
+    lib.ls_col_sum.restype = C.c_int
+    lib.ls_col_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]
     if lib.ls_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libls_raster.so ABI {lib.ls_raster_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -48,6 +48,19 @@ def gemm_tf32(A: Tensor, B: Tensor, *, M: int, N: int, K: int, a_mn: bool = Fals
     return out
 
 
+def col_sum(x2d: Tensor) -> Tensor:
+    """x2d.sum(dim=0) for a row-major CUDA fp32 matrix on libls_raster.so::ls_col_sum (bias gradients)."""
+    if not (x2d.is_cuda and x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.stride(0) % 4 == 0
+            and x2d.data_ptr() % 16 == 0 and x2d.shape[0] > 0):
+        return x2d.sum(dim=0)
+    out = torch.zeros(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        _capi.check(_capi.load().ls_col_sum(x2d.data_ptr(), out.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0),
+                                            torch.cuda.current_stream().cuda_stream), "ls_col_sum")
+    _capi.KERNEL_LAUNCHES[0] += 1
+    return out
+
+
 def _aligned(t: Tensor) -> bool:
     return t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0
 
@@ -75,7 +88,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:      # dW = dY^T X   : both operands MN-major, reduce over M (split-K)
             gw = gemm_tf32(gy, x2d, M=N, N=K, K=M, a_mn=True, b_mn=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(dim=0)
+            gb = col_sum(gy)
         return gx, gw, gb, None
 
 
@@ -107,7 +120,7 @@ class _GroupedLinearFn(torch.autograd.Function):
                 gemm_tf32(gy[g], weight[g], M=M, N=K, K=N, b_mn=True, out=gx[g])
             if gw is not None:
                 gemm_tf32(gy[g], x[g], M=N, N=K, K=M, a_mn=True, b_mn=True, out=gw[g])
-        gb = gy.sum(dim=1) if ctx.needs_input_grad[2] else None
+        gb = torch.stack([col_sum(gy[g]) for g in range(G)]) if ctx.needs_input_grad[2] else None
         return gx, gw, gb
 
 

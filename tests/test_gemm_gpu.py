@@ -325,3 +325,13 @@ def test_grouped_linear_matches_baddbmm(cuda):
     want = [ref.detach(), x.grad.double(), w.grad.double(), b.grad.double()]
     for a, r, name in zip(got, want, ("y", "dx", "dW", "db")):
         assert (a - r).abs().max().item() <= 2e-2 * r.abs().max().item(), f"{name}: {(a - r).abs().max().item():.3e}"   # TF32
+
+
+@pytest.mark.parametrize("rows,cols,ld", [(8200, 768, 768), (65536, 156, 156), (1000, 158, 160), (7, 4, 4)])
+def test_col_sum_matches_torch(cuda, rows, cols, ld):
+    from latentsplat_b200.gemm import col_sum
+    g = torch.Generator(cuda).manual_seed(1)
+    x = torch.randn(rows, ld, device=cuda, generator=g)[:, :cols]
+    got, want = col_sum(x).double(), x.double().sum(dim=0)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 1e-5 * x.abs().double().sum(dim=0).max().item() + 1e-6
