@@ -68,3 +68,55 @@ def test_synthetic_generator_is_deterministic_and_in_frustum():
     ev = torch.linalg.eigvalsh(a.covariances.double())
     assert (ev > 0).all()
     assert synthetic.sh_mask(2).tolist() == pytest.approx([1.0] + [0.025] * 3 + [0.00625] * 5)
+
+
+def test_harmonics_transform_equals_mask_then_rotate():
+    """GaussianAdapter.harmonics_transform(c2w) @ raw == the adapter's own masking + per-degree SH rotation of the raw
+    colour / feature blocks (gaussian_adapter.py:44-61, 104-105) and the identity on scales / rotation."""
+    import torch
+    from latentsplat_b200.model.encoder.common.gaussian_adapter import GaussianAdapter, GaussianAdapterCfg
+    torch.manual_seed(0)
+    ad = GaussianAdapter(GaussianAdapterCfg(0.5, 15.0, 4, 2), n_feature_channels=8).double()
+    q = torch.nn.functional.normalize(torch.randn(2, 3, 4, dtype=torch.float64), dim=-1)
+    from latentsplat_b200.model.encoder.common.gaussians import quaternion_to_matrix
+    rot = quaternion_to_matrix(q)                                           # (2, 3, 3, 3) proper rotations
+    raw = torch.randn(2, 3, 5, ad.d_in, dtype=torch.float64)               # 5 rays per view
+    t = ad.harmonics_transform(rot)                                         # (2, 3, d_in, d_in)
+    folded = torch.einsum("bvij,bvrj->bvri", t, raw)
+    scales, rots, csh, fsh = raw.split((3, 4, 3 * ad.d_color_sh, 8 * ad.d_feature_sh), dim=-1)
+    csh = csh.unflatten(-1, (3, ad.d_color_sh)) * ad.color_sh_mask
+    fsh = fsh.unflatten(-1, (8, ad.d_feature_sh)) * ad.feature_sh_mask
+    r = rot[:, :, None]                                                     # broadcast over rays
+    want = torch.cat((scales, rots, ad._rotate(csh, r, 4).flatten(-2), ad._rotate(fsh, r, 2).flatten(-2)), dim=-1)
+    torch.testing.assert_close(folded, want, rtol=1e-9, atol=1e-10)
+
+
+def test_epipolar_image_index_matches_the_transposes_around_grid_sample():
+    """EpipolarSampler.image_index(b, rays)[row] is the feature map the explicit transpose -> grid_sample -> transpose
+    sequence samples for that row: with every feature map constant (= its flattened index) the sampled features say so."""
+    import torch
+    from latentsplat_b200.model.encoder.epipolar.epipolar_sampler import EpipolarSampler
+    b, v, c, h, w = 2, 2, 3, 8, 8
+    sampler = EpipolarSampler(v, 4)
+    images = torch.arange(b * v, dtype=torch.float32).reshape(b, v, 1, 1, 1).expand(b, v, c, h, w).contiguous() + 1
+    ex = torch.eye(4).repeat(b, v, 1, 1)
+    ex[:, 1, 0, 3] = 0.2
+    intr = torch.tensor([[0.9, 0, 0.5], [0, 0.9, 0.5], [0, 0, 1.0]]).repeat(b, v, 1, 1)
+    near, far = torch.full((b, v), 1.0), torch.full((b, v), 20.0)
+    s = sampler(images, ex, intr, near, far)
+    idx = sampler.image_index(b, h * w).reshape(b, v, v - 1, h * w)
+    feat = s.features[..., 0]                                               # (b, v, ov, r, s)
+    inside = (s.xy_sample > 0.1).all(-1) & (s.xy_sample < 0.9).all(-1) & s.valid[..., None]
+    assert inside.any()
+    want = (idx[..., None].float() + 1).expand_as(feat)
+    torch.testing.assert_close(feat[inside], want[inside])
+
+
+def test_flat_gradients_follow_channels_last_parameters():
+    import torch
+    from latentsplat_b200.parallel import FlatGradients
+    conv = torch.nn.Conv2d(4, 6, 3).to(memory_format=torch.channels_last)
+    fg = FlatGradients(conv.parameters())
+    assert conv.weight.grad.stride() == conv.weight.stride()
+    conv(torch.randn(2, 4, 8, 8)).sum().backward()
+    assert float(fg.flat.abs().sum()) > 0 and fg.flat.numel() == sum(p.numel() for p in conv.parameters())
