@@ -1,0 +1,36 @@
+"""CPU: bench.py's contract where it can be checked without a GPU -- the reference arm prints ONE JSON line with the keys
+the driver reads, and the product arm refuses to run without CUDA (no CPU fallback)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _run(*args, timeout=600):
+    return subprocess.run([sys.executable, str(ROOT / "bench.py"), *args], capture_output=True, text=True, timeout=timeout,
+                          cwd=ROOT)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--resolution", "64", "--batch", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "novel_views_per_sec_fwd_bwd_256x256" and d["unit"] == "views/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_product_arm_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = _run("--steps", "1", "--warmup", "0", timeout=300)
+    assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
