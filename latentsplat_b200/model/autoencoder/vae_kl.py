@@ -54,7 +54,9 @@ class Attention(nn.Module):
         q, k, v = self.to_q(t), self.to_k(t), self.to_v(t)
         t = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
         t = self.to_out[1](self.to_out[0](t))
-        return t.transpose(1, 2).reshape(b, c, h, w) + x
+        # x first: the sum inherits x's NCHW layout.  With the (b, hw, c)-strided view first the result is channels-last and
+        # every later residual `x + h` keeps that layout, so each GroupNorm / convolution up the decoder pays a layout copy.
+        return x + t.transpose(1, 2).reshape(b, c, h, w)
 
 
 class UNetMidBlock2D(nn.Module):
