@@ -38,7 +38,11 @@ class _ConvBiasFn(torch.autograd.Function):
                                                         [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         gb = None
         if ctx.needs_input_grad[2] and not gy.is_contiguous():
-            gb = gy.sum(dim=(0, 2, 3))
+            if gy.is_contiguous(memory_format=torch.channels_last):      # memory is a row-major (N*H*W, C) matrix
+                from .gemm import col_sum
+                gb = col_sum(gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1]))
+            else:
+                gb = gy.sum(dim=(0, 2, 3))
         elif ctx.needs_input_grad[2]:
             N, Cn = gy.shape[:2]
             gb = torch.zeros(Cn, dtype=torch.float32, device=gy.device)
