@@ -854,12 +854,20 @@ def main():
     global H, W
     H = W = args.resolution
     cfg = dict(CFG, V_t=args.target_views, G=args.gaussians, B=args.batch, workload=args.workload)
+    # stdout carries exactly ONE JSON line: anything a library writes to file descriptor 1 while we run (NCCL prints
+    # "NCCL version ..." there on communicator creation, whatever NCCL_DEBUG says) is sent to stderr, and `print` is bound
+    # to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args, cfg)
     elif args.workload == "full":
         run_full(args, cfg)
     else:
         run_ours(args, cfg)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
