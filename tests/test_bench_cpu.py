@@ -34,3 +34,16 @@ def test_product_arm_refuses_to_run_without_cuda():
         pytest.skip("a GPU is present")
     r = _run("--steps", "1", "--warmup", "0", timeout=300)
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_under_torchrun_only_rank0_prints():
+    """N > 1 launch of the reference arm: rank 0 runs and prints the line, the other ranks exit 0 without work."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(ROOT / "bench.py"), "--gpus", "2", "--impl", "reference",
+                        "--steps", "1", "--warmup", "0", "--resolution", "64", "--batch", "1"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0
