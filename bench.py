@@ -44,13 +44,13 @@ CFG = dict(B=4, V_t=1, V_c=2, G=65_536, C=4, color_sh_degree=4, feature_sh_degre
 
 def workload_name(cfg) -> str:
     if cfg.get("workload", "splat") == "full":
-        return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views 256x256, "
+        return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views {H}x{W}, "
                 f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
                 "views -> VAE kl-f8 decoder with skips -> PatchGAN logits; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
                 "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar gather + depth encoding, weight-absorbed epipolar cross-attention, "
                 "GroupNorm+SiLU, LayerNorm; library: cuDNN convolutions (TF32), DINO / VAE-mid attention cores (bf16 flash / "
                 "mem-efficient SDPA), remaining elementwise glue (torch)")
-    return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views 256x256, "
+    return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views {H}x{W}, "
             f"G={cfg['G']} feature Gaussians/scene (colour SH deg {cfg['color_sh_degree']} + C={cfg['C']} feature SH "
             f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA fwd+bwd with scalar loss heads; "
             "encoder + VAE decoder of configs[1] not yet in the timed step")
@@ -263,7 +263,7 @@ def cpu_baseline(cfg, batch, min_seconds=10.0, max_views=64, threads=0):
         if el >= min_seconds or views >= max_views:
             break
     return {"value": views / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{views} single 256x256 views of G={G} (fwd+bwd, oracle/raster_oracle.c with OpenMP) in {el:.1f}s"}
+            "sample": f"{views} single {H}x{W} views of G={G} (fwd+bwd, oracle/raster_oracle.c with OpenMP) in {el:.1f}s"}
 
 
 def _sh_eval_np(deg, sh, dirs):
@@ -691,7 +691,7 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg), "step": "one 256x256 view fwd+bwd per step (bounded sample)"},
+            "config": {"workload": workload_name(cfg), "step": f"one {H}x{W} view fwd+bwd per step (bounded sample)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port",
                              "sample": "1 view of the workload per step, all host threads (OpenMP)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -819,7 +819,8 @@ def run_ours(args, cfg):
         ach = nbytes[dom] / (ms[dom] / 1000) / 1e9
         traffic = None
         prof = ROOT / "profiles" / "r01_splat_ncu_traffic.json"
-        if prof.exists():
+        default_shape = (H, cfg["G"], cfg["B"], cfg["V_t"]) == (256, CFG["G"], CFG["B"], CFG["V_t"])
+        if prof.exists() and default_shape:                  # the ncu capture was taken at the default shape only
             traffic = json.loads(prof.read_text()).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "num_rendered": num_rendered,
