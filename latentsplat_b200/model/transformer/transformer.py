@@ -1,25 +1,57 @@
-"""Pre-norm transformer stack (/root/reference/src/model/transformer/transformer.py:32-71):
-layers[i] = ModuleList([PreNorm(Attention), PreNorm(feed_forward_layer)]); x <- attn(x, z)+x; x <- ff(x)+x.
-Note that in cross-attention only x is normalised, z (keys/values) is used raw."""
-from torch import nn
+"""Pre-norm transformer stack with its two small building blocks.
+
+Parameter tree of /root/reference/src/model/transformer/{transformer.py:32-71, pre_norm.py:28-35, feed_forward.py:28-40}:
+`layers[i] = ModuleList([PreNorm(Attention), PreNorm(feed_forward_layer)])` with `PreNorm.{norm, fn}` and
+`FeedForward.net = Sequential(Linear, GELU, Dropout, Linear, Dropout)`;  x <- attn(x, z) + x;  x <- ff(x) + x.
+In cross-attention only x is normalised, z (keys/values) is used raw.  LayerNorm and the Linears run on our sm_100a
+kernels on CUDA (latentsplat_b200.norm / .gemm)."""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+from torch import Tensor, nn
+
+from latentsplat_b200.gemm import Linear
+from latentsplat_b200.norm import LayerNorm
 
 from .attention import Attention
-from .feed_forward import FeedForward
-from .pre_norm import PreNorm
+
+
+class FeedForward(nn.Module):
+    """Token MLP dim -> hidden_dim -> dim with GELU."""
+
+    def __init__(self, dim: int, hidden_dim: int, dropout: float = 0.0) -> None:
+        super().__init__()
+        stages = [Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout), Linear(hidden_dim, dim), nn.Dropout(dropout)]
+        self.net = nn.Sequential(*stages)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.net(x)
+
+
+class PreNorm(nn.Module):
+    """fn(LayerNorm(x), **kwargs): `norm` normalises the token dimension, extra keyword arguments go to `fn` untouched."""
+
+    def __init__(self, dim: int, fn: nn.Module) -> None:
+        super().__init__()
+        self.norm = LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x: Tensor, **kwargs) -> Tensor:
+        return self.fn(self.norm(x), **kwargs)
 
 
 class Transformer(nn.Module):
-    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.0, selfatt=True, kv_dim=None,
-                 feed_forward_layer=FeedForward):
+    def __init__(self, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int, dropout: float = 0.0,
+                 selfatt: bool = True, kv_dim: Optional[int] = None,
+                 feed_forward_layer: Callable[..., nn.Module] = FeedForward) -> None:
         super().__init__()
-        self.layers = nn.ModuleList([
-            nn.ModuleList([
-                PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout, selfatt=selfatt,
-                                       kv_dim=kv_dim)),
-                PreNorm(dim, feed_forward_layer(dim, mlp_dim, dropout=dropout)),
-            ]) for _ in range(depth)])
+        def block() -> nn.ModuleList:
+            attention = Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout, selfatt=selfatt, kv_dim=kv_dim)
+            return nn.ModuleList([PreNorm(dim, attention), PreNorm(dim, feed_forward_layer(dim, mlp_dim, dropout=dropout))])
+        self.layers = nn.ModuleList([block() for _ in range(depth)])
 
-    def forward(self, x, z=None, **kwargs):
+    def forward(self, x: Tensor, z: Optional[Tensor] = None, **kwargs) -> Tensor:
         for attn, ff in self.layers:
             x = attn(x, z=z) + x
             x = ff(x, **kwargs) + x
