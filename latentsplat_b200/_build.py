@@ -37,14 +37,28 @@ def is_stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [ROOT / "include" / "ls_raster.h"]
+    deps = list(CSRC.glob("*")) + list((ROOT / "include").glob("*.h"))
     return any(d.stat().st_mtime > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Build if stale.  Safe to call from several processes at once (one rank per GPU under torchrun): an exclusive file
+    lock serialises them, the link goes to a temporary name and is renamed into place, late-comers find a fresh library."""
     if not force and not is_stale():
         return LIB
+    import fcntl
     LIB_DIR.mkdir(exist_ok=True)
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
     obj_dir = LIB_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
     nvcc = _nvcc()
@@ -67,12 +81,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src.name}:\n{out}")
         if verbose and out:
             print(out)
+    tmp = LIB.with_suffix(f".so.tmp{os.getpid()}")
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin",
-            "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-o", str(LIB),
+            "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-o", str(tmp),
             *map(str, objs), "-lcudart"]
     r = subprocess.run(link, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)
     return LIB
 
 
