@@ -299,6 +299,226 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
 }
 
+// =================================================================================================================
+// EXPERIMENTAL (off unless LS_GEMM_2CTA=1): cta_group::2 variant -- a cluster of two CTAs (one TPC) owns a 256 x BN tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows); the leader's tcgen05.mma.cta_group::2 reads
+// A and B from both CTAs' shared memory, so per MMA (135 tensor cycles at M256 N256 K8) a CTA streams 4 KB of A +
+// 4 KB of B instead of 4 + 8 KB -- the shared-memory bandwidth that caps the 1-CTA kernel at 57-60 % tensor pipe.
+// Protocol (CUTLASS sm100 PipelineTmaUmmaAsync / Allocator2Sm, restated):
+//   full[s]   lives in the leader; armed by the leader's producer with the bytes of BOTH CTAs; each CTA's TMA
+//             (cp.async.bulk.tensor...cta_group::2) signals it through the peer-bit-cleared barrier address
+//   empty[s]  one per CTA, released by the leader's tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11)
+//   tfull[a]  one per CTA, same multicast commit -> each CTA's epilogue drains its own 128 TMEM lanes
+//   tempty[a] lives in the leader, 8 arrivals (4 epilogue warps x 2 CTAs; the peer arrives through shared::cluster)
+// Round-1 status: passes tests/test_gemm_gpu.py (all four operand layouts, tails, split-K, bias/activation, Linear
+// forward/backward) with LS_GEMM_2CTA=1 and is 4-13 % faster than the 1-CTA kernel on the DINO shapes
+// (scripts/gemm_ab.py: 8200x3072x768 506 -> 525 TF/s, 8200x768x3072 429 -> 484 TF/s); it stays opt-in until the
+// whole step has been validated with it and the remaining limiter (epilogue drain / wave quantisation) is profiled.
+// =================================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;        // shared::cluster address of the even (leader) CTA's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
+                 const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic,
+                 int tiles_m, int tiles_n, int splits) {
+    constexpr int BH = BN / 2;                                   // rows of B staged by each CTA
+    constexpr int STAGE_BYTES = A_BYTES + BH * BK * 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PATCH_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int nkb_total = (K + BK - 1) / BK;
+    const int n_items = tiles_m * tiles_n * splits;               // tiles_m counts 256-row tiles here
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                          // barriers of both CTAs initialised, TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    auto decode = [&](int item, int& tile_m, int& tile_n, int& kb0, int& nkb) {
+        tile_n = item % tiles_n;
+        const int rest = item / tiles_n;
+        tile_m = rest % tiles_m;
+        kb0 = (rest / tiles_m) * kb_per_split;
+        nkb = min(nkb_total, kb0 + kb_per_split) - kb0;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer (both CTAs) ------------------------------
+        uint32_t it = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const int m0 = tile_m * 2 * BM + (int)rank * BM, n0 = tile_n * BN + (int)rank * BH;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);                                   // own stage is free
+                if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);       // bytes of both CTAs
+                const uint32_t leader_full = (full0 + 8 * s) & kPeerBitMask;
+                const int k0 = (kb0 + kb) * BK;
+                const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                if (!A_MN) {
+                    tma_load_2d_2sm(a_dst, &map_a, leader_full, k0, m0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j) tma_load_2d_2sm(a_dst + j * 4096, &map_a, leader_full, m0 + 32 * j, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d_2sm(b_dst, &map_b, leader_full, k0, n0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BH / 32; ++j) tma_load_2d_2sm(b_dst + j * 4096, &map_b, leader_full, n0 + 32 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------ MMA issuer (leader CTA only) --------------------------
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+        uint32_t it = 0, local = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++local) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);            // both CTAs' epilogues have drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+                    const uint64_t bdesc = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
+                    tc_mma_tf32_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit_2sm(empty0 + 8 * s);       // releases the stage in BOTH CTAs
+            }
+            tc_commit_2sm(tfull0 + 8 * acc);         // accumulator complete, both CTAs
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue (both CTAs, own 128 rows) --------------------
+        const int q = warp - 4;
+        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        uint32_t local = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++local) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tc_fence_after();
+            const bool add_bias = bias != nullptr && kb0 == 0;
+            const int row_base = tile_m * 2 * BM + (int)rank * BM + q * 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = tile_n * BN + c0;
+                if (col0 >= N) break;
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const int col = col0 + sub_c;
+                float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (add_bias) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) if (col + t < N) b4[t] = bias[col + t];
+                }
+                float4 rows4[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = row_base + 4 * i + sub_r;
+                    const float4 v4 = rows4[i];
+                    float v[4] = {apply_act(v4.x + b4[0], act), apply_act(v4.y + b4[1], act), apply_act(v4.z + b4[2], act),
+                                  apply_act(v4.w + b4[3], act)};
+                    if (row < M) {
+                        float* dst = C + (long long)row * ldc + col;
+                        if (!atomic && vec_ok && col + 3 < N) {
+                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (col + t < N) {
+                                    if (atomic) atomicAdd(dst + t, v[t]); else dst[t] = v[t];
+                                }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty0 + 8 * acc);    // 8 arrivals (2 CTAs x 4 warps) release it
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                              // nobody frees TMEM / exits while the peer still uses it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
 }  // namespace lsg
 
 using namespace lsg;
@@ -360,6 +580,48 @@ int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, 
     return ls_check_cuda("k_gemm_tf32");
 }
 
+// EXPERIMENTAL 2-CTA launch (LS_GEMM_2CTA=1): grid.x counts 256-row tiles, one cluster of two CTAs per work item slot.
+constexpr int smem_bytes_2cta(int stages, int bn) { return stages * (A_BYTES + (bn / 2) * BK * 4) + PATCH_BYTES + 1024 + 256; }
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+int launch_2cta_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
+                  cudaStream_t stream) {
+    static bool configured = false;
+    constexpr int smem = smem_bytes_2cta(STAGES, BN);
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gemm_tf32_2cta<A_MN, B_MN, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return ls_check_cuda("gemm 2cta smem attribute");
+        configured = true;
+    }
+    const int n_items = (int)(grid.x * grid.y * grid.z);
+    int dev = 0, num_sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+    const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
+    k_gemm_tf32_2cta<A_MN, B_MN, BN, STAGES><<<2 * clusters, kThreads, smem, stream>>>(
+        ma, mb, a->C, a->bias, a->M, a->N, a->K, (long long)a->ldc, a->act, kb_per_split, atomic, (int)grid.x, (int)grid.y,
+        (int)grid.z);
+    return ls_check_cuda("k_gemm_tf32_2cta");
+}
+
+template <bool A_MN, bool B_MN>
+int launch_2cta(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
+                cudaStream_t stream) {
+    // per CTA and stage: 16 KB of A + BN/2 rows of B (16 KB at BN=256, 8 KB at BN=128); 6 stages + patches <= 211 KB
+    return bn == 256 ? launch_2cta_s<A_MN, B_MN, 256, 6>(ma, mb, a, grid, kb_per_split, atomic, stream)
+                     : launch_2cta_s<A_MN, B_MN, 128, 6>(ma, mb, a, grid, kb_per_split, atomic, stream);
+}
+
+bool use_2cta() {
+    static int flag = -1;
+    if (flag < 0) {
+        const char* e = getenv("LS_GEMM_2CTA");
+        flag = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return flag == 1;
+}
+
 template <bool A_MN, bool B_MN>
 int launch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
            cudaStream_t stream) {
@@ -403,6 +665,15 @@ extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
     const int BN = pick_bn(a->N);
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (use_2cta() && a->M > BM) {                     // experimental cta_group::2 path: 256-row tiles, B box = BN/2 rows
+        if (a->a_mn_major ? make_map(&ma, a->A, a->M, a->K, a->lda, 32, sw_mn) : make_map(&ma, a->A, a->K, a->M, a->lda, BM, sw_k)) return -1;
+        if (a->b_mn_major ? make_map(&mb, a->B, a->N, a->K, a->ldb, 32, sw_mn) : make_map(&mb, a->B, a->K, a->N, a->ldb, (uint32_t)(BN / 2), sw_k)) return -1;
+        dim3 grid2((a->M + 2 * BM - 1) / (2 * BM), (a->N + BN - 1) / BN, split);
+        if (a->a_mn_major) return a->b_mn_major ? launch_2cta<true, true>(BN, ma, mb, a, grid2, kb_per_split, atomic, stream)
+                                                : launch_2cta<true, false>(BN, ma, mb, a, grid2, kb_per_split, atomic, stream);
+        return a->b_mn_major ? launch_2cta<false, true>(BN, ma, mb, a, grid2, kb_per_split, atomic, stream)
+                             : launch_2cta<false, false>(BN, ma, mb, a, grid2, kb_per_split, atomic, stream);
+    }
     if (a->a_mn_major ? make_map(&ma, a->A, a->M, a->K, a->lda, 32, sw_mn) : make_map(&ma, a->A, a->K, a->M, a->lda, BM, sw_k)) return -1;
     if (a->b_mn_major ? make_map(&mb, a->B, a->N, a->K, a->ldb, 32, sw_mn) : make_map(&mb, a->B, a->K, a->N, a->ldb, (uint32_t)BN, sw_k)) return -1;
     dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN, split);
