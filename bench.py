@@ -8,10 +8,12 @@ Workloads (`--workload`, named in config.workload):
   full  (default) BASELINE.json configs[1]: RealEstate10k-shaped synthetic batch, B=4 scene pairs per GPU, 2
         context views 256x256, full encoder (DINO ViT-B/8 + epipolar transformer) -> 393 216 variational Gaussians
         per scene -> sample -> splat V_t target views -> latent sample -> 1/8 rescale -> VAE decoder with skip
-        injection; loss = 10 mse(colour) + l1(decoded image); backward to every weight; fused Adam step; for
-        N > 1 an NCCL all-reduce of the flat gradient buffer.  fp32 weights/activations (TF32 convolutions as in
-        the reference's torch defaults).  Encoder/VAE GEMMs and convolutions currently run through
-        cuDNN/cuBLAS (library calls); the rasterizer path is our sm_100a code.
+        injection -> PatchGAN logits (generator term, discriminator frozen); loss = 10 mse(colour) + l1(decoded image)
+        + hinge generator term; backward to every weight; fused Adam step; for N > 1 an NCCL all-reduce of the flat
+        gradient buffer.  fp32 weights/activations.  Ours (sm_100a, libls_raster.so): rasterizer fwd+bwd, every Linear
+        (tcgen05 TF32 GEMM), epipolar gather + depth encoding, weight-absorbed cross-attention, GroupNorm+SiLU, LayerNorm,
+        conv bias epilogues and bias gradients.  Library: cuDNN convolutions (TF32, as the reference's torch defaults),
+        the DINO / VAE-mid attention cores, remaining elementwise glue.
   splat the rasterizer path alone: B scenes x G=65 536 Gaussians (colour SH deg 4 + C=4 feature SH deg 2) through
         DecoderSplattingCUDA fwd+bwd with scalar loss heads (the round-1 kernel workload; roofline stages).
 One step = one such batch; value = target views / s over all ranks.
