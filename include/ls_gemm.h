@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-enum { LS_ACT_NONE = 0, LS_ACT_RELU = 1, LS_ACT_GELU = 2 /* exact erf GELU, torch.nn.GELU() */ };
+enum { LS_ACT_NONE = 0, LS_ACT_RELU = 1, LS_ACT_GELU = 2 /* exact erf GELU, torch.nn.GELU() */, LS_ACT_SILU = 3,
+       LS_ACT_LRELU = 4 /* LeakyReLU(0.2), discriminator_patch_gan.py:24 */ };
 
 typedef struct LsGemmArgs {
     int32_t M, N, K;

@@ -37,6 +37,12 @@ LS_API int ls_groupnorm_forward(const LsGroupNorm* args, float* y, void* stream 
  * ds = dy * act'(u): d beta_c = sum_n sums[n,c,0], d gamma_c = sum_n sums[n,c,1] (left to the caller: N*C values). */
 LS_API int ls_groupnorm_backward(const LsGroupNorm* args, const float* dy, float* dx, double* sums, void* stream /* cudaStream_t */);
 
+/* The same GroupNorm (+ SiLU) for NHWC activations (N, H*W, C) -- the layout the implicit-GEMM convolutions (ls_conv.h) keep
+ * the VAE decoder in.  Same argument struct, except that `stats` is (N, C, 2): per-(image, channel) {sum x, sum x^2} (group
+ * statistics are assembled from them), and `sums` of the backward is (N, C, 2) as above.  C % 4 == 0, C <= 1024.          */
+LS_API int ls_groupnorm_nhwc_forward(const LsGroupNorm* args, float* y, void* stream /* cudaStream_t */);
+LS_API int ls_groupnorm_nhwc_backward(const LsGroupNorm* args, const float* dy, float* dx, double* sums, void* stream /* cudaStream_t */);
+
 /* LayerNorm over the last dimension (C a multiple of 128, <= 1024), rows x C row-major fp32: nn.LayerNorm of the DINO
  * ViT blocks (the backbone behind src/model/encoder/backbone/backbone_dino.py:33) and of the epipolar transformer's
  * PreNorm (src/model/transformer/pre_norm.py:28-35).  mean_rstd (rows, 2) is written by forward and read by backward;

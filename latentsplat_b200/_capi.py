@@ -75,7 +75,11 @@ class LsGroupNorm(C.Structure):          # include/ls_norm.h
                 ("x", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("stats", C.c_void_p)]
 
 
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+class LsConv2d(C.Structure):             # include/ls_conv.h
+    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "transposed")]
+
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
 STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15
@@ -85,7 +89,9 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
            "ls_absorbed_attention_forward", "ls_absorbed_attention_backward",
            "ls_epipolar_gather_forward", "ls_epipolar_gather_backward", "ls_groupnorm_forward", "ls_groupnorm_backward",
-           "ls_layernorm_forward", "ls_layernorm_backward", "ls_conv_bias_add", "ls_conv_bias_grad", "ls_col_sum")
+           "ls_layernorm_forward", "ls_layernorm_backward", "ls_conv_bias_add", "ls_conv_bias_grad", "ls_col_sum",
+           "ls_groupnorm_nhwc_forward", "ls_groupnorm_nhwc_backward",
+           "ls_conv2d_out_size", "ls_conv2d_forward", "ls_conv2d_dgrad", "ls_conv2d_wgrad", "ls_act_backward")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -134,6 +140,10 @@ def load() -> C.CDLL:
     lib.ls_groupnorm_forward.argtypes = [C.POINTER(LsGroupNorm), C.c_void_p, C.c_void_p]
     lib.ls_groupnorm_backward.restype = C.c_int
     lib.ls_groupnorm_backward.argtypes = [C.POINTER(LsGroupNorm)] + [C.c_void_p] * 4
+    lib.ls_groupnorm_nhwc_forward.restype = C.c_int
+    lib.ls_groupnorm_nhwc_forward.argtypes = [C.POINTER(LsGroupNorm), C.c_void_p, C.c_void_p]
+    lib.ls_groupnorm_nhwc_backward.restype = C.c_int
+    lib.ls_groupnorm_nhwc_backward.argtypes = [C.POINTER(LsGroupNorm)] + [C.c_void_p] * 4
     lib.ls_layernorm_forward.restype = C.c_int
     lib.ls_layernorm_forward.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
     lib.ls_layernorm_backward.restype = C.c_int
@@ -141,6 +151,16 @@ def load() -> C.CDLL:
     for fn in (lib.ls_conv_bias_add, lib.ls_conv_bias_grad):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]
+    lib.ls_conv2d_out_size.restype = C.c_int
+    lib.ls_conv2d_out_size.argtypes = [C.POINTER(LsConv2d), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.ls_conv2d_forward.restype = C.c_int
+    lib.ls_conv2d_forward.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
+    lib.ls_conv2d_dgrad.restype = C.c_int
+    lib.ls_conv2d_dgrad.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 4
+    lib.ls_conv2d_wgrad.restype = C.c_int
+    lib.ls_conv2d_wgrad.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 4
+    lib.ls_act_backward.restype = C.c_int
+    lib.ls_act_backward.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p]
     lib.ls_col_sum.restype = C.c_int
     lib.ls_col_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]
     if lib.ls_raster_abi_version() != ABI_VERSION:

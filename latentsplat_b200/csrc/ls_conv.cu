@@ -1,0 +1,700 @@
+// ls_conv.cu -- implicit-GEMM convolutions for sm_100a on the tcgen05 pipeline of ls_gemm.cu (include/ls_conv.h).
+//
+// Activations are NHWC, so for one filter tap (r, s) the im2col matrix of a convolution is simply the activation tensor
+// shifted by (r - pad, s - pad): a 4-D TMA box {32 channels, BW pixels, BH rows, 1 image} of it IS a 128 x 32 K-major
+// GEMM operand tile, with TMA's out-of-bounds zero fill playing the padding and its element strides playing the
+// convolution stride.  Nothing is unfolded or transposed in memory.  Two kernel modes share one warp-specialised
+// pipeline (TMA producer lane / MMA issuer lane / TMEM allocator warp / 4 epilogue warps, persistent over a work list):
+//
+//   MODE_F  out[n, iy, ix, :] = act(bias + sum_taps in[n, iy*sy + dy(r), ix*sx + dx(s), :] * Wtap)        (pixels x Cout)
+//           A = activation boxes (K-major), B = weights [rows][taps*channels] read K-major (forward; transposed-conv
+//           dgrad) or MN-major (dgrad: dX = dY * W without a transposed weight copy; transposed-conv forward); the
+//           epilogue maps tile rows back to output pixels (with an output stride/offset for the stride classes of a
+//           strided dgrad and for the transposed convolution) and fuses bias + ReLU / GELU / SiLU / LeakyReLU, optionally
+//           storing the pre-activation for the backward pass.
+//   MODE_W  dW[m, n] = sum_pixels P[pixel, m] * Q[pixel + tap(n), n]                                       (weight gradient)
+//           both operands are activation tensors read MN-major in 32-pixel K blocks (SWIZZLE_128B with 32-B atoms, the
+//           only MN-major layout tcgen05 takes for 32-bit operands); each 32-channel box of an operand carries its own
+//           filter tap, so one tile may span several taps; split over the pixel dimension, combined with red.global.add.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "ls_conv.h"
+#include "ls_host.h"
+#include "ls_tc.cuh"
+
+namespace lsc {
+using namespace lstc;
+
+constexpr int BM = 128, BK = 32, UMMA_K = 8;
+constexpr int A_BYTES = BM * BK * 4;
+constexpr int kThreads = 256;
+constexpr int PITCH = 36;                                   // floats; 144-B rows: conflict-free float4 access
+constexpr int PATCH_BYTES = 4 * 32 * PITCH * 4;
+constexpr int smem_bytes(int stages, int bn) { return stages * (A_BYTES + bn * BK * 4) + PATCH_BYTES + 1024 + 256; }
+
+enum { MODE_F = 0, MODE_W = 1 };
+
+// how the 32-channel boxes of an activation operand map to TMA coordinates
+struct ActOp {
+    int cp;            // MODE_W: MN-index pitch of one filter tap (multiple of 32); one tap only: >= the MN extent
+    int S;             // MODE_W: taps per filter row
+    int sx, sy;        // coordinate multipliers (convolution stride) applied to the iteration-grid position
+    int dx0, dy0;      // offset of tap (0, 0)
+    int dxs, dys;      // offset step per tap (+1 forward, -1 flipped for dgrad)
+};
+
+struct ConvParams {
+    int P, Q, n_img;          // iteration grid (rows, columns) per image, images
+    int bw_log2;              // F: tile = (1 << bw_log2) x (128 >> bw_log2) pixels;  W: K block = (1 << bw_log2) x (32 >> bw_log2)
+    int tiles_x, tiles_y;     // F: M tiles per image;  W: K blocks per image
+    int tiles_m, tiles_n, splits, kb_per_split, nkb_total;
+    int R, S, chunks;         // F: taps iterated and 32-channel chunks per tap
+    ActOp a, b;
+    int wp, wr0, wrs, ws0, wss, wS;   // F: weight k/column offset of tap (r, s) = wp * ((wr0 + r*wrs) * wS + ws0 + s*wss)
+    long long o_sn, o_sh, o_sw;       // F: output element strides (image, row, pixel)
+    int oys, oyo, oxs, oxo;           // F: output pixel = (iy*oys + oyo, ix*oxs + oxo)
+    int n_out, act, vec_ok;
+    float* out;
+    float* pre_out;
+    const float* bias;
+    int cp_r, c_r, t_r, cp_c, c_c, t_c;   // W: tile row/column -> (tap, channel): tap = idx / cp, channel = idx % cp (< c), tap < t
+    long long rs, cs;                     // W: output address = (tap_r*c_r + ch_r)*rs + (tap_c*c_c + ch_c)*cs
+    int atomic;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case LS_ACT_RELU: return fmaxf(v, 0.f);
+        case LS_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+        case LS_ACT_SILU: return v / (1.f + __expf(-v));
+        case LS_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+        default: return v;
+    }
+}
+
+template <int MODE, bool BMN, int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ ConvParams p) {
+    constexpr bool A_MN = MODE == MODE_W;
+    constexpr bool B_MN = MODE == MODE_W || BMN;
+    constexpr int B_BYTES = BN * BK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;        // 64 / 256 / 512: powers of two >= 32
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PATCH_BYTES);    // full[S] empty[S] tfull[2] tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.tiles_m * p.tiles_n * p.splits;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    // item -> (tile_m, tile_n, first K block, K blocks); n-tile fastest so that concurrently running CTAs share the A panel
+    auto decode = [&](int item, int& tile_m, int& tile_n, int& kb0, int& nkb) {
+        tile_n = item % p.tiles_n;
+        const int rest = item / p.tiles_n;
+        tile_m = rest % p.tiles_m;
+        kb0 = (rest / p.tiles_m) * p.kb_per_split;
+        nkb = min(p.nkb_total, kb0 + p.kb_per_split) - kb0;
+    };
+    // F: M tile -> image and first pixel of the iteration grid
+    auto tile_origin = [&](int tile_m, int& n, int& y0, int& x0) {
+        const int tx = tile_m % p.tiles_x;
+        const int t = tile_m / p.tiles_x;
+        n = t / p.tiles_y;
+        y0 = (t - n * p.tiles_y) * (BM >> p.bw_log2);
+        x0 = tx << p.bw_log2;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            if constexpr (MODE == MODE_F) {
+                int n, y0, x0;
+                tile_origin(tile_m, n, y0, x0);
+                const int n0 = tile_n * BN;
+                for (int r = 0; r < p.R; ++r) {
+                    const int ay = y0 * p.a.sy + p.a.dy0 + r * p.a.dys;
+                    for (int s = 0; s < p.S; ++s) {
+                        const int ax = x0 * p.a.sx + p.a.dx0 + s * p.a.dxs;
+                        const int wk = p.wp * ((p.wr0 + r * p.wrs) * p.wS + p.ws0 + s * p.wss);
+                        for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                            const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                            mbar_wait(empty0 + 8 * st, ph ^ 1);
+                            mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
+                            const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                            tma_load_4d(a_dst, &map_a, full0 + 8 * st, ch * BK, ax, ay, n);
+                            if (!B_MN) {
+                                tma_load_2d(b_dst, &map_b, full0 + 8 * st, wk + ch * BK, n0);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < BN / 32; ++j)
+                                    tma_load_2d(b_dst + j * 4096, &map_b, full0 + 8 * st, wk + n0 + 32 * j, ch * BK);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // per 32-channel box: channel offset and tap shift (constant over the K loop)
+                int ac[BM / 32], ax[BM / 32], ay[BM / 32], bc[BN / 32], bx[BN / 32], by[BN / 32];
+#pragma unroll
+                for (int j = 0; j < BM / 32; ++j) {
+                    const int m = tile_m * BM + 32 * j, tap = m / p.a.cp, r = tap / p.a.S, s = tap - r * p.a.S;
+                    ac[j] = m - tap * p.a.cp; ax[j] = p.a.dx0 + s * p.a.dxs; ay[j] = p.a.dy0 + r * p.a.dys;
+                }
+#pragma unroll
+                for (int j = 0; j < BN / 32; ++j) {
+                    const int m = tile_n * BN + 32 * j, tap = m / p.b.cp, r = tap / p.b.S, s = tap - r * p.b.S;
+                    bc[j] = m - tap * p.b.cp; bx[j] = p.b.dx0 + s * p.b.dxs; by[j] = p.b.dy0 + r * p.b.dys;
+                }
+                const int kw_log2 = p.bw_log2, kh = 32 >> kw_log2;
+                int xb = kb0 % p.tiles_x, t = kb0 / p.tiles_x;
+                int n = t / p.tiles_y, yb = t - n * p.tiles_y;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(empty0 + 8 * st, ph ^ 1);
+                    mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
+                    const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    const int x0 = xb << kw_log2, y0 = yb * kh;
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j)
+                        tma_load_4d(a_dst + j * 4096, &map_a, full0 + 8 * st, ac[j], x0 * p.a.sx + ax[j], y0 * p.a.sy + ay[j], n);
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_4d(b_dst + j * 4096, &map_b, full0 + 8 * st, bc[j], x0 * p.b.sx + bx[j], y0 * p.b.sy + by[j], n);
+                    if (++xb == p.tiles_x) { xb = 0; if (++yb == p.tiles_y) { yb = 0; ++n; } }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------ MMA issuer --------------------------------
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t it = 0, local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + st * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+                    const uint64_t bdesc = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
+                    tc_mma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(empty0 + 8 * st);
+            }
+            tc_commit(tfull0 + 8 * acc);
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue ----------------------------------
+        const int q = warp - 4;
+        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        uint32_t local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int tile_m, tile_n, kb0, nkb;
+            decode(item, tile_m, tile_n, kb0, nkb);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tc_fence_after();
+
+            // rows of this warp: 8 per lane (4*i + sub_r), resolved to output offsets once per tile
+            long long row_off[8];
+            bool row_ok[8];
+            if constexpr (MODE == MODE_F) {
+                int n, y0, x0;
+                tile_origin(tile_m, n, y0, x0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = q * 32 + 4 * i + sub_r;
+                    const int iy = y0 + (row >> p.bw_log2), ix = x0 + (row & ((1 << p.bw_log2) - 1));
+                    row_ok[i] = iy < p.P && ix < p.Q;
+                    row_off[i] = (long long)n * p.o_sn + (long long)(iy * p.oys + p.oyo) * p.o_sh + (long long)(ix * p.oxs + p.oxo) * p.o_sw;
+                }
+            } else {
+                const int row0 = tile_m * BM + q * 32, tap = row0 / p.cp_r, ch0 = row0 - tap * p.cp_r;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ch = ch0 + 4 * i + sub_r;
+                    row_ok[i] = tap < p.t_r && ch < p.c_r;
+                    row_off[i] = (long long)(tap * p.c_r + ch) * p.rs;
+                }
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = tile_n * BN + c0;
+                int ncols, tapc = 0, chc0 = col0;                       // valid columns of this 32-wide chunk, column remap
+                if constexpr (MODE == MODE_F) {
+                    if (col0 >= p.n_out) break;                          // warp-uniform
+                    ncols = p.n_out - col0;
+                } else {
+                    tapc = col0 / p.cp_c;
+                    chc0 = col0 - tapc * p.cp_c;
+                    if (tapc >= p.t_c) break;
+                    ncols = p.c_c - chc0;                                // may be <= 0: padded channels of this tap
+                }
+                if (ncols <= 0) continue;                                // warp-uniform
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                float4 rows4[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
+                if constexpr (MODE == MODE_F) {
+                    const int col = col0 + sub_c;
+                    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) if (col + t < p.n_out) b4[t] = p.bias[col + t];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (!row_ok[i]) continue;
+                        const float4 v4 = rows4[i];
+                        const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
+                        float v[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) v[t] = apply_act(pre[t], p.act);
+                        float* dst = p.out + row_off[i] + col;
+                        if (p.vec_ok && col + 3 < p.n_out) {
+                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                            if (p.pre_out) *reinterpret_cast<float4*>(p.pre_out + row_off[i] + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (col + t < p.n_out) {
+                                    dst[t] = v[t];
+                                    if (p.pre_out) p.pre_out[row_off[i] + col + t] = pre[t];
+                                }
+                        }
+                    }
+                } else {
+                    const int ch = chc0 + sub_c;
+                    const long long col_off = (long long)(tapc * p.c_c + ch) * p.cs;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (!row_ok[i]) continue;
+                        const float4 v4 = rows4[i];
+                        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+                        float* dst = p.out + row_off[i] + col_off;
+                        if (p.vec_ok && ch + 3 < p.c_c) {
+                            if (p.atomic) red_add_v4(dst, v[0], v[1], v[2], v[3]);
+                            else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (ch + t < p.c_c) {
+                                    if (p.atomic) atomicAdd(dst + t * p.cs, v[t]); else dst[t * p.cs] = v[t];
+                                }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// elementwise backward of the fused epilogue activations: dx = dy * act'(pre)
+__global__ void __launch_bounds__(256) k_act_bwd(const float4* __restrict__ dy, const float4* __restrict__ pre,
+                                                 float4* __restrict__ dx, long long n4, int act) {
+    auto d = [act](float g, float x) {
+        switch (act) {
+            case LS_ACT_RELU: return x > 0.f ? g : 0.f;
+            case LS_ACT_GELU: {
+                const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+                return g * (cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x));
+            }
+            case LS_ACT_SILU: {
+                const float s = 1.f / (1.f + __expf(-x));
+                return g * s * (1.f + x * (1.f - s));
+            }
+            case LS_ACT_LRELU: return x > 0.f ? g : 0.2f * g;
+            default: return g;
+        }
+    };
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 g = dy[i], x = pre[i];
+        dx[i] = make_float4(d(g.x, x.x), d(g.y, x.y), d(g.z, x.z), d(g.w, x.w));
+    }
+}
+
+}  // namespace lsc
+
+using namespace lsc;
+
+namespace {
+
+struct Act4 {                 // an NHWC activation tensor
+    const float* ptr;
+    int N, H, W, C;
+};
+
+int pow2_ceil_log2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+// 4-D map over an NHWC tensor: box {32 channels, bx pixels, by rows, 1 image} traversed with strides (sx, sy)
+int make_act_map(CUtensorMap* map, const Act4& t, int bx, int by, int sx, int sy, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ls_fail("cuTensorMapEncodeTiled entry point not available");
+    if (t.C % 4) return ls_fail("conv: activation channels (%d) must be a multiple of 4 (TMA 16-byte stride rule)", t.C);
+    if (reinterpret_cast<uintptr_t>(t.ptr) & 15) return ls_fail("conv: activation pointer must be 16-byte aligned");
+    if (bx * sx > 256 || by * sy > 256) return ls_fail("conv: TMA box %dx%d with strides %dx%d exceeds 256", bx, by, sx, sy);
+    const cuuint64_t dims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)t.C * 4, (cuuint64_t)t.W * t.C * 4, (cuuint64_t)t.H * t.W * t.C * 4};
+    const cuuint32_t box[4] = {32u, (cuuint32_t)(bx * sx), (cuuint32_t)(by * sy), 1u};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)sx, (cuuint32_t)sy, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return ls_fail("cuTensorMapEncodeTiled(4d) failed (%d): N=%d H=%d W=%d C=%d box=%dx%d stride=%dx%d", (int)r, t.N, t.H, t.W, t.C,
+                       bx, by, sx, sy);
+    return 0;
+}
+
+// 2-D map over a weight matrix [rows][cols] (row pitch = cols)
+int make_w_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, int box_rows, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ls_fail("cuTensorMapEncodeTiled entry point not available");
+    if (cols % 4) return ls_fail("conv: weight row length (%lld) must be a multiple of 4", cols);
+    if (reinterpret_cast<uintptr_t>(ptr) & 15) return ls_fail("conv: weight pointer must be 16-byte aligned");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ls_fail("cuTensorMapEncodeTiled(2d weights) failed (%d): rows=%lld cols=%lld", (int)r, rows, cols);
+    return 0;
+}
+
+template <int MODE, bool BMN, int BN, int STAGES>
+int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
+    static PerDeviceOnce once;
+    constexpr int smem = smem_bytes(STAGES, BN);
+    if (once.ensure_smem(k_conv_tf32<MODE, BMN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
+    const long long n_items = (long long)p.tiles_m * p.tiles_n * p.splits;
+    if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
+    const int num_sms = current_sm_count();
+    const int ctas = n_items < num_sms ? (int)n_items : num_sms;
+    k_conv_tf32<MODE, BMN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, p);
+    return ls_check_cuda("k_conv_tf32");
+}
+
+template <int MODE, bool BMN>
+int launch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
+    // stage = 16 KB of A + BN rows of B: 128x256 tiles 4 x 48 KB, 128x128 6 x 32 KB, 128x32 8 x 20 KB (+ 18 KB of patches)
+    if (bn == 256) return launch_s<MODE, BMN, 256, 4>(ma, mb, p, stream);
+    if (bn == 128) return launch_s<MODE, BMN, 128, 6>(ma, mb, p, stream);
+    return launch_s<MODE, BMN, 32, 8>(ma, mb, p, stream);
+}
+
+int pick_bn(int n) { return n <= 32 ? 32 : (n <= 128 ? 128 : 256); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// MODE_F problem description (host)
+// ------------------------------------------------------------------------------------------------------------------
+struct FProblem {
+    Act4 in;                  // A operand
+    int P, Q;                 // iteration grid
+    int R, S;                 // taps iterated
+    int sy, sx, dy0, dx0, dys, dxs;
+    const float* w; long long w_rows, w_cols; int w_mn;      // weights [w_rows][w_cols]; w_mn: rows = k (input channel), cols = tap*wp + output column
+    int wp, wr0, wrs, ws0, wss, wS;
+    float* out; float* pre; const float* bias;
+    long long o_sn, o_sh, o_sw;
+    int oys, oyo, oxs, oxo;
+    int n_out, act;
+};
+
+int run_f(const FProblem& f, cudaStream_t stream) {
+    ConvParams p{};
+    p.P = f.P; p.Q = f.Q; p.n_img = f.in.N;
+    int bw = pow2_ceil_log2(f.Q);
+    if (bw > 7) bw = 7;
+    while ((1 << bw) * f.sx > 256) --bw;
+    while ((BM >> bw) * f.sy > 256) ++bw;                    // (cannot happen for stride <= 4; kept for clarity)
+    p.bw_log2 = bw;
+    const int BW = 1 << bw, BH = BM >> bw;
+    p.tiles_x = (f.Q + BW - 1) / BW;
+    p.tiles_y = (f.P + BH - 1) / BH;
+    const int BN = pick_bn(f.n_out);
+    p.tiles_m = f.in.N * p.tiles_x * p.tiles_y;
+    p.tiles_n = (f.n_out + BN - 1) / BN;
+    p.splits = 1;
+    p.R = f.R; p.S = f.S; p.chunks = (f.in.C + BK - 1) / BK;
+    p.nkb_total = p.kb_per_split = p.R * p.S * p.chunks;
+    p.a = ActOp{1 << 30, 1, f.sx, f.sy, f.dx0, f.dy0, f.dxs, f.dys};
+    p.b = p.a;
+    p.wp = f.wp; p.wr0 = f.wr0; p.wrs = f.wrs; p.ws0 = f.ws0; p.wss = f.wss; p.wS = f.wS;
+    p.o_sn = f.o_sn; p.o_sh = f.o_sh; p.o_sw = f.o_sw;
+    p.oys = f.oys; p.oyo = f.oyo; p.oxs = f.oxs; p.oxo = f.oxo;
+    p.n_out = f.n_out; p.act = f.act;
+    p.out = f.out; p.pre_out = f.pre; p.bias = f.bias;
+    p.vec_ok = (f.o_sn % 4 == 0 && f.o_sh % 4 == 0 && f.o_sw % 4 == 0 && (reinterpret_cast<uintptr_t>(f.out) & 15) == 0 &&
+                (f.pre == nullptr || (reinterpret_cast<uintptr_t>(f.pre) & 15) == 0)) ? 1 : 0;
+    p.atomic = 0;
+    if (p.nkb_total <= 0 || p.tiles_m <= 0) return ls_fail("conv: empty problem");
+    CUtensorMap ma, mb;
+    if (make_act_map(&ma, f.in, BW, BH, f.sx, f.sy, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (f.w_mn) {
+        if (make_w_map(&mb, f.w, f.w_rows, f.w_cols, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+        return launch<MODE_F, true>(BN, ma, mb, p, stream);
+    }
+    if (make_w_map(&mb, f.w, f.w_rows, f.w_cols, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    return launch<MODE_F, false>(BN, ma, mb, p, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// MODE_W problem description (host): out[(tap_r, ch_r), (tap_c, ch_c)] = sum_pixels A[pixel + tap_r][ch_r] * B[pixel + tap_c][ch_c]
+// ------------------------------------------------------------------------------------------------------------------
+struct WOperand {
+    Act4 t;
+    int C;               // channels used (== t.C)
+    int taps, S;         // filter taps carried by this operand (1 = unshifted)
+    int sx, sy, dx0, dy0;
+};
+
+int run_w(const WOperand& A, const WOperand& B, int P, int Q, float* out, long long rs, long long cs, cudaStream_t stream) {
+    ConvParams p{};
+    p.P = P; p.Q = Q; p.n_img = A.t.N;
+    int kw = pow2_ceil_log2(Q);
+    if (kw > 5) kw = 5;
+    p.bw_log2 = kw;
+    const int KW = 1 << kw, KH = 32 >> kw;
+    p.tiles_x = (Q + KW - 1) / KW;
+    p.tiles_y = (P + KH - 1) / KH;
+    p.nkb_total = A.t.N * p.tiles_x * p.tiles_y;
+    const int cpa = (A.C + 31) & ~31, cpb = (B.C + 31) & ~31;
+    const int M = A.taps * cpa, N = B.taps * cpb;
+    const int BN = pick_bn(N);
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    // split the pixel loop so that ~2 waves of work items exist, each at least 8 K blocks long
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int num_sms = current_sm_count();
+    int split = tiles >= 2 * num_sms ? 1 : (2 * num_sms + tiles - 1) / tiles;
+    if (split > p.nkb_total / 8) split = p.nkb_total / 8;
+    if (split < 1) split = 1;
+    p.kb_per_split = (p.nkb_total + split - 1) / split;
+    p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.a = ActOp{A.taps > 1 ? cpa : (1 << 30), A.S, A.sx, A.sy, A.dx0, A.dy0, 1, 1};
+    p.b = ActOp{B.taps > 1 ? cpb : (1 << 30), B.S, B.sx, B.sy, B.dx0, B.dy0, 1, 1};
+    p.cp_r = A.taps > 1 ? cpa : (1 << 30); p.c_r = A.C; p.t_r = A.taps;
+    p.cp_c = B.taps > 1 ? cpb : (1 << 30); p.c_c = B.C; p.t_c = B.taps;
+    p.rs = rs; p.cs = cs;
+    p.out = out;
+    p.atomic = p.splits > 1 ? 1 : 0;
+    p.vec_ok = (cs == 1 && rs % 4 == 0 && B.C % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    if (p.nkb_total <= 0) return ls_fail("conv wgrad: empty problem");
+    CUtensorMap ma, mb;
+    if (make_act_map(&ma, A.t, KW, KH, A.sx, A.sy, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+    if (make_act_map(&mb, B.t, KW, KH, B.sx, B.sy, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+    return launch<MODE_W, true>(BN, ma, mb, p, stream);
+}
+
+int validate(const LsConv2d* c) {
+    if (!c) return ls_fail("conv: descriptor is NULL");
+    bind_context();
+    if (c->N <= 0 || c->H <= 0 || c->W <= 0 || c->Cin <= 0 || c->Cout <= 0 || c->R <= 0 || c->S <= 0)
+        return ls_fail("conv: bad sizes N=%d H=%d W=%d Cin=%d Cout=%d R=%d S=%d", c->N, c->H, c->W, c->Cin, c->Cout, c->R, c->S);
+    if (c->Cin % 4 || c->Cout % 4) return ls_fail("conv: Cin (%d) and Cout (%d) must be multiples of 4 (pad the channels)", c->Cin, c->Cout);
+    if (c->stride < 1 || c->stride > 4) return ls_fail("conv: stride %d not in 1..4", c->stride);
+    if (c->pad < 0) return ls_fail("conv: negative padding");
+    if (c->transposed && (c->R != c->stride || c->S != c->stride || c->pad != 0))
+        return ls_fail("conv: transposed convolutions are supported for kernel == stride, pad == 0 only");
+    return 0;
+}
+
+void out_size(const LsConv2d* c, int& OH, int& OW) {
+    if (c->transposed) { OH = c->H * c->stride; OW = c->W * c->stride; }
+    else { OH = (c->H + 2 * c->pad - c->R) / c->stride + 1; OW = (c->W + 2 * c->pad - c->S) / c->stride + 1; }
+}
+
+}  // namespace
+
+extern "C" int ls_conv2d_out_size(const LsConv2d* c, int32_t* out_h, int32_t* out_w) {
+    if (validate(c)) return -1;
+    int OH, OW;
+    out_size(c, OH, OW);
+    if (OH <= 0 || OW <= 0) return ls_fail("conv: empty output");
+    if (out_h) *out_h = OH;
+    if (out_w) *out_w = OW;
+    return 0;
+}
+
+extern "C" int ls_conv2d_forward(const LsConv2d* c, const float* x, const float* w, const float* bias, float* y, float* y_pre,
+                                 int32_t act, void* stream_) {
+    if (validate(c)) return -1;
+    if (!x || !w || !y) return ls_fail("conv forward: NULL pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int OH, OW;
+    out_size(c, OH, OW);
+    if (OH <= 0 || OW <= 0) return ls_fail("conv: empty output");
+    FProblem f{};
+    f.in = Act4{x, c->N, c->H, c->W, c->Cin};
+    f.w = w; f.out = y; f.pre = y_pre; f.bias = bias; f.act = act;
+    f.n_out = c->Cout;
+    f.o_sw = c->Cout; f.o_sh = (long long)OW * c->Cout; f.o_sn = (long long)OH * OW * c->Cout;
+    if (!c->transposed) {
+        // y[n,oy,ox,:] = sum_{r,s} x[n, oy*st + r - pad, ox*st + s - pad, :] W[:, r, s, :]^T ; W = [Cout][R*S*Cin] K-major
+        f.P = OH; f.Q = OW; f.R = c->R; f.S = c->S;
+        f.sy = f.sx = c->stride; f.dy0 = f.dx0 = -c->pad; f.dys = f.dxs = 1;
+        f.w_rows = c->Cout; f.w_cols = (long long)c->R * c->S * c->Cin; f.w_mn = 0;
+        f.wp = c->Cin; f.wr0 = 0; f.wrs = 1; f.ws0 = 0; f.wss = 1; f.wS = c->S;
+        f.oys = f.oxs = 1; f.oyo = f.oxo = 0;
+        return run_f(f, stream);
+    }
+    // transposed, kernel == stride: y[n, k*Y + r, k*X + s, :] = x[n, Y, X, :] W[:, r, s, :] ; one 1-tap GEMM per (r, s) class,
+    // W = [Cin][R*S*Cout] read MN-major (rows = input channel = k, columns = tap*Cout + output channel)
+    f.P = c->H; f.Q = c->W; f.R = 1; f.S = 1;
+    f.sy = f.sx = 1; f.dy0 = f.dx0 = 0; f.dys = f.dxs = 1;
+    f.w_rows = c->Cin; f.w_cols = (long long)c->R * c->S * c->Cout; f.w_mn = 1;
+    f.wp = c->Cout; f.wrs = 1; f.wss = 1; f.wS = c->S;
+    f.oys = f.oxs = c->stride;
+    for (int r = 0; r < c->R; ++r)
+        for (int s = 0; s < c->S; ++s) {
+            f.wr0 = r; f.ws0 = s; f.oyo = r; f.oxo = s;
+            if (run_f(f, stream)) return -1;
+        }
+    return 0;
+}
+
+extern "C" int ls_conv2d_dgrad(const LsConv2d* c, const float* dy, const float* w, float* dx, void* stream_) {
+    if (validate(c)) return -1;
+    if (!dy || !w || !dx) return ls_fail("conv dgrad: NULL pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int OH, OW;
+    out_size(c, OH, OW);
+    if (OH <= 0 || OW <= 0) return ls_fail("conv: empty output");
+    FProblem f{};
+    f.in = Act4{dy, c->N, OH, OW, c->Cout};
+    f.w = w; f.out = dx; f.pre = nullptr; f.bias = nullptr; f.act = LS_ACT_NONE;
+    f.n_out = c->Cin;
+    f.o_sw = c->Cin; f.o_sh = (long long)c->W * c->Cin; f.o_sn = (long long)c->H * c->W * c->Cin;
+    if (c->transposed) {
+        // dx[n,Y,X,ci] = sum_{r,s,co} dy[n, k*Y + r, k*X + s, co] W[ci, r, s, co] : a strided convolution, W K-major [Cin][R*S*Cout]
+        f.P = c->H; f.Q = c->W; f.R = c->R; f.S = c->S;
+        f.sy = f.sx = c->stride; f.dy0 = f.dx0 = 0; f.dys = f.dxs = 1;
+        f.w_rows = c->Cin; f.w_cols = (long long)c->R * c->S * c->Cout; f.w_mn = 0;
+        f.wp = c->Cout; f.wr0 = 0; f.wrs = 1; f.ws0 = 0; f.wss = 1; f.wS = c->S;
+        f.oys = f.oxs = 1; f.oyo = f.oxo = 0;
+        return run_f(f, stream);
+    }
+    // dx[n,y,x,ci] = sum_{r,s,co} dy[n, (y + pad - r)/st, (x + pad - s)/st, co] W[co, r, s, ci]  (terms with a remainder vanish):
+    // one stride-1 gather per residue class (y % st, x % st), taps r = ra + st*i with ra = (py + pad) % st.
+    // W = [Cout][R*S*Cin] read MN-major (rows = output channel = k, columns = tap*Cin + input channel).
+    const int st = c->stride;
+    f.w_rows = c->Cout; f.w_cols = (long long)c->R * c->S * c->Cin; f.w_mn = 1;
+    f.wp = c->Cin; f.wS = c->S;
+    f.sy = f.sx = 1; f.dys = f.dxs = -1;
+    f.oys = f.oxs = st;
+    // residue classes no filter tap reaches (only when stride > kernel) keep a zero gradient: clear dx once up front
+    bool uncovered = false;
+    for (int q = 0; q < st; ++q) uncovered |= ((q + c->pad) % st >= c->R) || ((q + c->pad) % st >= c->S);
+    if (uncovered && cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)c->N * c->H * c->W * c->Cin, stream) != cudaSuccess)
+        return ls_check_cuda("conv dgrad memset");
+    for (int py = 0; py < st; ++py)
+        for (int px = 0; px < st; ++px) {
+            const int ra = (py + c->pad) % st, sa = (px + c->pad) % st;
+            const int nr = ra < c->R ? (c->R - ra + st - 1) / st : 0, ns = sa < c->S ? (c->S - sa + st - 1) / st : 0;
+            const int P = py < c->H ? (c->H - py + st - 1) / st : 0, Q = px < c->W ? (c->W - px + st - 1) / st : 0;
+            if (P == 0 || Q == 0 || nr == 0 || ns == 0) continue;
+            f.P = P; f.Q = Q; f.R = nr; f.S = ns;
+            f.dy0 = (py + c->pad - ra) / st; f.dx0 = (px + c->pad - sa) / st;
+            f.wr0 = ra; f.wrs = st; f.ws0 = sa; f.wss = st;
+            f.oyo = py; f.oxo = px;
+            if (run_f(f, stream)) return -1;
+        }
+    return 0;
+}
+
+extern "C" int ls_conv2d_wgrad(const LsConv2d* c, const float* dy, const float* x, float* dw, void* stream_) {
+    if (validate(c)) return -1;
+    if (!dy || !x || !dw) return ls_fail("conv wgrad: NULL pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int OH, OW;
+    out_size(c, OH, OW);
+    if (OH <= 0 || OW <= 0) return ls_fail("conv: empty output");
+    const size_t n_w = (size_t)c->Cout * c->R * c->S * c->Cin;
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * n_w, stream) != cudaSuccess) return ls_check_cuda("conv wgrad memset");
+    const int taps = c->R * c->S;
+    if (!c->transposed) {
+        // dw[co, r, s, ci] = sum_{n,oy,ox} dy[n,oy,ox,co] x[n, oy*st + r - pad, ox*st + s - pad, ci]; pixel loop over the OUTPUT grid
+        WOperand g{Act4{dy, c->N, OH, OW, c->Cout}, c->Cout, 1, 1, 1, 1, 0, 0};
+        WOperand xs{Act4{x, c->N, c->H, c->W, c->Cin}, c->Cin, taps, c->S, c->stride, c->stride, -c->pad, -c->pad};
+        const long long ldw = (long long)taps * c->Cin;
+        if (c->Cout <= 32 && taps * ((c->Cin + 31) & ~31) >= 128)       // few output channels: put the taps on the M side
+            return run_w(xs, g, OH, OW, dw, 1, ldw, stream);
+        return run_w(g, xs, OH, OW, dw, ldw, 1, stream);
+    }
+    // transposed: dw[ci, r, s, co] = sum_{n,Y,X} x[n,Y,X,ci] dy[n, k*Y + r, k*X + s, co]; pixel loop over the INPUT grid
+    WOperand xi{Act4{x, c->N, c->H, c->W, c->Cin}, c->Cin, 1, 1, 1, 1, 0, 0};
+    WOperand gs{Act4{dy, c->N, OH, OW, c->Cout}, c->Cout, taps, c->S, c->stride, c->stride, 0, 0};
+    return run_w(xi, gs, c->H, c->W, dw, (long long)taps * c->Cout, 1, stream);
+}
+
+extern "C" int ls_act_backward(const float* dy, const float* pre, float* dx, int64_t n, int32_t act, void* stream_) {
+    if (!dy || !pre || !dx) return ls_fail("act backward: NULL pointer");
+    if (n <= 0 || n % 4) return ls_fail("act backward: element count %lld must be a positive multiple of 4", (long long)n);
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dx)) & 15)
+        return ls_fail("act backward: pointers must be 16-byte aligned");
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)current_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_act_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(pre),
+                                                                  reinterpret_cast<float4*>(dx), n4, act);
+    return ls_check_cuda("k_act_bwd");
+}

@@ -28,6 +28,7 @@
 
 #include "ls_gemm.h"
 #include "ls_host.h"
+#include "ls_tc.cuh"
 
 namespace lsg {
 
@@ -40,87 +41,12 @@ constexpr int PITCH = 36;                                   // floats; 144-B row
 constexpr int PATCH_BYTES = 4 * 32 * PITCH * 4;              // one 32 x 32 transpose patch per epilogue warp
 constexpr int smem_bytes(int stages, int bn) { return stages * stage_bytes(bn) + PATCH_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/; }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 24)) __trap();   // a protocol bug must fail loudly, never hang the device
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// 64-bit shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
-// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
-// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit operands).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-    const uint64_t lo = (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16);
-    const uint64_t hi = (uint64_t)(sbo_bytes >> 4) | (1ull << 14) | ((uint64_t)layout_type << 29);
-    return lo | (hi << 32);
-}
-
-// Explicit shared-memory accesses: through a generic pointer the compiler emits generic LD/ST (ncu: ST.E.128 /
-// long-scoreboard waits) and, unable to prove that the patch does not alias C, serialises every load behind the
-// previous global store -- 64 dependent round trips per tile.
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
+using namespace lstc;   // mbarrier / TMA / tcgen05 wrappers, make_desc, sts128 / lds128 (ls_tc.cuh)
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == LS_ACT_RELU) return fmaxf(v, 0.f);
     if (act == LS_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
     return v;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // Persistent: each CTA walks the work list  item = blockIdx.x + i * gridDim.x  (item -> n-tile fastest, then m-tile,
@@ -524,20 +450,6 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 using namespace lsg;
 
 namespace {
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 // 2-D fp32 tensor [outer][inner] with row pitch ld (elements), 128B-swizzled boxes {32, box_rows}, zero fill out of bounds
 int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_rows,
              CUtensorMapSwizzle swizzle) {
@@ -558,21 +470,11 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer,
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
              cudaStream_t stream) {
-    static bool configured = false;
+    static PerDeviceOnce once;                    // per instantiation, per device (ls_tc.cuh)
     constexpr int smem = smem_bytes(STAGES, BN);
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_gemm_tf32<A_MN, B_MN, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return ls_check_cuda("gemm smem attribute");
-        configured = true;
-    }
+    if (once.ensure_smem(k_gemm_tf32<A_MN, B_MN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("gemm smem attribute");
     const int n_items = (int)(grid.x * grid.y * grid.z);
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = current_sm_count();
     const int ctas = n_items < num_sms ? n_items : num_sms;
     k_gemm_tf32<A_MN, B_MN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K,
                                                                        (long long)a->ldc, a->act, kb_per_split, atomic,
@@ -586,18 +488,11 @@ constexpr int smem_bytes_2cta(int stages, int bn) { return stages * (A_BYTES + (
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 int launch_2cta_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, dim3 grid, int kb_per_split, int atomic,
                   cudaStream_t stream) {
-    static bool configured = false;
+    static PerDeviceOnce once;
     constexpr int smem = smem_bytes_2cta(STAGES, BN);
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_gemm_tf32_2cta<A_MN, B_MN, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return ls_check_cuda("gemm 2cta smem attribute");
-        configured = true;
-    }
+    if (once.ensure_smem(k_gemm_tf32_2cta<A_MN, B_MN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("gemm 2cta smem attribute");
     const int n_items = (int)(grid.x * grid.y * grid.z);
-    int dev = 0, num_sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
+    const int num_sms = current_sm_count();
     const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
     k_gemm_tf32_2cta<A_MN, B_MN, BN, STAGES><<<2 * clusters, kThreads, smem, stream>>>(
         ma, mb, a->C, a->bias, a->M, a->N, a->K, (long long)a->ldc, a->act, kb_per_split, atomic, (int)grid.x, (int)grid.y,
@@ -646,6 +541,7 @@ int pick_bn(int N) {
 
 extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
     if (!a) return ls_fail("gemm args is NULL");
+    bind_context();
     if (a->M <= 0 || a->N <= 0 || a->K <= 0) return ls_fail("gemm: bad sizes M=%d N=%d K=%d", a->M, a->N, a->K);
     if (!a->A || !a->B || !a->C) return ls_fail("gemm: NULL operand");
     if ((a->lda % 4) || (a->ldb % 4)) return ls_fail("gemm: lda/ldb must be multiples of 4 elements (TMA 16-byte stride rule)");

@@ -18,7 +18,7 @@ from torch.nn.functional import interpolate
 from ..diagonal_gaussian_distribution import DiagonalGaussianDistribution
 from .autoencoder import Autoencoder
 from .vae_kl import AutoencoderKLModel
-from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
+from latentsplat_b200.conv import Conv2d  # tcgen05 implicit-GEMM convolutions (NHWC) with fused bias + activation
 
 PRETRAINED_AUTOENCODER_PATH = "pretrained/autoencoder"     # /root/reference/src/constants.py:1
 

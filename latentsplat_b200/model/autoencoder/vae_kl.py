@@ -14,8 +14,8 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
-from latentsplat_b200.norm import GroupNorm  # nn.GroupNorm with the following SiLU fused in (sm_100a kernels on CUDA)
-from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
+from latentsplat_b200.norm import GroupNorm, group_norm_tokens  # GroupNorm with the following SiLU fused in (sm_100a kernels on CUDA)
+from latentsplat_b200.conv import Conv2d  # nn.Conv2d on the tcgen05 implicit-GEMM kernels (NHWC / channels_last on CUDA)
 
 
 class ResnetBlock2D(nn.Module):
@@ -50,13 +50,15 @@ class Attention(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         b, c, h, w = x.shape
-        t = self.group_norm(x.view(b, c, h * w)).transpose(1, 2)            # (b, hw, c)
+        # token-major (b, hw, c) view: free for channels_last activations (the convolutions' layout), one copy for NCHW
+        t = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+        gn = self.group_norm
+        t = group_norm_tokens(t, gn.num_groups, gn.weight, gn.bias, gn.eps)
         q, k, v = self.to_q(t), self.to_k(t), self.to_v(t)
         t = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
         t = self.to_out[1](self.to_out[0](t))
-        # x first: the sum inherits x's NCHW layout.  With the (b, hw, c)-strided view first the result is channels-last and
-        # every later residual `x + h` keeps that layout, so each GroupNorm / convolution up the decoder pays a layout copy.
-        return x + t.transpose(1, 2).reshape(b, c, h, w)
+        # x first: the sum inherits x's memory format, so the residual stream keeps one layout up the decoder
+        return x + t.reshape(b, h, w, c).permute(0, 3, 1, 2)
 
 
 class UNetMidBlock2D(nn.Module):

@@ -11,7 +11,7 @@ import torch
 from torch import Tensor, nn
 
 from .discriminator import Discriminator
-from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
+from latentsplat_b200.conv import Conv2d  # tcgen05 implicit-GEMM convolutions (NHWC) with fused bias + activation
 
 PRETRAINED_DISCRIMINATOR_PATH = "pretrained/discriminator"
 
@@ -35,8 +35,11 @@ class DiscriminatorPatchGan(Discriminator[DiscriminatorPatchGanCfg]):
         super().__init__(cfg)
         c = self.cfg
         act = lambda: nn.LeakyReLU(negative_slope=c.leaky_relu_neg_slope, inplace=True)
-        conv = lambda i, o, s, bias: Conv2d(i, o, kernel_size=c.kernel_size, stride=s, padding=c.padding, bias=bias)
-        layers = [conv(d_in, c.base_dim, c.downscale_factor, True), act()]
+        conv = lambda i, o, s, bias, a="none": Conv2d(i, o, kernel_size=c.kernel_size, stride=s, padding=c.padding, bias=bias, act=a)
+        # the first LeakyReLU follows its convolution directly: fused into the epilogue when the slope is the kernel's 0.2
+        # (an Identity keeps the Sequential indices main.N of the checkpoint)
+        fuse = c.leaky_relu_neg_slope == 0.2
+        layers = [conv(d_in, c.base_dim, c.downscale_factor, True, "lrelu" if fuse else "none"), nn.Identity() if fuse else act()]
         mult = 1
         for n in range(1, c.n_layers):
             prev, mult = mult, min(c.downscale_factor ** n, c.max_dim_mult)

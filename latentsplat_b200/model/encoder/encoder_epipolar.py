@@ -29,7 +29,7 @@ from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
 from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
 from .shims import apply_bounds_shim, apply_patch_shim
 from latentsplat_b200.gemm import Linear, grouped_linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
-from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
+from latentsplat_b200.conv import Conv2d  # tcgen05 implicit-GEMM convolutions (NHWC) with fused bias + activation
 
 
 @dataclass
@@ -81,7 +81,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         self.to_gaussians = nn.Sequential(nn.ReLU(), Linear(cfg.d_feature,
                                                                cfg.num_surfaces * (2 + self.gaussian_adapter.d_in)))
         # the high-resolution skip only exists without downscaling (:104-111)
-        self.high_resolution_skip = nn.Sequential(Conv2d(3, cfg.d_feature, 7, 1, 3), nn.ReLU()) \
+        self.high_resolution_skip = nn.Sequential(Conv2d(3, cfg.d_feature, 7, 1, 3, act="relu"), nn.Identity()) \
             if scale_factor == 1 else None
 
     def map_pdf_to_opacity(self, pdf: Tensor, global_step: int) -> Tensor:
@@ -91,15 +91,15 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         exponent = 2 ** x
         return 0.5 * (1 - (1 - pdf) ** exponent + pdf ** (1 / exponent))
 
-    def _backbone_features(self, images: Tensor) -> Tensor:
-        """(bv, c, H, W) -> projected features (bv, d_feature, h, w) == backbone_projection(backbone(x))."""
+    def _backbone_features(self, images: Tensor) -> tuple[Tensor, int]:
+        """(bv, c, H, W) -> (projected features (bv, d_feature, h, w), repeats): backbone_projection(backbone(x)) == the
+        returned map with every pixel replicated repeats x repeats times (repeats = 1: already full resolution)."""
         if isinstance(self.backbone, BackboneDino) and self.backbone.cfg.upscale_mode == "repeat":
             local, glob = self.backbone.forward_tokens(images)
             x = self.backbone_projection((local + glob).permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
-            n = self.backbone.n_repeats
-            return x.repeat_interleave(n, dim=2).repeat_interleave(n, dim=3)
+            return x, self.backbone.n_repeats
         x = self.backbone(images)
-        return self.backbone_projection(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return self.backbone_projection(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2), 1
 
     def _gaussian_head(self, features: Tensor, c2w_rotations: Tensor) -> Tensor:
         """to_gaussians(features) (:97-103) -- with the SH masking and the camera-to-world SH rotation of the Gaussian
@@ -125,15 +125,18 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
                 deterministic: bool = False, visualization_dump: Optional[dict] = None) -> VariationalGaussians:
         b, v = context["image"].shape[:2]
         images = context["image"].flatten(0, 1)
-        features = self._backbone_features(images if features is None else features)
+        features, repeats = self._backbone_features(images if features is None else features)
         device = features.device
-        h, w = features.shape[-2:]
+        h, w = features.shape[-2] * repeats, features.shape[-1] * repeats
         features = features.unflatten(0, (b, v))
 
         sampling = None
         if self.epipolar_transformer is not None:
+            # the un-replicated token grid goes in: the transformer's down-scaler collapses the replication algebraically
             features, sampling = self.epipolar_transformer(features, context["extrinsics"], context["intrinsics"],
-                                                           context["near"], context["far"])
+                                                           context["near"], context["far"], repeats=repeats)
+        elif repeats > 1:
+            features = features.repeat_interleave(repeats, dim=3).repeat_interleave(repeats, dim=4)
         if self.high_resolution_skip is not None:
             features = features + self.high_resolution_skip(images).unflatten(0, (b, v))
 

@@ -20,9 +20,9 @@ from ...transformer.transformer import Transformer
 from .conversions import depth_to_relative_disparity
 from .epipolar_sampler import EpipolarSampler, EpipolarSampling
 from .image_self_attention import ImageSelfAttention, ImageSelfAttentionCfg
-from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200.gemm import Linear, linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200 import epipolar_gather as fused_gather
-from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
+from latentsplat_b200.conv import Conv2d, ConvTranspose2d  # tcgen05 implicit-GEMM convolutions (NHWC) with fused bias + activation
 
 
 @dataclass
@@ -42,7 +42,9 @@ class ConvFeedForward(nn.Module):
 
     def __init__(self, self_attention_cfg: ImageSelfAttentionCfg, d_in: int, d_hidden: int, dropout: float) -> None:
         super().__init__()
-        self.layers = nn.Sequential(Conv2d(d_in, d_hidden, 7, 1, 3), nn.GELU(), nn.Dropout(dropout),
+        # reference: Conv, GELU, Dropout, Conv, Dropout (:164-170).  The GELU runs in the first convolution's epilogue; an
+        # Identity keeps the Sequential indices (checkpoint keys layers.0 / layers.3).
+        self.layers = nn.Sequential(Conv2d(d_in, d_hidden, 7, 1, 3, act="gelu"), nn.Identity(), nn.Dropout(dropout),
                                     Conv2d(d_hidden, d_in, 7, 1, 3), nn.Dropout(dropout))
         self.self_attention = ImageSelfAttention(self_attention_cfg, d_in, d_in)
 
@@ -65,16 +67,42 @@ class EpipolarTransformer(nn.Module):
                                        kv_dim=d_in, feed_forward_layer=partial(ConvFeedForward, cfg.self_attention))
         if cfg.downscale > 1:
             self.downscaler = Conv2d(d_in, d_in, cfg.downscale, cfg.downscale)
-            self.upscaler = nn.ConvTranspose2d(d_in, d_in, cfg.downscale, cfg.downscale)
-            self.upscale_refinement = nn.Sequential(Conv2d(d_in, d_in * 2, 7, 1, 3), nn.GELU(),
-                                                    Conv2d(d_in * 2, d_in, 7, 1, 3))
+            self.upscaler = ConvTranspose2d(d_in, d_in, cfg.downscale, cfg.downscale)
+            self.upscale_refinement = nn.Sequential(Conv2d(d_in, d_in * 2, 7, 1, 3, act="gelu"), nn.Identity(),
+                                                    Conv2d(d_in * 2, d_in, 7, 1, 3))      # Conv, GELU (fused), Conv (:70-74)
         else:
             self.downscaler = self.upscaler = self.upscale_refinement = None
 
-    def forward(self, features: Tensor, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor):
+    def _downscale(self, features: Tensor, repeats: int) -> Tensor:
+        """downscaler(repeat(features, repeats)) for (bv, c, h, w) features.  When every `repeats x repeats` block of the
+        full-resolution map is one replicated pixel (BackboneDino's "repeat" up-sampling, backbone_dino.py:72-84) and the
+        stride-`downscale` filter windows do not straddle blocks, the strided convolution sees a constant window:
+            conv(x_rep)[y, x] = (sum_{r,s} W[:, :, r, s]) x[y', x'] + b
+        i.e. a 1x1 Linear with the tap-summed weight on the coarse grid, replicated repeats/downscale times -- exact, and the
+        256x256x128 replicated tensor (268 MB at the bench shape) is never formed nor convolved (8.6 GMAC -> 0.13)."""
+        d = self.cfg.downscale
+        conv = self.downscaler
+        if repeats > 1 and repeats % d == 0:
+            w_sum = conv.weight.sum(dim=(2, 3))                                        # (c_out, c_in); autograd spreads the gradient over the taps
+            y = linear(features.permute(0, 2, 3, 1), w_sum, conv.bias)                  # (bv, h, w, c_out) token-major
+            k = repeats // d
+            if k > 1:
+                bv, hc, wc, c = y.shape
+                y = y[:, :, None, :, None, :].expand(bv, hc, k, wc, k, c).reshape(bv, hc * k, wc * k, c)
+            return y.permute(0, 3, 1, 2)                                                # NCHW view of NHWC memory (channels_last)
+        if repeats > 1:
+            features = features.repeat_interleave(repeats, dim=2).repeat_interleave(repeats, dim=3)
+        return conv(features)
+
+    def forward(self, features: Tensor, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, repeats: int = 1):
+        """`repeats` > 1: `features` is a coarse map whose pixels each stand for repeats x repeats identical full-resolution
+        pixels (the encoder passes the backbone's un-replicated token grid)."""
         b, v, c, h, w = features.shape
+        h, w = h * repeats, w * repeats
         if self.downscaler is not None:
-            features = self.downscaler(features.flatten(0, 1)).unflatten(0, (b, v))
+            features = self._downscale(features.flatten(0, 1), repeats).unflatten(0, (b, v))
+        elif repeats > 1:
+            features = features.repeat_interleave(repeats, dim=3).repeat_interleave(repeats, dim=4)
         hd, wd = h // self.cfg.downscale, w // self.cfg.downscale
 
         encoding = self.depth_encoding[1] if self.cfg.num_octaves > 0 else None

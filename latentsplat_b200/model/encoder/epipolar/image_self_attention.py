@@ -10,7 +10,7 @@ from ....geometry.projection import sample_image_grid
 from ...encodings.positional_encoding import PositionalEncoding
 from ...transformer.transformer import Transformer
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
-from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
+from latentsplat_b200.conv import Conv2d, ConvTranspose2d  # tcgen05 implicit-GEMM convolutions (NHWC) with fused bias + activation
 
 
 @dataclass
@@ -29,9 +29,9 @@ class ImageSelfAttention(nn.Module):
         super().__init__()
         pe = PositionalEncoding(cfg.num_octaves)
         self.positional_encoding = nn.Sequential(pe, Linear(pe.d_out(2), cfg.d_token))
-        self.patch_embedder = nn.Sequential(Conv2d(d_in, cfg.d_token, cfg.patch_size, cfg.patch_size), nn.ReLU())
+        self.patch_embedder = nn.Sequential(Conv2d(d_in, cfg.d_token, cfg.patch_size, cfg.patch_size, act="relu"), nn.Identity())
         self.transformer = Transformer(cfg.d_token, cfg.num_layers, cfg.num_heads, cfg.d_dot, cfg.d_mlp)
-        self.resampler = nn.ConvTranspose2d(cfg.d_token, d_out, cfg.patch_size, cfg.patch_size)
+        self.resampler = ConvTranspose2d(cfg.d_token, d_out, cfg.patch_size, cfg.patch_size)
 
     def forward(self, image: Tensor) -> Tensor:
         tokens = self.patch_embedder(image)

@@ -51,7 +51,58 @@ class _GroupNormFn(torch.autograd.Function):
         return dx, per_channel[:, 1].contiguous(), per_channel[:, 0].contiguous(), None, None, None
 
 
+class _GroupNormNhwcFn(torch.autograd.Function):
+    """GroupNorm (+ SiLU) over a token-major tensor x (N, L, C) -- the memory of an NCHW tensor in channels_last format."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, groups: int, eps: float, act: int):
+        N, L, Cn = x.shape
+        stats = torch.empty((N, Cn, 2), dtype=torch.float64, device=x.device)
+        y = torch.empty_like(x)
+        a = _capi.LsGroupNorm(N, Cn, groups, act, L, eps, x.data_ptr(), weight.data_ptr(), bias.data_ptr(), stats.data_ptr())
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.load().ls_groupnorm_nhwc_forward(C.byref(a), y.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "ls_groupnorm_nhwc_forward")
+        _capi.KERNEL_LAUNCHES[0] += 2
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.cfg = (groups, eps, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, weight, bias, stats = ctx.saved_tensors
+        groups, eps, act = ctx.cfg
+        N, L, Cn = x.shape
+        dy = dy.contiguous()
+        sums = torch.empty((N, Cn, 2), dtype=torch.float64, device=x.device)
+        dx = torch.empty_like(x)
+        a = _capi.LsGroupNorm(N, Cn, groups, act, L, eps, x.data_ptr(), weight.data_ptr(), bias.data_ptr(), stats.data_ptr())
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.load().ls_groupnorm_nhwc_backward(C.byref(a), dy.data_ptr(), dx.data_ptr(), sums.data_ptr(),
+                                                                torch.cuda.current_stream().cuda_stream), "ls_groupnorm_nhwc_backward")
+        _capi.KERNEL_LAUNCHES[0] += 2
+        per_channel = sums.sum(dim=0).to(torch.float32)            # (C, 2): d beta, d gamma
+        return dx, per_channel[:, 1].contiguous(), per_channel[:, 0].contiguous(), None, None, None
+
+
+def group_norm_tokens(t: Tensor, groups: int, weight: Tensor, bias: Tensor, eps: float, act: str = "none") -> Tensor:
+    """GroupNorm of a token-major tensor t (N, L, C) == F.group_norm(t.transpose(1, 2), ...).transpose(1, 2)."""
+    Cn = t.shape[-1]
+    if (ENABLED and t.is_cuda and t.dtype == torch.float32 and t.dim() == 3 and Cn % 4 == 0 and Cn <= 1024
+            and weight is not None and bias is not None and t.shape[0] <= 65535 and t.numel() > 0):
+        return _GroupNormNhwcFn.apply(t.contiguous(), weight, bias, groups, eps, 1 if act == "silu" else 0)
+    y = F.group_norm(t.transpose(1, 2), groups, weight, bias, eps).transpose(1, 2)
+    return F.silu(y) if act == "silu" else y
+
+
 def group_norm(x: Tensor, groups: int, weight: Tensor, bias: Tensor, eps: float, act: str = "none") -> Tensor:
+    if (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and not x.is_contiguous()
+            and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
+            and weight is not None and bias is not None and x.shape[0] <= 65535):
+        # channels_last activations (the implicit-GEMM convolutions' layout): normalise the (N, H*W, C) memory in place
+        N, Cn, H, W = x.shape
+        y = _GroupNormNhwcFn.apply(x.permute(0, 2, 3, 1).reshape(N, H * W, Cn), weight, bias, groups, eps, 1 if act == "silu" else 0)
+        return y.view(N, H, W, Cn).permute(0, 3, 1, 2)
     if (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x[0, 0].numel() % 4 == 0
             and weight is not None and bias is not None and x.shape[0] * x.shape[1] <= 65535):
         return _GroupNormFn.apply(x, weight, bias, groups, eps, 1 if act == "silu" else 0)

@@ -114,9 +114,27 @@ def test_hoisted_backbone_projection_equals_reference_order():
     with torch.no_grad():
         full = model.backbone(x)                                         # reference data flow (backbone_dino.py:72-84)
         ref = model.backbone_projection(full.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
-        ours = model._backbone_features(x)
+        coarse, repeats = model._backbone_features(x)
+        ours = coarse.repeat_interleave(repeats, dim=2).repeat_interleave(repeats, dim=3)
     assert full.shape == (2, 96, 32, 32)
     torch.testing.assert_close(ours, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_downscaler_on_replicated_features_is_a_linear_on_the_coarse_grid():
+    """EpipolarTransformer._downscale: the strided convolution over an 8x replicated map == tap-summed Linear on the
+    coarse grid, replicated 2x (exact up to fp32 summation order)."""
+    model = build_encoder()
+    helpers.init_by_name(model, seed=10)
+    et = model.epipolar_transformer
+    g = torch.Generator().manual_seed(3)
+    coarse = torch.randn(2, et.downscaler.in_channels, 4, 4, generator=g)
+    with torch.no_grad():
+        ref = et.downscaler(coarse.repeat_interleave(8, dim=2).repeat_interleave(8, dim=3))
+        ours = et._downscale(coarse, 8)
+        fallback = et._downscale(coarse, 3)          # 3 % 4 != 0: windows straddle blocks -> explicit path
+        ref3 = et.downscaler(coarse.repeat_interleave(3, dim=2).repeat_interleave(3, dim=3))
+    torch.testing.assert_close(ours, ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fallback, ref3, rtol=1e-5, atol=1e-6)
 
 
 def test_patch_gan_matches_reference_golden():
