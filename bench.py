@@ -343,12 +343,8 @@ def build_pipeline(device, seed=0):
     for q in disc.parameters():          # generator step: the discriminator is applied, not updated (model_wrapper.py:412-440)
         q.requires_grad_(False)
     pipe = RenderPipeline(ae, enc, dec, disc).to(device)
-    cl = os.environ.get("LS_CHANNELS_LAST", "")             # experiment switch: NHWC conv weights/activations
-    if "enc" in cl:
-        pipe.encoder.to(memory_format=torch.channels_last)
-    if "vae" in cl:
-        pipe.autoencoder.to(memory_format=torch.channels_last)
-        pipe.discriminator.to(memory_format=torch.channels_last)
+    # conv weights in channels_last = (Cout, R, S, Cin): the K-major matrix the implicit-GEMM kernels read (no per-call copy)
+    pipe.to(memory_format=torch.channels_last)
     # only the VAE *decoder* side is on the path (autoencoder.encode is never called)
     params = [p for n, p in pipe.named_parameters()
               if not (n.startswith("autoencoder.model.encoder") or n.startswith("autoencoder.model.quant_conv"))

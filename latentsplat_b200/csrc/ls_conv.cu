@@ -115,13 +115,32 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    // item -> (tile_m, tile_n, first K block, K blocks); n-tile fastest so that concurrently running CTAs share the A panel
-    auto decode = [&](int item, int& tile_m, int& tile_n, int& kb0, int& nkb) {
-        tile_n = item % p.tiles_n;
-        const int rest = item / p.tiles_n;
-        tile_m = rest % p.tiles_m;
-        kb0 = (rest / p.tiles_m) * p.kb_per_split;
-        nkb = min(p.nkb_total, kb0 + p.kb_per_split) - kb0;
+    // Work iterator.  MODE_F: whole tiles, item = blockIdx.x + i*gridDim.x (n-tile fastest so that concurrently running CTAs
+    // share the A panel).  MODE_W (stream-K): the tiles' K loops are laid end to end (tile-major) and cut into gridDim.x equal
+    // runs of K blocks, so every CTA does the same amount of tensor work whatever the tile count; a run may end inside one tile
+    // and continue in the next -- each piece is accumulated separately and leaves through red.global.add.
+    const long long w_total = (long long)p.tiles_m * p.tiles_n * p.nkb_total;
+    const long long w_per = (w_total + gridDim.x - 1) / gridDim.x;
+    const long long w_begin = MODE == MODE_W ? (long long)blockIdx.x * w_per : (long long)blockIdx.x;
+    const long long w_end = MODE == MODE_W ? min(w_total, w_begin + w_per) : (long long)n_items;
+    auto next_work = [&](long long& cur, int& tile_m, int& tile_n, int& kb0, int& nkb) -> bool {
+        if (cur >= w_end) return false;
+        if constexpr (MODE == MODE_W) {
+            const int tile = (int)(cur / p.nkb_total);
+            kb0 = (int)(cur - (long long)tile * p.nkb_total);
+            nkb = (int)min((long long)(p.nkb_total - kb0), w_end - cur);
+            tile_n = tile % p.tiles_n;
+            tile_m = tile / p.tiles_n;
+            cur += nkb;
+        } else {
+            const int item = (int)cur;
+            tile_n = item % p.tiles_n;
+            tile_m = item / p.tiles_n;
+            kb0 = 0;
+            nkb = p.nkb_total;
+            cur += gridDim.x;
+        }
+        return true;
     };
     // F: M tile -> image and first pixel of the iteration grid
     auto tile_origin = [&](int tile_m, int& n, int& y0, int& x0) {
@@ -135,9 +154,9 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (warp == 0 && lane == 0) {
         // ------------------------------ TMA producer ------------------------------
         uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int tile_m, tile_n, kb0, nkb;
-            decode(item, tile_m, tile_n, kb0, nkb);
+        long long cur = w_begin;
+        int tile_m, tile_n, kb0, nkb;
+        while (next_work(cur, tile_m, tile_n, kb0, nkb)) {
             if constexpr (MODE == MODE_F) {
                 int n, y0, x0;
                 tile_origin(tile_m, n, y0, x0);
@@ -200,9 +219,9 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         uint32_t it = 0, local = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
-            int tile_m, tile_n, kb0, nkb;
-            decode(item, tile_m, tile_n, kb0, nkb);
+        long long cur = w_begin;
+        int tile_m, tile_n, kb0, nkb;
+        for (; next_work(cur, tile_m, tile_n, kb0, nkb); ++local) {
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
             mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);
             tc_fence_after();
@@ -228,9 +247,9 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         uint32_t local = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
-            int tile_m, tile_n, kb0, nkb;
-            decode(item, tile_m, tile_n, kb0, nkb);
+        long long cur = w_begin;
+        int tile_m, tile_n, kb0, nkb;
+        for (; next_work(cur, tile_m, tile_n, kb0, nkb); ++local) {
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
             mbar_wait(tfull0 + 8 * acc, acc_ph);
             tc_fence_after();
@@ -345,6 +364,167 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
 }
 
+// =================================================================================================================
+// MODE_T: the transposed orientation of MODE_F,  D[channel, pixel] = sum_k W[channel, k] * X[pixel, k]:
+//   A = 128 output channels of the weight matrix (K-major box, or MN-major boxes for dgrad / transposed-conv forward)
+//   B = BN = 256 (or 128) pixels of the activation tensor: ONE 4-D TMA box {32 channels, BW, BH, 1} per K block
+// Every layer -- also the Cout = 128 ones, which as N = 128 tiles were shared-memory bound -- runs M128 x N256 MMAs
+// (12 KB of operands per 135 tensor cycles), and the accumulator arrives with one output channel per TMEM lane: a warp's
+// tcgen05.ld hands lane l the values of channel c0+l for 32 consecutive pixels, so each store instruction writes 32
+// consecutive channels of one NHWC pixel (128 contiguous bytes) -- no shared-memory transpose in the epilogue.
+// =================================================================================================================
+constexpr int smem_bytes_t(int stages, int bn) { return stages * (A_BYTES + bn * BK * 4) + 1024 + 256; }
+
+template <bool AMN, int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+         const __grid_constant__ ConvParams p) {
+    constexpr int B_BYTES = BN * BK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = 2 * BN;                           // 256 / 512
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S] empty[S] tfull[2] tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.tiles_m * p.tiles_n;                  // tiles_m: channel tiles (128), tiles_n: pixel tiles (BN)
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    // item -> channel tile (fastest: CTAs running together share the pixel box in L2) and pixel tile -> image, first pixel
+    auto decode = [&](int item, int& tile_m, int& n, int& y0, int& x0) {
+        tile_m = item % p.tiles_m;
+        const int tp = item / p.tiles_m;
+        const int tx = tp % p.tiles_x;
+        const int t = tp / p.tiles_x;
+        n = t / p.tiles_y;
+        y0 = (t - n * p.tiles_y) * (BN >> p.bw_log2);
+        x0 = tx << p.bw_log2;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int tile_m, n, y0, x0;
+            decode(item, tile_m, n, y0, x0);
+            const int m0 = tile_m * BM;
+            for (int r = 0; r < p.R; ++r) {
+                const int by = y0 * p.a.sy + p.a.dy0 + r * p.a.dys;
+                for (int s = 0; s < p.S; ++s) {
+                    const int bx = x0 * p.a.sx + p.a.dx0 + s * p.a.dxs;
+                    const int wk = p.wp * ((p.wr0 + r * p.wrs) * p.wS + p.ws0 + s * p.wss);
+                    for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                        const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                        mbar_wait(empty0 + 8 * st, ph ^ 1);
+                        mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
+                        const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                        if (!AMN) {
+                            tma_load_2d(a_dst, &map_w, full0 + 8 * st, wk + ch * BK, m0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / 32; ++j)
+                                tma_load_2d(a_dst + j * 4096, &map_w, full0 + 8 * st, wk + m0 + 32 * j, ch * BK);
+                        }
+                        tma_load_4d(b_dst, &map_x, full0 + 8 * st, ch * BK, bx, by, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------ MMA issuer --------------------------------
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t it = 0, local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < p.nkb_total; ++kb, ++it) {
+                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + st * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = AMN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+                    const uint64_t bdesc = make_desc(b_src + k * 32, 16, 1024, 2);
+                    tc_mma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(empty0 + 8 * st);
+            }
+            tc_commit(tfull0 + 8 * acc);
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue ----------------------------------
+        const int q = warp - 4;                  // TMEM lane quarter == warp % 4
+        uint32_t local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int tile_m, n, y0, x0;
+            decode(item, tile_m, n, y0, x0);
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            const int co = tile_m * BM + q * 32 + lane;             // this lane's output channel
+            const bool co_ok = co < p.n_out;
+            const float bias = (p.bias != nullptr && co_ok) ? p.bias[co] : 0.f;
+            float* __restrict__ out = p.out + (long long)n * p.o_sn + co;
+            float* __restrict__ pre = p.pre_out ? p.pre_out + (long long)n * p.o_sn + co : nullptr;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tc_fence_after();
+            if (tile_m * BM + q * 32 < p.n_out) {                   // warp-uniform: this warp owns live channels
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int iy0 = y0 + (c0 >> p.bw_log2);
+                    if (iy0 >= p.P) break;                           // the remaining pixel rows of the box lie outside the grid
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int pix = c0 + j;
+                        const int iy = y0 + (pix >> p.bw_log2), ix = x0 + (pix & ((1 << p.bw_log2) - 1));
+                        if (iy < p.P && ix < p.Q && co_ok) {
+                            const long long off = (long long)(iy * p.oys + p.oyo) * p.o_sh + (long long)(ix * p.oxs + p.oxo) * p.o_sw;
+                            const float v = __uint_as_float(r[j]) + bias;
+                            out[off] = apply_act(v, p.act);
+                            if (pre) pre[off] = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // elementwise backward of the fused epilogue activations: dx = dy * act'(pre)
 __global__ void __launch_bounds__(256) k_act_bwd(const float4* __restrict__ dy, const float4* __restrict__ pre,
                                                  float4* __restrict__ dx, long long n4, int act) {
@@ -424,10 +604,16 @@ int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, 
     static PerDeviceOnce once;
     constexpr int smem = smem_bytes(STAGES, BN);
     if (once.ensure_smem(k_conv_tf32<MODE, BMN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
-    const long long n_items = (long long)p.tiles_m * p.tiles_n * p.splits;
+    const long long n_items = (long long)p.tiles_m * p.tiles_n;
     if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
     const int num_sms = current_sm_count();
-    const int ctas = n_items < num_sms ? (int)n_items : num_sms;
+    int ctas;
+    if (MODE == MODE_W) {                       // stream-K: every CTA gets an equal run of K blocks (at least 8)
+        const long long runs = n_items * p.nkb_total / 8;
+        ctas = runs < num_sms ? (runs < 1 ? 1 : (int)runs) : num_sms;
+    } else {
+        ctas = n_items < num_sms ? (int)n_items : num_sms;
+    }
     k_conv_tf32<MODE, BMN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, p);
     return ls_check_cuda("k_conv_tf32");
 }
@@ -496,6 +682,74 @@ int run_f(const FProblem& f, cudaStream_t stream) {
     return launch<MODE_F, false>(BN, ma, mb, p, stream);
 }
 
+template <bool AMN, int BN, int STAGES>
+int launch_t_s(const CUtensorMap& mw, const CUtensorMap& mx, const ConvParams& p, cudaStream_t stream) {
+    static PerDeviceOnce once;
+    constexpr int smem = smem_bytes_t(STAGES, BN);
+    if (once.ensure_smem(k_conv_t<AMN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
+    const long long n_items = (long long)p.tiles_m * p.tiles_n;
+    if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
+    const int num_sms = current_sm_count();
+    const int ctas = n_items < num_sms ? (int)n_items : num_sms;
+    k_conv_t<AMN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(mw, mx, p);
+    return ls_check_cuda("k_conv_t");
+}
+
+// MODE_T host side: same problem description as MODE_F
+int run_t(const FProblem& f, cudaStream_t stream) {
+    ConvParams p{};
+    p.P = f.P; p.Q = f.Q; p.n_img = f.in.N;
+    const int num_sms = current_sm_count();
+    const int tiles_m = (f.n_out + BM - 1) / BM;
+    // 256-pixel tiles unless they leave most SMs idle (small feature maps): then 128-pixel tiles double the CTA count
+    int BN = 256;
+    {
+        const long long px256 = (long long)f.in.N * ((f.P * (long long)f.Q + 255) / 256);
+        if (px256 * tiles_m < num_sms) BN = 128;
+    }
+    int bw = pow2_ceil_log2(f.Q);
+    const int bn_log2 = BN == 256 ? 8 : 7;
+    if (bw > bn_log2) bw = bn_log2;
+    while ((1 << bw) * f.sx > 256) --bw;
+    while ((BN >> bw) * f.sy > 256) ++bw;
+    if ((1 << bw) * f.sx > 256) return ls_fail("conv: no TMA box for a %d-pixel tile at stride %d", BN, f.sx);
+    p.bw_log2 = bw;
+    const int BW = 1 << bw, BH = BN >> bw;
+    p.tiles_x = (f.Q + BW - 1) / BW;
+    p.tiles_y = (f.P + BH - 1) / BH;
+    p.tiles_m = tiles_m;
+    p.tiles_n = f.in.N * p.tiles_x * p.tiles_y;
+    p.splits = 1;
+    p.R = f.R; p.S = f.S; p.chunks = (f.in.C + BK - 1) / BK;
+    p.nkb_total = p.kb_per_split = p.R * p.S * p.chunks;
+    p.a = ActOp{1 << 30, 1, f.sx, f.sy, f.dx0, f.dy0, f.dxs, f.dys};
+    p.b = p.a;
+    p.wp = f.wp; p.wr0 = f.wr0; p.wrs = f.wrs; p.ws0 = f.ws0; p.wss = f.wss; p.wS = f.wS;
+    p.o_sn = f.o_sn; p.o_sh = f.o_sh; p.o_sw = f.o_sw;
+    p.oys = f.oys; p.oyo = f.oyo; p.oxs = f.oxs; p.oxo = f.oxo;
+    p.n_out = f.n_out; p.act = f.act;
+    p.out = f.out; p.pre_out = f.pre; p.bias = f.bias;
+    if (p.nkb_total <= 0 || p.tiles_n <= 0) return ls_fail("conv: empty problem");
+    CUtensorMap mw, mx;
+    if (make_act_map(&mx, f.in, BW, BH, f.sx, f.sy, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (f.w_mn) {
+        if (make_w_map(&mw, f.w, f.w_rows, f.w_cols, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+        return BN == 256 ? launch_t_s<true, 256, 4>(mw, mx, p, stream) : launch_t_s<true, 128, 6>(mw, mx, p, stream);
+    }
+    if (make_w_map(&mw, f.w, f.w_rows, f.w_cols, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    return BN == 256 ? launch_t_s<false, 256, 4>(mw, mx, p, stream) : launch_t_s<false, 128, 6>(mw, mx, p, stream);
+}
+
+// orientation switch (A/B measurements): LS_CONV_ORIENT=f keeps pixels on the M side (MODE_F), default = MODE_T
+int run_fwdlike(const FProblem& f, cudaStream_t stream) {
+    static int use_f = -1;
+    if (use_f < 0) {
+        const char* e = getenv("LS_CONV_ORIENT");
+        use_f = (e && (e[0] == 'f' || e[0] == 'F')) ? 1 : 0;
+    }
+    return use_f ? run_f(f, stream) : run_t(f, stream);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // MODE_W problem description (host): out[(tap_r, ch_r), (tap_c, ch_c)] = sum_pixels A[pixel + tap_r][ch_r] * B[pixel + tap_c][ch_c]
 // ------------------------------------------------------------------------------------------------------------------
@@ -521,21 +775,15 @@ int run_w(const WOperand& A, const WOperand& B, int P, int Q, float* out, long l
     const int BN = pick_bn(N);
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
-    // split the pixel loop so that ~2 waves of work items exist, each at least 8 K blocks long
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int num_sms = current_sm_count();
-    int split = tiles >= 2 * num_sms ? 1 : (2 * num_sms + tiles - 1) / tiles;
-    if (split > p.nkb_total / 8) split = p.nkb_total / 8;
-    if (split < 1) split = 1;
-    p.kb_per_split = (p.nkb_total + split - 1) / split;
-    p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = 1;                                   // stream-K inside the kernel: the grid cuts the concatenated K loops evenly
+    p.kb_per_split = p.nkb_total;
     p.a = ActOp{A.taps > 1 ? cpa : (1 << 30), A.S, A.sx, A.sy, A.dx0, A.dy0, 1, 1};
     p.b = ActOp{B.taps > 1 ? cpb : (1 << 30), B.S, B.sx, B.sy, B.dx0, B.dy0, 1, 1};
     p.cp_r = A.taps > 1 ? cpa : (1 << 30); p.c_r = A.C; p.t_r = A.taps;
     p.cp_c = B.taps > 1 ? cpb : (1 << 30); p.c_c = B.C; p.t_c = B.taps;
     p.rs = rs; p.cs = cs;
     p.out = out;
-    p.atomic = p.splits > 1 ? 1 : 0;
+    p.atomic = 1;                                   // pieces of one tile come from several CTAs; dw is zero-filled by the caller
     p.vec_ok = (cs == 1 && rs % 4 == 0 && B.C % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     if (p.nkb_total <= 0) return ls_fail("conv wgrad: empty problem");
     CUtensorMap ma, mb;
@@ -594,7 +842,7 @@ extern "C" int ls_conv2d_forward(const LsConv2d* c, const float* x, const float*
         f.w_rows = c->Cout; f.w_cols = (long long)c->R * c->S * c->Cin; f.w_mn = 0;
         f.wp = c->Cin; f.wr0 = 0; f.wrs = 1; f.ws0 = 0; f.wss = 1; f.wS = c->S;
         f.oys = f.oxs = 1; f.oyo = f.oxo = 0;
-        return run_f(f, stream);
+        return run_fwdlike(f, stream);
     }
     // transposed, kernel == stride: y[n, k*Y + r, k*X + s, :] = x[n, Y, X, :] W[:, r, s, :] ; one 1-tap GEMM per (r, s) class,
     // W = [Cin][R*S*Cout] read MN-major (rows = input channel = k, columns = tap*Cout + output channel)
@@ -606,7 +854,7 @@ extern "C" int ls_conv2d_forward(const LsConv2d* c, const float* x, const float*
     for (int r = 0; r < c->R; ++r)
         for (int s = 0; s < c->S; ++s) {
             f.wr0 = r; f.ws0 = s; f.oyo = r; f.oxo = s;
-            if (run_f(f, stream)) return -1;
+            if (run_fwdlike(f, stream)) return -1;
         }
     return 0;
 }
@@ -630,7 +878,7 @@ extern "C" int ls_conv2d_dgrad(const LsConv2d* c, const float* dy, const float* 
         f.w_rows = c->Cin; f.w_cols = (long long)c->R * c->S * c->Cout; f.w_mn = 0;
         f.wp = c->Cout; f.wr0 = 0; f.wrs = 1; f.ws0 = 0; f.wss = 1; f.wS = c->S;
         f.oys = f.oxs = 1; f.oyo = f.oxo = 0;
-        return run_f(f, stream);
+        return run_fwdlike(f, stream);
     }
     // dx[n,y,x,ci] = sum_{r,s,co} dy[n, (y + pad - r)/st, (x + pad - s)/st, co] W[co, r, s, ci]  (terms with a remainder vanish):
     // one stride-1 gather per residue class (y % st, x % st), taps r = ra + st*i with ra = (py + pad) % st.
@@ -655,7 +903,7 @@ extern "C" int ls_conv2d_dgrad(const LsConv2d* c, const float* dy, const float* 
             f.dy0 = (py + c->pad - ra) / st; f.dx0 = (px + c->pad - sa) / st;
             f.wr0 = ra; f.wrs = st; f.ws0 = sa; f.wss = st;
             f.oyo = py; f.oxo = px;
-            if (run_f(f, stream)) return -1;
+            if (run_fwdlike(f, stream)) return -1;
         }
     return 0;
 }

@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def test_library_exports_every_declared_symbol(lib):
     header = (ROOT / "include" / "ls_raster.h").read_text()
-    both = header + (ROOT / "include" / "ls_gemm.h").read_text() + (ROOT / "include" / "ls_epipolar.h").read_text() + (ROOT / "include" / "ls_norm.h").read_text()
+    both = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))      # every header of the C ABI
     declared = set(re.findall(r"LS_API\s+[\w\s\*]+?\b(ls_\w+)\s*\(", both))
     from latentsplat_b200 import _capi
     assert declared == set(_capi.EXPORTS), declared
@@ -24,9 +24,9 @@ def test_struct_layouts_match_the_header():
     """Field order of the ctypes mirrors == field order in the header (names), a cheap drift detector."""
     from latentsplat_b200 import _capi
     header = (ROOT / "include" / "ls_raster.h").read_text()
-    header += (ROOT / "include" / "ls_gemm.h").read_text() + (ROOT / "include" / "ls_epipolar.h").read_text() + (ROOT / "include" / "ls_norm.h").read_text()
+    header = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))
     for name in ("LsRasterScene", "LsRasterState", "LsRasterImages", "LsRasterGrads", "LsRasterSizes", "LsGemmArgs",
-                 "LsEpipolarGather", "LsGroupNorm"):
+                 "LsEpipolarGather", "LsGroupNorm", "LsConv2d"):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
@@ -61,6 +61,23 @@ def test_sizes_and_validation_without_gpu(lib):
     sc.feature_mode, sc.C = _capi.FEATURE_PRECOMP, 40
     assert lib.ls_raster_forward(C.byref(sc), C.byref(st), C.byref(im), 3, None) != 0
     assert b"LS_MAX_VALUE_CHANNELS" in lib.ls_last_error()
+
+
+def test_conv_descriptor_validation_without_gpu(lib):
+    """ls_conv2d_*: sizes and argument checks run on the host before anything is enqueued."""
+    from latentsplat_b200 import _capi
+    d = _capi.LsConv2d(2, 64, 48, 32, 64, 3, 3, 1, 1, 0)
+    oh, ow = C.c_int32(), C.c_int32()
+    assert lib.ls_conv2d_out_size(C.byref(d), C.byref(oh), C.byref(ow)) == 0 and (oh.value, ow.value) == (64, 48)
+    d = _capi.LsConv2d(2, 64, 64, 32, 64, 4, 4, 2, 1, 0)
+    assert lib.ls_conv2d_out_size(C.byref(d), C.byref(oh), C.byref(ow)) == 0 and (oh.value, ow.value) == (32, 32)
+    d = _capi.LsConv2d(2, 16, 16, 32, 64, 4, 4, 4, 0, 1)
+    assert lib.ls_conv2d_out_size(C.byref(d), C.byref(oh), C.byref(ow)) == 0 and (oh.value, ow.value) == (64, 64)
+    bad = _capi.LsConv2d(2, 16, 16, 3, 64, 3, 3, 1, 1, 0)                      # channels must be padded to a multiple of 4
+    assert lib.ls_conv2d_out_size(C.byref(bad), C.byref(oh), C.byref(ow)) != 0 and b"multiples of 4" in lib.ls_last_error()
+    bad = _capi.LsConv2d(2, 16, 16, 32, 64, 3, 3, 2, 0, 1)                     # overlapping transposed convolution
+    assert lib.ls_conv2d_forward(C.byref(bad), None, None, None, None, None, 0, None) != 0 and b"transposed" in lib.ls_last_error()
+    assert lib.ls_conv2d_forward(C.byref(d), None, None, None, None, None, 0, None) != 0 and b"NULL" in lib.ls_last_error()
 
 
 def test_product_fails_loudly_without_cuda():
