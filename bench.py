@@ -52,10 +52,10 @@ def workload_name(cfg) -> str:
                 "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar gather + depth encoding, weight-absorbed epipolar cross-attention, "
                 "GroupNorm+SiLU, LayerNorm; library: cuDNN convolutions (TF32), DINO / VAE-mid attention cores (bf16 flash / "
                 "mem-efficient SDPA), remaining elementwise glue (torch)")
-    return (f"re10k_shaped_splat_fwd_bwd: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views {H}x{W}, "
+    return (f"splat_{'fwd_only' if FWD_ONLY else 'fwd_bwd'}: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views {H}x{W}, "
             f"G={cfg['G']} feature Gaussians/scene (colour SH deg {cfg['color_sh_degree']} + C={cfg['C']} feature SH "
-            f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA fwd+bwd with scalar loss heads; "
-            "encoder + VAE decoder of configs[1] not yet in the timed step")
+            f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA {'forward' if FWD_ONLY else 'fwd+bwd'} with scalar loss heads "
+            "(the rasterizer alone; BASELINE configs[4] when 512x512 / 250 000 / V_t=4 / forward only)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -92,16 +92,22 @@ def loss_heads(out, target):
         0.01 * out.depth.mean()
 
 
+FWD_ONLY = False      # --fwd-only / --config 4: the rasterizer stress of BASELINE configs[4] is a forward-only workload
+
+
 def step_device(dec, dev_batch, leaves):
     """value: inputs already resident in HBM."""
+    import torch
     from latentsplat_b200.model.types import Gaussians
     for t in leaves.values():
         t.grad = None
-    g = Gaussians(leaves["means"], leaves["covariances"], leaves["opacities"], leaves["color_harmonics"],
-                  leaves["feature_harmonics"])
-    out = dec(g, dev_batch["extrinsics"], dev_batch["intrinsics"], dev_batch["near"], dev_batch["far"], (H, W))
-    loss = loss_heads(out, dev_batch["target"])
-    loss.backward()
+    with torch.set_grad_enabled(not FWD_ONLY):
+        g = Gaussians(leaves["means"], leaves["covariances"], leaves["opacities"], leaves["color_harmonics"],
+                      leaves["feature_harmonics"])
+        out = dec(g, dev_batch["extrinsics"], dev_batch["intrinsics"], dev_batch["near"], dev_batch["far"], (H, W))
+        loss = loss_heads(out, dev_batch["target"])
+    if not FWD_ONLY:
+        loss.backward()
     return loss
 
 
@@ -477,10 +483,11 @@ def run_full(args, cfg):
     value = world * views_per_step / (ms_per_step / 1000)
     e2e_value = world * views_per_step / (e2e_ms / args.steps / 1000)
 
-    roofline = stages = cpu = None
+    roofline = stages = cpu = gpu_base = None
     if rank == 0:
         roofline, stages = full_stage_profile(pipe, dev_flat, cfg, fwd_bwd)
         if world == 1:
+            gpu_base = gpu_baseline_full(pipe, fwd_bwd, opt_step, dev_flat, timed_loop, views_per_step)
             cpu = cpu_baseline_full(cfg, min_seconds=0.0, max_steps=1)
     if world > 1:
         dist.barrier()
@@ -504,11 +511,54 @@ def run_full(args, cfg):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "stages": stages,
         }
+        if gpu_base is not None:
+            line["gpu_baseline"] = gpu_base
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_baseline_full(pipe, fwd_bwd, opt_step, dev_flat, timed_loop, views_per_step, steps=5):
+    """GPU comparator (north_star: "next to the reference's own CUDA rasterizer + PyTorch path timed on the same box").
+    The reference's rasterizer fork is not installable here (un-vendored, no network), so the comparator is the reference's
+    MATH on this box: the same modules and weights with every kernel of ours switched off -- nn.Linear on cuBLAS fp32
+    (torch default matmul precision "highest", as the reference), convolutions on cuDNN (TF32 allowed, torch default),
+    GroupNorm / LayerNorm / attention / epipolar sampling as the explicit torch op sequence of the reference modules, fp32 SDPA
+    -- executed eagerly (no CUDA graph) with the reference's per-view rasterizer loop and its host syncs
+    (cuda_splatting.py:124-162), on OUR rasterizer kernels (labelled accordingly)."""
+    import torch
+    from latentsplat_b200 import attention, conv, epipolar_gather, gemm, norm
+    from latentsplat_b200.model.decoder import cuda_splatting
+    from latentsplat_b200.model.encoder import encoder_epipolar
+    from latentsplat_b200.model.encoder.backbone import dino_vit
+    saved = (gemm.enabled, conv.ENABLED, norm.ENABLED, attention.ABSORB, attention.ENABLED, epipolar_gather.ENABLED,
+             dino_vit.ATTENTION_BF16, encoder_epipolar.FOLD_HARMONICS, cuda_splatting.PER_VIEW_LOOP,
+             torch.backends.cuda.matmul.allow_tf32, pipe.decoder.raster_capacity)
+    try:
+        gemm.enabled = conv.ENABLED = norm.ENABLED = attention.ABSORB = attention.ENABLED = epipolar_gather.ENABLED = False
+        dino_vit.ATTENTION_BF16 = encoder_epipolar.FOLD_HARMONICS = False
+        cuda_splatting.PER_VIEW_LOOP = True
+        torch.backends.cuda.matmul.allow_tf32 = False
+        pipe.decoder.raster_capacity = None                       # exact sizing: one host sync per view, as the reference
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fwd_bwd(dev_flat); opt_step()
+            ms, _ = timed_loop(lambda: (fwd_bwd(dev_flat), opt_step()), steps)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+    finally:
+        (gemm.enabled, conv.ENABLED, norm.ENABLED, attention.ABSORB, attention.ENABLED, epipolar_gather.ENABLED,
+         dino_vit.ATTENTION_BF16, encoder_epipolar.FOLD_HARMONICS, cuda_splatting.PER_VIEW_LOOP,
+         torch.backends.cuda.matmul.allow_tf32, pipe.decoder.raster_capacity) = saved
+    ms /= steps
+    return {"value": views_per_step / (ms / 1000), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "kind": "reference math on our rasterizer: same modules/weights, all own encoder/decoder kernels off (cuBLAS fp32 "
+                    "linears, cuDNN TF32 convolutions, torch norms / attention / grid_sample), eager, per-view rasterizer loop "
+                    "with host syncs; the reference's rasterizer fork itself is not installable here"}
 
 
 def full_stage_profile(pipe, dev_flat, cfg, fwd_bwd):
@@ -764,6 +814,11 @@ def run_ours(args, cfg):
     capacity = dec.calibrate_raster_capacity(slack=1.5)
 
     def graph_fn(inp):
+        if FWD_ONLY:
+            with torch.no_grad():
+                g = Gaussians(*[inp[k] for k in GAUSSIAN_KEYS])
+                out = dec(g, inp["extrinsics"], inp["intrinsics"], inp["near"], inp["far"], (H, W))
+                return {"loss": loss_heads(out, inp["target"])}
         lv = {k: inp[k].detach().requires_grad_(True) for k in GAUSSIAN_KEYS}
         g = Gaussians(lv["means"], lv["covariances"], lv["opacities"], lv["color_harmonics"], lv["feature_harmonics"])
         out = dec(g, inp["extrinsics"], inp["intrinsics"], inp["near"], inp["far"], (H, W))
@@ -845,7 +900,7 @@ def run_ours(args, cfg):
                                     f"rasterizer in sync-free capacity mode ({capacity} key slots, overflow flag checked)",
                        "eager_exact_ms_per_step": eager_ms / args.steps},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": 7, "clocks": clocks, "roofline": roofline, "stages": stages,
+            "gpu_launches": 5 if FWD_ONLY else 7, "clocks": clocks, "roofline": roofline, "stages": stages,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -868,10 +923,27 @@ def main():
     ap.add_argument("--profiler-range", nargs="?", const="graph", default=None, choices=["graph", "eager"],
                     help="for `ncu --profile-from-start off`: bracket the timed device steps with cudaProfilerStart/Stop and "
                          "skip the e2e / stage / CPU-baseline legs (numbers printed by such a run are not bench values)")
+    ap.add_argument("--focal", type=float, default=CFG["f"], help="normalised focal length (RE10k-shaped 0.86, CO3D-shaped 1.2)")
+    ap.add_argument("--fwd-only", action="store_true", help="splat workload: forward only (BASELINE configs[4])")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="reproduce BASELINE.json configs[N] exactly: 1 = RE10k-shaped full step B=4 V_t=1 (the default), "
+                         "2 = CO3D-shaped full step B=2, 2->3 views, f=1.2, background 0, variational sampling in the timed region, "
+                         "3 = RE10k-shaped full step B=8 per GPU (run under torchrun at 2/4/8 ranks), "
+                         "4 = rasterizer stress 512x512, 250 000 Gaussians, 4 target views, forward only")
     args = ap.parse_args()
-    global H, W
+    if args.config == 1:
+        args.workload, args.batch, args.target_views, args.focal, args.resolution = "full", 4, 1, 0.86, 256
+    elif args.config == 2:
+        args.workload, args.batch, args.target_views, args.focal, args.resolution = "full", 2, 3, 1.2, 256
+    elif args.config == 3:
+        args.workload, args.batch, args.target_views, args.focal, args.resolution = "full", 8, 1, 0.86, 256
+    elif args.config == 4:
+        args.workload, args.batch, args.target_views, args.gaussians, args.resolution, args.fwd_only = "splat", 1, 4, 250_000, 512, True
+    global H, W, FWD_ONLY
     H = W = args.resolution
-    cfg = dict(CFG, V_t=args.target_views, G=args.gaussians, B=args.batch, workload=args.workload)
+    FWD_ONLY = bool(args.fwd_only)
+    cfg = dict(CFG, V_t=args.target_views, G=args.gaussians, B=args.batch, workload=args.workload, f=args.focal,
+               baseline_config=args.config or (1 if (args.workload, args.batch, args.target_views, args.resolution) == ("full", 4, 1, 256) else None))
     # stdout carries exactly ONE JSON line: anything a library writes to file descriptor 1 while we run (NCCL prints
     # "NCCL version ..." there on communicator creation, whatever NCCL_DEBUG says) is sent to stderr, and `print` is bound
     # to the saved descriptor.

@@ -35,7 +35,7 @@ extern "C" {
 typedef struct LsConv2d {
     int32_t N, H, W, Cin;  /* input x (N,H,W,Cin); Cin % 4 == 0                                                   */
     int32_t Cout, R, S;    /* filter; Cout % 4 == 0                                                               */
-    int32_t stride, pad;   /* same in both directions; Conv2d: stride 1..4.  transposed: stride == R == S, pad 0  */
+    int32_t stride, pad;   /* same in both directions; Conv2d: stride 1..8.  transposed: stride == R == S, pad 0  */
     int32_t transposed;    /* 0: nn.Conv2d   1: nn.ConvTranspose2d (non-overlapping: kernel == stride)            */
 } LsConv2d;
 

@@ -7,6 +7,7 @@ from torch import Tensor
 from . import _capi
 
 ABSORB = True      # use the weight-absorbed cross-attention when applicable (set False for A/B comparisons)
+ENABLED = True     # set False to route the epipolar cross-attention through the explicit torch sequence (bench comparator)
 
 
 class _SingleQueryAttention(torch.autograd.Function):
@@ -48,7 +49,7 @@ def single_query_attention(q: Tensor, kv: Tensor, heads: int, scale: float) -> T
 
 
 def supported(q: Tensor, kv: Tensor, heads: int) -> bool:
-    return (q.is_cuda and q.dtype == torch.float32 and kv.dtype == torch.float32 and q.dim() == 2 and kv.dim() == 3
+    return (ENABLED and q.is_cuda and q.dtype == torch.float32 and kv.dtype == torch.float32 and q.dim() == 2 and kv.dim() == 3
             and q.shape[1] == heads * 128 and kv.shape[2] == 2 * heads * 128 and kv.shape[1] <= 32)
 
 
@@ -123,6 +124,6 @@ def absorbed_cross_attention(q: Tensor, z: Tensor, w_kv: Tensor, heads: int, sca
 
 
 def absorbed_supported(q: Tensor, z: Tensor, w_kv: Tensor, heads: int) -> bool:
-    return (q.is_cuda and q.dtype == z.dtype == w_kv.dtype == torch.float32 and q.dim() == 2 and z.dim() == 3
+    return (ENABLED and q.is_cuda and q.dtype == z.dtype == w_kv.dtype == torch.float32 and q.dim() == 2 and z.dim() == 3
             and z.shape[2] == 128 and z.shape[1] <= 32 and heads <= 8 and q.shape[1] % heads == 0
             and (q.shape[1] // heads) % 4 == 0 and w_kv.shape == (2 * q.shape[1], 128))

@@ -155,7 +155,7 @@ class Conv2d(nn.Conv2d):
         return (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[0] > 0 and self.groups == 1
                 and self.padding_mode == "zeros" and not isinstance(self.padding, str) and tuple(self.dilation) == (1, 1)
                 and _int_pair(self.stride) is not None and _int_pair(self.padding) is not None
-                and 1 <= _int_pair(self.stride) <= 4 and self.weight.dtype == torch.float32)
+                and 1 <= _int_pair(self.stride) <= 8 and self.weight.dtype == torch.float32)
 
     def forward(self, input: Tensor) -> Tensor:
         if self._native(input):
@@ -175,7 +175,7 @@ class ConvTranspose2d(nn.ConvTranspose2d):
     def _native(self, x: Tensor) -> bool:
         k, s = _int_pair(self.kernel_size), _int_pair(self.stride)
         return (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[0] > 0 and self.groups == 1
-                and k is not None and k == s and 1 <= s <= 4 and _int_pair(self.padding) == 0
+                and k is not None and k == s and 1 <= s <= 8 and _int_pair(self.padding) == 0
                 and _int_pair(self.output_padding) == 0 and tuple(self.dilation) == (1, 1) and self.weight.dtype == torch.float32)
 
     def forward(self, input: Tensor, output_size=None) -> Tensor:

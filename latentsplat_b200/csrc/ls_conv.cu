@@ -116,30 +116,30 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     // Work iterator.  MODE_F: whole tiles, item = blockIdx.x + i*gridDim.x (n-tile fastest so that concurrently running CTAs
-    // share the A panel).  MODE_W (stream-K): the tiles' K loops are laid end to end (tile-major) and cut into gridDim.x equal
-    // runs of K blocks, so every CTA does the same amount of tensor work whatever the tile count; a run may end inside one tile
-    // and continue in the next -- each piece is accumulated separately and leaves through red.global.add.
-    const long long w_total = (long long)p.tiles_m * p.tiles_n * p.nkb_total;
-    const long long w_per = (w_total + gridDim.x - 1) / gridDim.x;
-    const long long w_begin = MODE == MODE_W ? (long long)blockIdx.x * w_per : (long long)blockIdx.x;
-    const long long w_end = MODE == MODE_W ? min(w_total, w_begin + w_per) : (long long)n_items;
+    // share the A panel).  MODE_W: the pixel (K) loop is cut into chunks of kb_per_split K blocks and an item is
+    // (chunk, tile) with the TILE index fastest: the CTAs running at any moment work on the same few pixel chunks for
+    // different filter taps / channel tiles, so the two activation tensors are read from DRAM once and from L2 otherwise
+    // (a tile-major split re-read them once per tile: ncu 1.3 GB of DRAM reads for 268 MB of operands); items are equal-sized
+    // and many (host: >= 8 per CTA), every item leaves through red.global.add.
+    const long long w_tiles = (long long)p.tiles_m * p.tiles_n;
+    const long long w_end = MODE == MODE_W ? w_tiles * p.splits : (long long)n_items;
+    const long long w_begin = blockIdx.x;
     auto next_work = [&](long long& cur, int& tile_m, int& tile_n, int& kb0, int& nkb) -> bool {
         if (cur >= w_end) return false;
         if constexpr (MODE == MODE_W) {
-            const int tile = (int)(cur / p.nkb_total);
-            kb0 = (int)(cur - (long long)tile * p.nkb_total);
-            nkb = (int)min((long long)(p.nkb_total - kb0), w_end - cur);
+            const int chunk = (int)(cur / w_tiles), tile = (int)(cur - (long long)chunk * w_tiles);
+            kb0 = chunk * p.kb_per_split;
+            nkb = min(p.nkb_total - kb0, p.kb_per_split);
             tile_n = tile % p.tiles_n;
             tile_m = tile / p.tiles_n;
-            cur += nkb;
         } else {
             const int item = (int)cur;
             tile_n = item % p.tiles_n;
             tile_m = item / p.tiles_n;
             kb0 = 0;
             nkb = p.nkb_total;
-            cur += gridDim.x;
         }
+        cur += gridDim.x;
         return true;
     };
     // F: M tile -> image and first pixel of the iteration grid
@@ -375,8 +375,10 @@ k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // =================================================================================================================
 constexpr int smem_bytes_t(int stages, int bn) { return stages * (A_BYTES + bn * BK * 4) + 1024 + 256; }
 
+constexpr int kThreadsT = 384;      // warps 0-3: TMA producer, MMA issuer, TMEM allocator, (idle); warps 4-11: epilogue
+
 template <bool AMN, int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsT, 1)
 k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
          const __grid_constant__ ConvParams p) {
     constexpr int B_BYTES = BN * BK * 4;
@@ -400,7 +402,7 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -478,37 +480,54 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             tc_commit(tfull0 + 8 * acc);
         }
     } else if (warp >= 4) {
-        // ------------------------------ epilogue ----------------------------------
-        const int q = warp - 4;                  // TMEM lane quarter == warp % 4
+        // ------------------------------ epilogue (8 warps) ------------------------
+        // warp w reads TMEM lanes (w % 4) * 32 .. +31 (its output channels); warps 4-7 take the even 32-pixel column chunks,
+        // warps 8-11 the odd ones.  A chunk is 32 consecutive pixels of ONE grid row (the host guarantees BW >= 32), so
+        // the output address is base + j * step with a warp-uniform base: per value one compare, one add, one store.
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        constexpr int kChunks = BN / 64;                            // chunks per warp
         uint32_t local = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
             int tile_m, n, y0, x0;
             decode(item, tile_m, n, y0, x0);
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
             const int co = tile_m * BM + q * 32 + lane;             // this lane's output channel
+            const bool live = tile_m * BM + q * 32 < p.n_out;       // warp-uniform: the warp owns live channels
             const bool co_ok = co < p.n_out;
             const float bias = (p.bias != nullptr && co_ok) ? p.bias[co] : 0.f;
-            float* __restrict__ out = p.out + (long long)n * p.o_sn + co;
-            float* __restrict__ pre = p.pre_out ? p.pre_out + (long long)n * p.o_sn + co : nullptr;
+            const long long img = (long long)n * p.o_sn + co;
+            const long long step = (long long)p.oxs * p.o_sw;
             mbar_wait(tfull0 + 8 * acc, acc_ph);
             tc_fence_after();
-            if (tile_m * BM + q * 32 < p.n_out) {                   // warp-uniform: this warp owns live channels
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    const int iy0 = y0 + (c0 >> p.bw_log2);
-                    if (iy0 >= p.P) break;                           // the remaining pixel rows of the box lie outside the grid
-                    uint32_t r[32];
-                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+            if (live) {
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+                uint32_t ra[32], rb[32];
+                tc_ld32_nowait(t0 + (uint32_t)(half * 32), ra);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int pix = c0 + j;
-                        const int iy = y0 + (pix >> p.bw_log2), ix = x0 + (pix & ((1 << p.bw_log2) - 1));
-                        if (iy < p.P && ix < p.Q && co_ok) {
-                            const long long off = (long long)(iy * p.oys + p.oyo) * p.o_sh + (long long)(ix * p.oxs + p.oxo) * p.o_sw;
-                            const float v = __uint_as_float(r[j]) + bias;
-                            out[off] = apply_act(v, p.act);
-                            if (pre) pre[off] = v;
-                        }
+                for (int c = 0; c < kChunks; ++c) {
+                    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+                    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+                    tc_wait_ld();
+                    if (c + 1 < kChunks) tc_ld32_nowait(t0 + (uint32_t)((2 * (c + 1) + half) * 32), nxt);   // overlaps the stores below
+                    const int c0 = (2 * c + half) * 32;
+                    const int iy = y0 + (c0 >> p.bw_log2), ix0 = x0 + (c0 & ((1 << p.bw_log2) - 1));
+                    int nvalid = (iy < p.P && co_ok) ? p.Q - ix0 : 0;                  // pixels of this chunk inside the grid
+                    nvalid = nvalid > 32 ? 32 : nvalid;
+                    const long long off = img + (long long)(iy * p.oys + p.oyo) * p.o_sh + (long long)(ix0 * p.oxs + p.oxo) * p.o_sw;
+                    float* __restrict__ o = p.out + off;
+                    if (p.act == LS_ACT_NONE && p.pre_out == nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) o[j * step] = __uint_as_float(cur[j]) + bias;
+                    } else {
+                        float* __restrict__ pr = p.pre_out ? p.pre_out + off : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) {
+                                const float v = __uint_as_float(cur[j]) + bias;
+                                o[j * step] = apply_act(v, p.act);
+                                if (pr) pr[j * step] = v;
+                            }
                     }
                 }
             }
@@ -607,13 +626,8 @@ int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, 
     const long long n_items = (long long)p.tiles_m * p.tiles_n;
     if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
     const int num_sms = current_sm_count();
-    int ctas;
-    if (MODE == MODE_W) {                       // stream-K: every CTA gets an equal run of K blocks (at least 8)
-        const long long runs = n_items * p.nkb_total / 8;
-        ctas = runs < num_sms ? (runs < 1 ? 1 : (int)runs) : num_sms;
-    } else {
-        ctas = n_items < num_sms ? (int)n_items : num_sms;
-    }
+    const long long total = n_items * (MODE == MODE_W ? p.splits : 1);
+    const int ctas = total < num_sms ? (int)total : num_sms;
     k_conv_tf32<MODE, BMN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, p);
     return ls_check_cuda("k_conv_tf32");
 }
@@ -691,7 +705,7 @@ int launch_t_s(const CUtensorMap& mw, const CUtensorMap& mx, const ConvParams& p
     if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
     const int num_sms = current_sm_count();
     const int ctas = n_items < num_sms ? (int)n_items : num_sms;
-    k_conv_t<AMN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(mw, mx, p);
+    k_conv_t<AMN, BN, STAGES><<<ctas, kThreadsT, smem, stream>>>(mw, mx, p);
     return ls_check_cuda("k_conv_t");
 }
 
@@ -710,6 +724,7 @@ int run_t(const FProblem& f, cudaStream_t stream) {
     int bw = pow2_ceil_log2(f.Q);
     const int bn_log2 = BN == 256 ? 8 : 7;
     if (bw > bn_log2) bw = bn_log2;
+    if (bw < 5) bw = 5;                                      // the epilogue's 32-pixel chunks must not straddle grid rows
     while ((1 << bw) * f.sx > 256) --bw;
     while ((BN >> bw) * f.sy > 256) ++bw;
     if ((1 << bw) * f.sx > 256) return ls_fail("conv: no TMA box for a %d-pixel tile at stride %d", BN, f.sx);
@@ -775,15 +790,23 @@ int run_w(const WOperand& A, const WOperand& B, int P, int Q, float* out, long l
     const int BN = pick_bn(N);
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
-    p.splits = 1;                                   // stream-K inside the kernel: the grid cuts the concatenated K loops evenly
-    p.kb_per_split = p.nkb_total;
+    // pixel chunks: equal K-block counts, >= 32 K blocks each (amortises the red.add epilogue), ~8 items per CTA
+    {
+        const long long tiles = (long long)p.tiles_m * p.tiles_n;
+        long long want = (8ll * current_sm_count() + tiles - 1) / tiles;       // chunks wanted
+        const long long max_chunks = p.nkb_total / 32 > 0 ? p.nkb_total / 32 : 1;
+        if (want > max_chunks) want = max_chunks;
+        if (want < 1) want = 1;
+        p.kb_per_split = (int)((p.nkb_total + want - 1) / want);
+        p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;
+    }
     p.a = ActOp{A.taps > 1 ? cpa : (1 << 30), A.S, A.sx, A.sy, A.dx0, A.dy0, 1, 1};
     p.b = ActOp{B.taps > 1 ? cpb : (1 << 30), B.S, B.sx, B.sy, B.dx0, B.dy0, 1, 1};
     p.cp_r = A.taps > 1 ? cpa : (1 << 30); p.c_r = A.C; p.t_r = A.taps;
     p.cp_c = B.taps > 1 ? cpb : (1 << 30); p.c_c = B.C; p.t_c = B.taps;
     p.rs = rs; p.cs = cs;
     p.out = out;
-    p.atomic = 1;                                   // pieces of one tile come from several CTAs; dw is zero-filled by the caller
+    p.atomic = p.splits > 1 ? 1 : 0;                // chunks of one tile come from several CTAs; dw is zero-filled by the caller
     p.vec_ok = (cs == 1 && rs % 4 == 0 && B.C % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     if (p.nkb_total <= 0) return ls_fail("conv wgrad: empty problem");
     CUtensorMap ma, mb;
@@ -798,7 +821,7 @@ int validate(const LsConv2d* c) {
     if (c->N <= 0 || c->H <= 0 || c->W <= 0 || c->Cin <= 0 || c->Cout <= 0 || c->R <= 0 || c->S <= 0)
         return ls_fail("conv: bad sizes N=%d H=%d W=%d Cin=%d Cout=%d R=%d S=%d", c->N, c->H, c->W, c->Cin, c->Cout, c->R, c->S);
     if (c->Cin % 4 || c->Cout % 4) return ls_fail("conv: Cin (%d) and Cout (%d) must be multiples of 4 (pad the channels)", c->Cin, c->Cout);
-    if (c->stride < 1 || c->stride > 4) return ls_fail("conv: stride %d not in 1..4", c->stride);
+    if (c->stride < 1 || c->stride > 8) return ls_fail("conv: stride %d not in 1..8 (TMA element-stride limit)", c->stride);
     if (c->pad < 0) return ls_fail("conv: negative padding");
     if (c->transposed && (c->R != c->stride || c->S != c->stride || c->pad != 0))
         return ls_fail("conv: transposed convolutions are supported for kernel == stride, pad == 0 only");

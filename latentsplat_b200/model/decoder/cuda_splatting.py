@@ -134,8 +134,34 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
                                      gaussian_means, gaussian_covariances, gaussian_opacities,
                                      gaussian_color_sh_coefficients, gaussian_feature_sh_coefficients,
                                      scale_invariant, use_sh)
+    if PER_VIEW_LOOP:
+        return _render_per_view(args, kwargs, views_per_scene)
     color, feature, alpha, depth, _ = rasterize_views(*args, debug=debug, capacity=capacity, **kwargs)
     return RenderOutput(color, feature, alpha, depth)
+
+
+PER_VIEW_LOOP = False     # bench.py's GPU comparator: call the rasterizer once per view, like the reference's host loop
+
+_PER_VIEW_KEYS = ("viewmatrix", "projmatrix", "campos", "tanfov", "bg", "scene_scale")
+
+
+def _render_per_view(args, kwargs, views_per_scene: int) -> RenderOutput:
+    """The reference's call structure (cuda_splatting.py:124-166): one rasterizer invocation per view with exact key-list
+    sizing (one host sync each), outputs stacked afterwards.  Only used as the measured baseline of bench.py."""
+    n_views = kwargs["viewmatrix"].shape[0]
+    outs = []
+    for i in range(n_views):
+        s = i // views_per_scene
+        a = tuple(t[s:s + 1] for t in args)
+        kw = {}
+        for k, v in kwargs.items():
+            if isinstance(v, Tensor):
+                kw[k] = v[i:i + 1] if k in _PER_VIEW_KEYS else v[s:s + 1]
+            else:
+                kw[k] = v
+        outs.append(rasterize_views(*a, **kw))
+    cat = lambda j: None if outs[0][j] is None else torch.cat([o[j] for o in outs])
+    return RenderOutput(cat(0), cat(1), cat(2), cat(3))
 
 
 def prepare_render_call(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,

@@ -36,6 +36,7 @@ CONV_CASES = [
     (2, 32, 64, 64, 32, 4, 4, 0),        # down-scaler 4x4 stride 4
     (2, 40, 8, 8, 72, 1, 1, 0),          # 1x1 shortcut, channel tails
     (1, 8, 256, 256, 16, 3, 1, 1),       # full-width rows (BW = 128)
+    (2, 4, 64, 64, 96, 8, 8, 0),         # DINO patch embedding: 8x8 stride 8 on a (padded) RGB image
 ]
 
 
