@@ -10,7 +10,7 @@
  * operands read straight from HBM by TMA (no cast passes), fp32 accumulation in TMEM, and bias /
  * activation fused into the epilogue.
  *
- *   C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]) -> act
+ *   C[M,N] (+)= act(A[M,K] * B[N,K]^T (+ bias[N])) (+ residual[M,N])
  *
  * Either operand may be K-major (row-major [rows][K], e.g. activations X and weights W in Y = X W^T)
  * or MN-major (stored [K][rows]; e.g. W in dX = dY W, and both dY and X in dW = dY^T X), so forward,
@@ -47,6 +47,10 @@ typedef struct LsGemmArgs {
     const float* B;
     float* C;            /* [M][ldc] row-major fp32                                               */
     const float* bias;   /* (N) or NULL                                                           */
+    const float* residual; /* [M][ldr] or NULL: C = act(A B^T + bias) + residual -- the skip connection of a
+                              transformer block (x + proj(...), x + fc2(...)) in the epilogue; not with split-K  */
+    int64_t ldr;
+    float* pre_out;      /* [M][ldc] or NULL: the pre-activation A B^T + bias, kept for the backward of GELU     */
 } LsGemmArgs;
 
 LS_API int ls_gemm_tf32(const LsGemmArgs* args, void* stream /* cudaStream_t */);

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define LS_RASTER_ABI_VERSION 1
+#define LS_RASTER_ABI_VERSION 2
 #if defined(__GNUC__)
 #define LS_API __attribute__((visibility("default")))
 #else
@@ -111,6 +111,13 @@ typedef struct LsRasterState {
     int32_t   chan_stride;   /* floats per chan record = round_up(max(1, ncolor + C), 4)     */
     int32_t   sort_smem_keys;/* keys of one tile held in shared memory by the per-tile sort
                                 (0 = default 4096); longer tiles sort through keys_tmp       */
+    /* The per-tile Gaussian QUEUES in list order, written by the sort stage (a permute-after-sort): the blend
+     * kernels stage them with 1-D bulk TMA copies (cp.async.bulk + mbarrier) instead of per-thread gathers.    */
+    float*    sorted_cull;   /* (capacity, 4): x, y, fp16x2 half-extents, Gaussian id (bit pattern) -- what the
+                                per-warp compaction pass reads, 16 B per entry, bank-conflict free              */
+    float*    sorted_rec;    /* (capacity, rec_stride): the 8-float geometry record followed by the chan record */
+    int32_t   rec_stride;    /* 8 + chan_stride                                                                 */
+    int32_t   reserved1;
 } LsRasterState;
 
 typedef struct LsRasterImages {
@@ -138,12 +145,18 @@ typedef struct LsRasterGrads {
     float* dL_dcolor_in;      /* PRECOMP: (S,G,3); SH: (S,G,(deg+1)^2,3); NULL if none       */
     float* dL_dfeature_in;    /* PRECOMP: (S,G,C); SH: (S,G,C,(fdeg+1)^2); NULL if none      */
     float* dL_dmeans2D;       /* (V,G,3) screen-space sink (z = 0), per view; may be NULL    */
+    /* Row pitch (floats) of dL_dcolor_in / dL_dfeature_in, 0 = dense.  The SH coefficient rows are 75 / 36 floats (300 / 144
+     * B): written densely, their 60-B chunks straddle 32-B sectors and L2 read-modify-writes them (ncu r01: 2.1x the
+     * algorithmic DRAM traffic).  A pitch that is a multiple of 8 floats makes every chunk whole sectors; the caller hands the
+     * [:, :row] view of the padded buffer to autograd.                                                                        */
+    int32_t color_grad_pitch, feature_grad_pitch;
 } LsRasterGrads;
 
 /* Buffer sizes (in elements) for a given problem; `out` is a host pointer. */
 typedef struct LsRasterSizes {
     int64_t n_scenes, tiles_per_view, geom, chan, per_view_gaussian, tile_slots, pixels, grad_record;
     int32_t chan_stride, grad_stride, n_color, n_value_channels;
+    int32_t rec_stride, reserved0;
 } LsRasterSizes;
 
 LS_API int ls_raster_sizes(const LsRasterScene* scene, LsRasterSizes* out /* host */);

@@ -31,6 +31,7 @@ class LsRasterState(C.Structure):
         ("clamped", C.c_void_p), ("tile_count", C.c_void_p), ("tile_offsets", C.c_void_p), ("stats", C.c_void_p),
         ("keys", C.c_void_p), ("keys_tmp", C.c_void_p), ("capacity", C.c_int64), ("final_T", C.c_void_p),
         ("n_contrib", C.c_void_p), ("chan_stride", C.c_int32), ("sort_smem_keys", C.c_int32),
+        ("sorted_cull", C.c_void_p), ("sorted_rec", C.c_void_p), ("rec_stride", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -44,6 +45,7 @@ class LsRasterGrads(C.Structure):
         ("dL_drecord", C.c_void_p), ("grad_stride", C.c_int32), ("reserved0", C.c_int32),
         ("dL_dmeans3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dopacity", C.c_void_p),
         ("dL_dcolor_in", C.c_void_p), ("dL_dfeature_in", C.c_void_p), ("dL_dmeans2D", C.c_void_p),
+        ("color_grad_pitch", C.c_int32), ("feature_grad_pitch", C.c_int32),
     ]
 
 
@@ -52,7 +54,7 @@ class LsRasterSizes(C.Structure):
         ("n_scenes", C.c_int64), ("tiles_per_view", C.c_int64), ("geom", C.c_int64), ("chan", C.c_int64),
         ("per_view_gaussian", C.c_int64), ("tile_slots", C.c_int64), ("pixels", C.c_int64),
         ("grad_record", C.c_int64), ("chan_stride", C.c_int32), ("grad_stride", C.c_int32),
-        ("n_color", C.c_int32), ("n_value_channels", C.c_int32),
+        ("n_color", C.c_int32), ("n_value_channels", C.c_int32), ("rec_stride", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -62,6 +64,7 @@ class LsGemmArgs(C.Structure):
         ("act", C.c_int32), ("split_k", C.c_int32), ("accumulate", C.c_int32),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
         ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64), ("pre_out", C.c_void_p),
     ]
 
 
@@ -84,7 +87,7 @@ COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
 STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15
 BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
            "ls_absorbed_attention_forward", "ls_absorbed_attention_backward",

@@ -180,6 +180,35 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- mbarrier + 1-D bulk TMA copies (cp.async.bulk): staging of the sorted per-tile queues ----------------------------
+constexpr int kBatch = 256;                         // queue entries staged per round by the blend kernels
+// shared memory of a blend kernel: 2 x kBatch records of `rv` float4 + 2 x kBatch cull records + 8 per-warp survivor lists
+__host__ __device__ constexpr int blend_smem_bytes(int rv) { return 2 * kBatch * rv * 16 + 2 * kBatch * 16 + 8 * kBatch; }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();           // a protocol bug must fail loudly, never hang the device
+    }
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // ---- warp-cooperative staging of per-Gaussian coefficient rows ---------------------------------------------------
 // A thread per Gaussian reading its own 300-B SH row makes every warp-level load touch 32 different sectors for 128
 // useful bytes (the preprocess kernels then sit at 12-35 % of HBM bandwidth, L2->L1 sector traffic bound).  Instead the

@@ -1,21 +1,30 @@
 // ls_conv.cu -- implicit-GEMM convolutions for sm_100a on the tcgen05 pipeline of ls_gemm.cu (include/ls_conv.h).
 //
 // Activations are NHWC, so for one filter tap (r, s) the im2col matrix of a convolution is simply the activation tensor
-// shifted by (r - pad, s - pad): a 4-D TMA box {32 channels, BW pixels, BH rows, 1 image} of it IS a 128 x 32 K-major
-// GEMM operand tile, with TMA's out-of-bounds zero fill playing the padding and its element strides playing the
-// convolution stride.  Nothing is unfolded or transposed in memory.  Two kernel modes share one warp-specialised
-// pipeline (TMA producer lane / MMA issuer lane / TMEM allocator warp / 4 epilogue warps, persistent over a work list):
+// shifted by (r - pad, s - pad): a 4-D TMA box {32 channels, BW pixels, BH rows, 1 image} of it IS a K-major GEMM operand
+// tile, with TMA's out-of-bounds zero fill playing the padding and its element strides playing the convolution stride.
+// Nothing is unfolded or transposed in memory.  Two kernels share one warp-specialised pipeline (TMA producer lane / MMA
+// issuer lane / TMEM allocator warp / epilogue warps, persistent over a work list); both exist for cta_group::1 and for
+// cta_group::2 (a cluster of two CTAs on one TPC computes a 256-row tile; each CTA stages its own 128 rows of A and HALF of
+// B, which cuts the L2 -> shared-memory traffic per flop by a third -- with fp32 operands that traffic, ~61 B/clk/SM measured,
+// is what bounds the 1-CTA kernels at ~70 % of the tensor pipe):
 //
-//   MODE_F  out[n, iy, ix, :] = act(bias + sum_taps in[n, iy*sy + dy(r), ix*sx + dx(s), :] * Wtap)        (pixels x Cout)
-//           A = activation boxes (K-major), B = weights [rows][taps*channels] read K-major (forward; transposed-conv
-//           dgrad) or MN-major (dgrad: dX = dY * W without a transposed weight copy; transposed-conv forward); the
-//           epilogue maps tile rows back to output pixels (with an output stride/offset for the stride classes of a
-//           strided dgrad and for the transposed convolution) and fuses bias + ReLU / GELU / SiLU / LeakyReLU, optionally
-//           storing the pre-activation for the backward pass.
-//   MODE_W  dW[m, n] = sum_pixels P[pixel, m] * Q[pixel + tap(n), n]                                       (weight gradient)
-//           both operands are activation tensors read MN-major in 32-pixel K blocks (SWIZZLE_128B with 32-B atoms, the
-//           only MN-major layout tcgen05 takes for 32-bit operands); each 32-channel box of an operand carries its own
-//           filter tap, so one tile may span several taps; split over the pixel dimension, combined with red.global.add.
+//   k_conv_t  D[channel, pixel] = sum_taps sum_k W[channel, tap, k] * X[pixel + tap, k]          (forward, dgrad, transposed conv)
+//             A = 128 (x2) output channels of the weight matrix (K-major box, or MN-major boxes for dgrad / transposed-conv
+//             forward: dX = dY * W without a transposed weight copy), B = 256 pixels of the activation tensor in ONE 4-D TMA
+//             box per K block.  The accumulator arrives with one output channel per TMEM lane, so a warp's tcgen05.ld hands
+//             lane l the values of channel c0+l for 32 consecutive pixels and every store instruction writes 32 consecutive
+//             channels of one NHWC pixel (128 contiguous bytes): no shared-memory transpose; bias + ReLU / GELU / SiLU /
+//             LeakyReLU fused, optionally storing the pre-activation for the backward pass; an output stride/offset serves the
+//             stride classes of a strided dgrad and the transposed convolution.
+//   k_conv_w  dW[m, n] = sum_pixels P[pixel + tap(m), m] * Q[pixel + tap(n), n]                   (weight gradient)
+//             both operands are activation tensors read MN-major in 64-pixel K blocks (SWIZZLE_128B with 32-B atoms, the only
+//             MN-major layout tcgen05 takes for 32-bit operands); each 32-channel box of an operand carries its own filter tap,
+//             so one tile may span several taps.  The pixel loop is cut into chunks and an item is (chunk, tile) with the tile
+//             index fastest: the CTAs running at any moment work on the same few pixel chunks, so both activation tensors are
+//             read from DRAM once (a tile-major split re-read them once per tile: 1.3 GB for 268 MB of operands in ncu);
+//             items leave through red.global.add.v4.  64-pixel K blocks halve the number of 4-D boxes per byte (ncu: the 12
+//             boxes of a 32-pixel block cost ~40 cycles each in the TMA unit on top of the data time).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,18 +38,16 @@ namespace lsc {
 using namespace lstc;
 
 constexpr int BM = 128, BK = 32, UMMA_K = 8;
+constexpr int BKW = 64;                                     // K block (pixels) of the weight-gradient kernel
 constexpr int A_BYTES = BM * BK * 4;
-constexpr int kThreads = 256;
 constexpr int PITCH = 36;                                   // floats; 144-B rows: conflict-free float4 access
 constexpr int PATCH_BYTES = 4 * 32 * PITCH * 4;
-constexpr int smem_bytes(int stages, int bn) { return stages * (A_BYTES + bn * BK * 4) + PATCH_BYTES + 1024 + 256; }
-
-enum { MODE_F = 0, MODE_W = 1 };
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;              // shared::cluster address of the even (leader) CTA's copy
 
 // how the 32-channel boxes of an activation operand map to TMA coordinates
 struct ActOp {
-    int cp;            // MODE_W: MN-index pitch of one filter tap (multiple of 32); one tap only: >= the MN extent
-    int S;             // MODE_W: taps per filter row
+    int cp;            // k_conv_w: MN-index pitch of one filter tap (multiple of 32); one tap only: >= the MN extent
+    int S;             // k_conv_w: taps per filter row
     int sx, sy;        // coordinate multipliers (convolution stride) applied to the iteration-grid position
     int dx0, dy0;      // offset of tap (0, 0)
     int dxs, dys;      // offset step per tap (+1 forward, -1 flipped for dgrad)
@@ -48,14 +55,15 @@ struct ActOp {
 
 struct ConvParams {
     int P, Q, n_img;          // iteration grid (rows, columns) per image, images
-    int bw_log2;              // F: tile = (1 << bw_log2) x (128 >> bw_log2) pixels;  W: K block = (1 << bw_log2) x (32 >> bw_log2)
-    int tiles_x, tiles_y;     // F: M tiles per image;  W: K blocks per image
+    int bw_log2;              // T: one CTA's pixel box = (1 << bw_log2) x (NSUB >> bw_log2);  W: K block = (1 << bw_log2) x (64 >> bw_log2)
+    int sub_dx, sub_dy;       // T, cta_group::2: pixel offset of the second CTA's box inside the pair's tile
+    int tiles_x, tiles_y;     // T: pixel tiles per image;  W: K blocks per image
     int tiles_m, tiles_n, splits, kb_per_split, nkb_total;
-    int R, S, chunks;         // F: taps iterated and 32-channel chunks per tap
+    int R, S, chunks;         // T: taps iterated and 32-channel chunks per tap
     ActOp a, b;
-    int wp, wr0, wrs, ws0, wss, wS;   // F: weight k/column offset of tap (r, s) = wp * ((wr0 + r*wrs) * wS + ws0 + s*wss)
-    long long o_sn, o_sh, o_sw;       // F: output element strides (image, row, pixel)
-    int oys, oyo, oxs, oxo;           // F: output pixel = (iy*oys + oyo, ix*oxs + oxo)
+    int wp, wr0, wrs, ws0, wss, wS;   // T: weight k/column offset of tap (r, s) = wp * ((wr0 + r*wrs) * wS + ws0 + s*wss)
+    long long o_sn, o_sh, o_sw;       // T: output element strides (image, row, pixel)
+    int oys, oyo, oxs, oxo;           // T: output pixel = (iy*oys + oyo, ix*oxs + oxo)
     int n_out, act, vec_ok;
     float* out;
     float* pre_out;
@@ -75,322 +83,108 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
-template <int MODE, bool BMN, int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
-k_conv_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-            const __grid_constant__ ConvParams p) {
-    constexpr bool A_MN = MODE == MODE_W;
-    constexpr bool B_MN = MODE == MODE_W || BMN;
-    constexpr int B_BYTES = BN * BK * 4;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;        // 64 / 256 / 512: powers of two >= 32
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PATCH_BYTES);    // full[S] empty[S] tfull[2] tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.tiles_m * p.tiles_n * p.splits;
-
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
-    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+// ---- cta_group-dependent PTX (CG = 1: one CTA; CG = 2: a CTA pair, protocol of ls_gemm.cu's k_gemm_tf32_2cta) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void cg_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if constexpr (CG == 1) {
+        tma_load_2d(dst, map, bar, c0, c1);
+    } else {        // signals the LEADER's barrier (peer bit cleared)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void cg_tma_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    if constexpr (CG == 1) {
+        tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void cg_commit(uint32_t bar) {
+    if constexpr (CG == 1) {
+        tc_commit(bar);
+    } else {        // arrives on the barrier at this offset in BOTH CTAs
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void cg_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void cg_arrive_leader(uint32_t bar) {      // accumulator-drained signal to the MMA issuer
+    if constexpr (CG == 1) {
+        mbar_arrive(bar);
+    } else {
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void cg_tmem_alloc(uint32_t slot, uint32_t cols) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-
-    // Work iterator.  MODE_F: whole tiles, item = blockIdx.x + i*gridDim.x (n-tile fastest so that concurrently running CTAs
-    // share the A panel).  MODE_W: the pixel (K) loop is cut into chunks of kb_per_split K blocks and an item is
-    // (chunk, tile) with the TILE index fastest: the CTAs running at any moment work on the same few pixel chunks for
-    // different filter taps / channel tiles, so the two activation tensors are read from DRAM once and from L2 otherwise
-    // (a tile-major split re-read them once per tile: ncu 1.3 GB of DRAM reads for 268 MB of operands); items are equal-sized
-    // and many (host: >= 8 per CTA), every item leaves through red.global.add.
-    const long long w_tiles = (long long)p.tiles_m * p.tiles_n;
-    const long long w_end = MODE == MODE_W ? w_tiles * p.splits : (long long)n_items;
-    const long long w_begin = blockIdx.x;
-    auto next_work = [&](long long& cur, int& tile_m, int& tile_n, int& kb0, int& nkb) -> bool {
-        if (cur >= w_end) return false;
-        if constexpr (MODE == MODE_W) {
-            const int chunk = (int)(cur / w_tiles), tile = (int)(cur - (long long)chunk * w_tiles);
-            kb0 = chunk * p.kb_per_split;
-            nkb = min(p.nkb_total - kb0, p.kb_per_split);
-            tile_n = tile % p.tiles_n;
-            tile_m = tile / p.tiles_n;
-        } else {
-            const int item = (int)cur;
-            tile_n = item % p.tiles_n;
-            tile_m = item / p.tiles_n;
-            kb0 = 0;
-            nkb = p.nkb_total;
-        }
-        cur += gridDim.x;
-        return true;
-    };
-    // F: M tile -> image and first pixel of the iteration grid
-    auto tile_origin = [&](int tile_m, int& n, int& y0, int& x0) {
-        const int tx = tile_m % p.tiles_x;
-        const int t = tile_m / p.tiles_x;
-        n = t / p.tiles_y;
-        y0 = (t - n * p.tiles_y) * (BM >> p.bw_log2);
-        x0 = tx << p.bw_log2;
-    };
-
-    if (warp == 0 && lane == 0) {
-        // ------------------------------ TMA producer ------------------------------
-        uint32_t it = 0;
-        long long cur = w_begin;
-        int tile_m, tile_n, kb0, nkb;
-        while (next_work(cur, tile_m, tile_n, kb0, nkb)) {
-            if constexpr (MODE == MODE_F) {
-                int n, y0, x0;
-                tile_origin(tile_m, n, y0, x0);
-                const int n0 = tile_n * BN;
-                for (int r = 0; r < p.R; ++r) {
-                    const int ay = y0 * p.a.sy + p.a.dy0 + r * p.a.dys;
-                    for (int s = 0; s < p.S; ++s) {
-                        const int ax = x0 * p.a.sx + p.a.dx0 + s * p.a.dxs;
-                        const int wk = p.wp * ((p.wr0 + r * p.wrs) * p.wS + p.ws0 + s * p.wss);
-                        for (int ch = 0; ch < p.chunks; ++ch, ++it) {
-                            const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
-                            mbar_wait(empty0 + 8 * st, ph ^ 1);
-                            mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
-                            const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                            tma_load_4d(a_dst, &map_a, full0 + 8 * st, ch * BK, ax, ay, n);
-                            if (!B_MN) {
-                                tma_load_2d(b_dst, &map_b, full0 + 8 * st, wk + ch * BK, n0);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < BN / 32; ++j)
-                                    tma_load_2d(b_dst + j * 4096, &map_b, full0 + 8 * st, wk + n0 + 32 * j, ch * BK);
-                            }
-                        }
-                    }
-                }
-            } else {
-                // per 32-channel box: channel offset and tap shift (constant over the K loop)
-                int ac[BM / 32], ax[BM / 32], ay[BM / 32], bc[BN / 32], bx[BN / 32], by[BN / 32];
-#pragma unroll
-                for (int j = 0; j < BM / 32; ++j) {
-                    const int m = tile_m * BM + 32 * j, tap = m / p.a.cp, r = tap / p.a.S, s = tap - r * p.a.S;
-                    ac[j] = m - tap * p.a.cp; ax[j] = p.a.dx0 + s * p.a.dxs; ay[j] = p.a.dy0 + r * p.a.dys;
-                }
-#pragma unroll
-                for (int j = 0; j < BN / 32; ++j) {
-                    const int m = tile_n * BN + 32 * j, tap = m / p.b.cp, r = tap / p.b.S, s = tap - r * p.b.S;
-                    bc[j] = m - tap * p.b.cp; bx[j] = p.b.dx0 + s * p.b.dxs; by[j] = p.b.dy0 + r * p.b.dys;
-                }
-                const int kw_log2 = p.bw_log2, kh = 32 >> kw_log2;
-                int xb = kb0 % p.tiles_x, t = kb0 / p.tiles_x;
-                int n = t / p.tiles_y, yb = t - n * p.tiles_y;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(empty0 + 8 * st, ph ^ 1);
-                    mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
-                    const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                    const int x0 = xb << kw_log2, y0 = yb * kh;
-#pragma unroll
-                    for (int j = 0; j < BM / 32; ++j)
-                        tma_load_4d(a_dst + j * 4096, &map_a, full0 + 8 * st, ac[j], x0 * p.a.sx + ax[j], y0 * p.a.sy + ay[j], n);
-#pragma unroll
-                    for (int j = 0; j < BN / 32; ++j)
-                        tma_load_4d(b_dst + j * 4096, &map_b, full0 + 8 * st, bc[j], x0 * p.b.sx + bx[j], y0 * p.b.sy + by[j], n);
-                    if (++xb == p.tiles_x) { xb = 0; if (++yb == p.tiles_y) { yb = 0; ++n; } }
-                }
-            }
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------ MMA issuer --------------------------------
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        uint32_t it = 0, local = 0;
-        long long cur = w_begin;
-        int tile_m, tile_n, kb0, nkb;
-        for (; next_work(cur, tile_m, tile_n, kb0, nkb); ++local) {
-            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
-            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * BN;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(full0 + 8 * st, ph);
-                tc_fence_after();
-                const uint32_t a_src = smem_base + st * STAGE_BYTES, b_src = a_src + A_BYTES;
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t adesc = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
-                    const uint64_t bdesc = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
-                    tc_mma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-                }
-                tc_commit(empty0 + 8 * st);
-            }
-            tc_commit(tfull0 + 8 * acc);
-        }
-    } else if (warp >= 4) {
-        // ------------------------------ epilogue ----------------------------------
-        const int q = warp - 4;
-        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-        uint32_t local = 0;
-        long long cur = w_begin;
-        int tile_m, tile_n, kb0, nkb;
-        for (; next_work(cur, tile_m, tile_n, kb0, nkb); ++local) {
-            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
-            mbar_wait(tfull0 + 8 * acc, acc_ph);
-            tc_fence_after();
-
-            // rows of this warp: 8 per lane (4*i + sub_r), resolved to output offsets once per tile
-            long long row_off[8];
-            bool row_ok[8];
-            if constexpr (MODE == MODE_F) {
-                int n, y0, x0;
-                tile_origin(tile_m, n, y0, x0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = q * 32 + 4 * i + sub_r;
-                    const int iy = y0 + (row >> p.bw_log2), ix = x0 + (row & ((1 << p.bw_log2) - 1));
-                    row_ok[i] = iy < p.P && ix < p.Q;
-                    row_off[i] = (long long)n * p.o_sn + (long long)(iy * p.oys + p.oyo) * p.o_sh + (long long)(ix * p.oxs + p.oxo) * p.o_sw;
-                }
-            } else {
-                const int row0 = tile_m * BM + q * 32, tap = row0 / p.cp_r, ch0 = row0 - tap * p.cp_r;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int ch = ch0 + 4 * i + sub_r;
-                    row_ok[i] = tap < p.t_r && ch < p.c_r;
-                    row_off[i] = (long long)(tap * p.c_r + ch) * p.rs;
-                }
-            }
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int col0 = tile_n * BN + c0;
-                int ncols, tapc = 0, chc0 = col0;                       // valid columns of this 32-wide chunk, column remap
-                if constexpr (MODE == MODE_F) {
-                    if (col0 >= p.n_out) break;                          // warp-uniform
-                    ncols = p.n_out - col0;
-                } else {
-                    tapc = col0 / p.cp_c;
-                    chc0 = col0 - tapc * p.cp_c;
-                    if (tapc >= p.t_c) break;
-                    ncols = p.c_c - chc0;                                // may be <= 0: padded channels of this tap
-                }
-                if (ncols <= 0) continue;                                // warp-uniform
-                uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                __syncwarp();
-                float4 rows4[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
-                if constexpr (MODE == MODE_F) {
-                    const int col = col0 + sub_c;
-                    float b4[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (p.bias != nullptr) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) if (col + t < p.n_out) b4[t] = p.bias[col + t];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (!row_ok[i]) continue;
-                        const float4 v4 = rows4[i];
-                        const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
-                        float v[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) v[t] = apply_act(pre[t], p.act);
-                        float* dst = p.out + row_off[i] + col;
-                        if (p.vec_ok && col + 3 < p.n_out) {
-                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                            if (p.pre_out) *reinterpret_cast<float4*>(p.pre_out + row_off[i] + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-                                if (col + t < p.n_out) {
-                                    dst[t] = v[t];
-                                    if (p.pre_out) p.pre_out[row_off[i] + col + t] = pre[t];
-                                }
-                        }
-                    }
-                } else {
-                    const int ch = chc0 + sub_c;
-                    const long long col_off = (long long)(tapc * p.c_c + ch) * p.cs;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (!row_ok[i]) continue;
-                        const float4 v4 = rows4[i];
-                        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-                        float* dst = p.out + row_off[i] + col_off;
-                        if (p.vec_ok && ch + 3 < p.c_c) {
-                            if (p.atomic) red_add_v4(dst, v[0], v[1], v[2], v[3]);
-                            else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-                                if (ch + t < p.c_c) {
-                                    if (p.atomic) atomicAdd(dst + t * p.cs, v[t]); else dst[t * p.cs] = v[t];
-                                }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
+}
+template <int CG>
+__device__ __forceinline__ void cg_tmem_dealloc(uint32_t base, uint32_t cols) {
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void cg_sync() {        // all threads of the CTA (pair)
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
 }
 
 // =================================================================================================================
-// MODE_T: the transposed orientation of MODE_F,  D[channel, pixel] = sum_k W[channel, k] * X[pixel, k]:
-//   A = 128 output channels of the weight matrix (K-major box, or MN-major boxes for dgrad / transposed-conv forward)
-//   B = BN = 256 (or 128) pixels of the activation tensor: ONE 4-D TMA box {32 channels, BW, BH, 1} per K block
-// Every layer -- also the Cout = 128 ones, which as N = 128 tiles were shared-memory bound -- runs M128 x N256 MMAs
-// (12 KB of operands per 135 tensor cycles), and the accumulator arrives with one output channel per TMEM lane: a warp's
-// tcgen05.ld hands lane l the values of channel c0+l for 32 consecutive pixels, so each store instruction writes 32
-// consecutive channels of one NHWC pixel (128 contiguous bytes) -- no shared-memory transpose in the epilogue.
+// k_conv_t
 // =================================================================================================================
-constexpr int smem_bytes_t(int stages, int bn) { return stages * (A_BYTES + bn * BK * 4) + 1024 + 256; }
-
 constexpr int kThreadsT = 384;      // warps 0-3: TMA producer, MMA issuer, TMEM allocator, (idle); warps 4-11: epilogue
+constexpr int smem_bytes_t(int stages, int bn, int cg) { return stages * (A_BYTES + (bn / cg) * BK * 4) + 1024 + 256; }
 
-template <bool AMN, int BN, int STAGES>
+template <bool AMN, int BN, int STAGES, int CG>
 __global__ void __launch_bounds__(kThreadsT, 1)
 k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
          const __grid_constant__ ConvParams p) {
-    constexpr int B_BYTES = BN * BK * 4;
+    constexpr int NSUB = BN / CG;                               // pixels staged by one CTA
+    constexpr int B_BYTES = NSUB * BK * 4;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = 2 * BN;                           // 256 / 512
+    constexpr int TMEM_COLS = 2 * BN;                           // 256 / 512: double-buffered accumulator
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.tiles_m * p.tiles_n;                  // tiles_m: channel tiles (128), tiles_n: pixel tiles (BN)
+    const int rank = CG == 1 ? 0 : (int)cluster_ctarank();
+    const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;     // a worker = one CTA or one CTA pair
+    const int n_items = p.tiles_m * p.tiles_n;                  // tiles_m: channel tiles (128*CG), tiles_n: pixel tiles (BN)
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
@@ -402,64 +196,63 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 2) cg_tmem_alloc<CG>(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    cg_sync<CG>();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    // item -> channel tile (fastest: CTAs running together share the pixel box in L2) and pixel tile -> image, first pixel
+    // item -> channel tile (fastest: workers running together share the pixel box in L2) and pixel tile -> image, first pixel
     auto decode = [&](int item, int& tile_m, int& n, int& y0, int& x0) {
         tile_m = item % p.tiles_m;
         const int tp = item / p.tiles_m;
         const int tx = tp % p.tiles_x;
         const int t = tp / p.tiles_x;
         n = t / p.tiles_y;
-        y0 = (t - n * p.tiles_y) * (BN >> p.bw_log2);
-        x0 = tx << p.bw_log2;
+        // the pair's tile = the CTA box doubled along y (sub_dy > 0) or x (sub_dx > 0)
+        y0 = (t - n * p.tiles_y) * ((NSUB >> p.bw_log2) + (CG == 2 ? p.sub_dy : 0));
+        x0 = tx * ((1 << p.bw_log2) + (CG == 2 ? p.sub_dx : 0));
     };
 
     if (warp == 0 && lane == 0) {
-        // ------------------------------ TMA producer ------------------------------
+        // ------------------------------ TMA producer (every CTA) ------------------
         uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = worker; item < n_items; item += n_workers) {
             int tile_m, n, y0, x0;
             decode(item, tile_m, n, y0, x0);
-            const int m0 = tile_m * BM;
+            const int m0 = tile_m * BM * CG + rank * BM;
+            const int ys = y0 + rank * p.sub_dy, xs = x0 + rank * p.sub_dx;       // this CTA's pixel box
             for (int r = 0; r < p.R; ++r) {
-                const int by = y0 * p.a.sy + p.a.dy0 + r * p.a.dys;
+                const int by = ys * p.a.sy + p.a.dy0 + r * p.a.dys;
                 for (int s = 0; s < p.S; ++s) {
-                    const int bx = x0 * p.a.sx + p.a.dx0 + s * p.a.dxs;
+                    const int bx = xs * p.a.sx + p.a.dx0 + s * p.a.dxs;
                     const int wk = p.wp * ((p.wr0 + r * p.wrs) * p.wS + p.ws0 + s * p.wss);
                     for (int ch = 0; ch < p.chunks; ++ch, ++it) {
                         const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(empty0 + 8 * st, ph ^ 1);
-                        mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
+                        if (rank == 0) mbar_expect_tx(full0 + 8 * st, CG * STAGE_BYTES);        // bytes of both CTAs
                         const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + A_BYTES;
                         if (!AMN) {
-                            tma_load_2d(a_dst, &map_w, full0 + 8 * st, wk + ch * BK, m0);
+                            cg_tma_2d<CG>(a_dst, &map_w, full0 + 8 * st, wk + ch * BK, m0);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BM / 32; ++j)
-                                tma_load_2d(a_dst + j * 4096, &map_w, full0 + 8 * st, wk + m0 + 32 * j, ch * BK);
+                                cg_tma_2d<CG>(a_dst + j * 4096, &map_w, full0 + 8 * st, wk + m0 + 32 * j, ch * BK);
                         }
-                        tma_load_4d(b_dst, &map_x, full0 + 8 * st, ch * BK, bx, by, n);
+                        cg_tma_4d<CG>(b_dst, &map_x, full0 + 8 * st, ch * BK, bx, by, n);
                     }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------ MMA issuer --------------------------------
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------ MMA issuer (leader CTA) -------------------
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
         uint32_t it = 0, local = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        for (int item = worker; item < n_items; item += n_workers, ++local) {
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
             mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);
             tc_fence_after();
@@ -473,26 +266,27 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adesc = AMN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
                     const uint64_t bdesc = make_desc(b_src + k * 32, 16, 1024, 2);
-                    tc_mma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    cg_mma<CG>(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
-                tc_commit(empty0 + 8 * st);
+                cg_commit<CG>(empty0 + 8 * st);
             }
-            tc_commit(tfull0 + 8 * acc);
+            cg_commit<CG>(tfull0 + 8 * acc);
         }
     } else if (warp >= 4) {
-        // ------------------------------ epilogue (8 warps) ------------------------
+        // ------------------------------ epilogue (8 warps per CTA) ----------------
         // warp w reads TMEM lanes (w % 4) * 32 .. +31 (its output channels); warps 4-7 take the even 32-pixel column chunks,
-        // warps 8-11 the odd ones.  A chunk is 32 consecutive pixels of ONE grid row (the host guarantees BW >= 32), so
+        // warps 8-11 the odd ones.  A chunk is 32 consecutive pixels of ONE grid row (the host guarantees box width >= 32), so
         // the output address is base + j * step with a warp-uniform base: per value one compare, one add, one store.
         const int q = warp & 3, half = (warp - 4) >> 2;
         constexpr int kChunks = BN / 64;                            // chunks per warp
         uint32_t local = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        for (int item = worker; item < n_items; item += n_workers, ++local) {
             int tile_m, n, y0, x0;
             decode(item, tile_m, n, y0, x0);
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
-            const int co = tile_m * BM + q * 32 + lane;             // this lane's output channel
-            const bool live = tile_m * BM + q * 32 < p.n_out;       // warp-uniform: the warp owns live channels
+            const int c_base = tile_m * BM * CG + rank * BM + q * 32;
+            const int co = c_base + lane;                           // this lane's output channel
+            const bool live = c_base < p.n_out;                     // warp-uniform: the warp owns live channels
             const bool co_ok = co < p.n_out;
             const float bias = (p.bias != nullptr && co_ok) ? p.bias[co] : 0.f;
             const long long img = (long long)n * p.o_sn + co;
@@ -509,9 +303,11 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                     uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
                     tc_wait_ld();
                     if (c + 1 < kChunks) tc_ld32_nowait(t0 + (uint32_t)((2 * (c + 1) + half) * 32), nxt);   // overlaps the stores below
-                    const int c0 = (2 * c + half) * 32;
-                    const int iy = y0 + (c0 >> p.bw_log2), ix0 = x0 + (c0 & ((1 << p.bw_log2) - 1));
-                    int nvalid = (iy < p.P && co_ok) ? p.Q - ix0 : 0;                  // pixels of this chunk inside the grid
+                    const int col = (2 * c + half) * 32;            // first pixel column of the chunk
+                    const int sub = col / NSUB, cc = col - sub * NSUB;                   // which CTA's pixel box, position in it
+                    const int iy = y0 + sub * p.sub_dy + (cc >> p.bw_log2);
+                    const int ix0 = x0 + sub * p.sub_dx + (cc & ((1 << p.bw_log2) - 1));
+                    int nvalid = (iy < p.P && co_ok) ? p.Q - ix0 : 0;                   // pixels of this chunk inside the grid
                     nvalid = nvalid > 32 ? 32 : nvalid;
                     const long long off = img + (long long)(iy * p.oys + p.oyo) * p.o_sh + (long long)(ix0 * p.oxs + p.oxo) * p.o_sw;
                     float* __restrict__ o = p.out + off;
@@ -533,14 +329,209 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) cg_arrive_leader<CG>(tempty0 + 8 * acc);
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cg_sync<CG>();                                                   // nobody frees TMEM / exits while the peer still uses it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        cg_tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+    }
+}
+
+// =================================================================================================================
+// k_conv_w
+// =================================================================================================================
+constexpr int kThreadsW = 256;      // warps 0-3: producer, MMA issuer, TMEM allocator, (idle); warps 4-7: epilogue
+constexpr int smem_bytes_w(int stages, int bn, int cg) { return stages * (BM + bn / cg) * BKW * 4 + PATCH_BYTES + 1024 + 256; }
+
+template <int BN, int STAGES, int CG>
+__global__ void __launch_bounds__(kThreadsW, 1)
+k_conv_w(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+         const __grid_constant__ ConvParams p) {
+    constexpr int NSUB = BN / CG;                               // B columns staged by one CTA
+    constexpr int AW_BYTES = BM * BKW * 4, BW_BYTES = NSUB * BKW * 4;
+    constexpr int STAGE_BYTES = AW_BYTES + BW_BYTES;
+    constexpr int CHUNK = BKW * 128;                            // one 32-channel x 64-pixel box: 8 KB
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PATCH_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CG == 1 ? 0 : (int)cluster_ctarank();
+    const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4 * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) cg_tmem_alloc<CG>(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    cg_sync<CG>();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    // item = (pixel chunk, tile), tile fastest
+    const long long w_tiles = (long long)p.tiles_m * p.tiles_n;
+    const long long w_end = w_tiles * p.splits;
+    auto next_work = [&](long long& cur, int& tile_m, int& tile_n, int& kb0, int& nkb) -> bool {
+        if (cur >= w_end) return false;
+        const int chunk = (int)(cur / w_tiles), tile = (int)(cur - (long long)chunk * w_tiles);
+        kb0 = chunk * p.kb_per_split;
+        nkb = min(p.nkb_total - kb0, p.kb_per_split);
+        tile_n = tile % p.tiles_n;
+        tile_m = tile / p.tiles_n;
+        cur += n_workers;
+        return true;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer (every CTA) ------------------
+        uint32_t it = 0;
+        long long cur = worker;
+        int tile_m, tile_n, kb0, nkb;
+        while (next_work(cur, tile_m, tile_n, kb0, nkb)) {
+            // per 32-channel box: channel offset and tap shift (constant over the K loop)
+            int ac[BM / 32], ax[BM / 32], ay[BM / 32], bc[NSUB / 32], bx[NSUB / 32], by[NSUB / 32];
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) {
+                const int m = tile_m * BM * CG + rank * BM + 32 * j, tap = m / p.a.cp, r = tap / p.a.S, s = tap - r * p.a.S;
+                ac[j] = m - tap * p.a.cp; ax[j] = p.a.dx0 + s * p.a.dxs; ay[j] = p.a.dy0 + r * p.a.dys;
+            }
+#pragma unroll
+            for (int j = 0; j < NSUB / 32; ++j) {
+                const int m = tile_n * BN + rank * NSUB + 32 * j, tap = m / p.b.cp, r = tap / p.b.S, s = tap - r * p.b.S;
+                bc[j] = m - tap * p.b.cp; bx[j] = p.b.dx0 + s * p.b.dxs; by[j] = p.b.dy0 + r * p.b.dys;
+            }
+            const int kw_log2 = p.bw_log2, kh = BKW >> kw_log2;
+            int xb = kb0 % p.tiles_x, t = kb0 / p.tiles_x;
+            int n = t / p.tiles_y, yb = t - n * p.tiles_y;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (rank == 0) mbar_expect_tx(full0 + 8 * st, CG * STAGE_BYTES);
+                const uint32_t a_dst = smem_base + st * STAGE_BYTES, b_dst = a_dst + AW_BYTES;
+                const int x0 = xb << kw_log2, y0 = yb * kh;
+#pragma unroll
+                for (int j = 0; j < BM / 32; ++j)
+                    cg_tma_4d<CG>(a_dst + j * CHUNK, &map_a, full0 + 8 * st, ac[j], x0 * p.a.sx + ax[j], y0 * p.a.sy + ay[j], n);
+#pragma unroll
+                for (int j = 0; j < NSUB / 32; ++j)
+                    cg_tma_4d<CG>(b_dst + j * CHUNK, &map_b, full0 + 8 * st, bc[j], x0 * p.b.sx + bx[j], y0 * p.b.sy + by[j], n);
+                if (++xb == p.tiles_x) { xb = 0; if (++yb == p.tiles_y) { yb = 0; ++n; } }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------ MMA issuer (leader CTA) -------------------
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+        uint32_t it = 0, local = 0;
+        long long cur = worker;
+        int tile_m, tile_n, kb0, nkb;
+        for (; next_work(cur, tile_m, tile_n, kb0, nkb); ++local) {
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + st * STAGE_BYTES, b_src = a_src + AW_BYTES;
+#pragma unroll
+                for (int k = 0; k < BKW / UMMA_K; ++k) {        // 8 K rows = two 4-row (512 B) atoms per MMA; 32-channel chunks CHUNK apart
+                    const uint64_t adesc = make_desc(a_src + k * 1024, CHUNK, 512, 1);
+                    const uint64_t bdesc = make_desc(b_src + k * 1024, CHUNK, 512, 1);
+                    cg_mma<CG>(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                cg_commit<CG>(empty0 + 8 * st);
+            }
+            cg_commit<CG>(tfull0 + 8 * acc);
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue (4 warps per CTA) ----------------
+        const int q = warp - 4;
+        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        uint32_t local = 0;
+        long long cur = worker;
+        int tile_m, tile_n, kb0, nkb;
+        for (; next_work(cur, tile_m, tile_n, kb0, nkb); ++local) {
+            const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tc_fence_after();
+            // rows of this warp: 8 per lane (4*i + sub_r), resolved to output offsets once per tile (one tap per 32 rows)
+            long long row_off[8];
+            bool row_ok[8];
+            {
+                const int row0 = tile_m * BM * CG + rank * BM + q * 32, tap = row0 / p.cp_r, ch0 = row0 - tap * p.cp_r;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ch = ch0 + 4 * i + sub_r;
+                    row_ok[i] = tap < p.t_r && ch < p.c_r;
+                    row_off[i] = (long long)(tap * p.c_r + ch) * p.rs;
+                }
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = tile_n * BN + c0;
+                const int tapc = col0 / p.cp_c, chc0 = col0 - tapc * p.cp_c;
+                if (tapc >= p.t_c) break;                                // warp-uniform
+                if (p.c_c - chc0 <= 0) continue;                         // padded channels of this tap
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                float4 rows4[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
+                const int ch = chc0 + sub_c;
+                const long long col_off = (long long)(tapc * p.c_c + ch) * p.cs;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (!row_ok[i]) continue;
+                    const float4 v4 = rows4[i];
+                    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+                    float* dst = p.out + row_off[i] + col_off;
+                    if (p.vec_ok && ch + 3 < p.c_c) {
+                        if (p.atomic) red_add_v4(dst, v[0], v[1], v[2], v[3]);
+                        else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (ch + t < p.c_c) {
+                                if (p.atomic) atomicAdd(dst + t * p.cs, v[t]); else dst[t * p.cs] = v[t];
+                            }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) cg_arrive_leader<CG>(tempty0 + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    cg_sync<CG>();
+    if (warp == 2) {
+        tc_fence_after();
+        cg_tmem_dealloc<CG>(tmem_base, TMEM_COLS);
     }
 }
 
@@ -618,35 +609,56 @@ int make_w_map(CUtensorMap* map, const float* ptr, long long rows, long long col
     return 0;
 }
 
-template <int MODE, bool BMN, int BN, int STAGES>
-int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
+// cta_group::2 switch: LS_CONV_2CTA=0 keeps every convolution on the one-CTA kernels (A/B measurements), =2 takes the pair
+// kernels whenever the shape allows it, however little work there is (tests at small sizes); default 1 = heuristic
+int mode_2cta() {
+    static int flag = -1;
+    if (flag < 0) {
+        const char* e = getenv("LS_CONV_2CTA");
+        flag = e ? atoi(e) : 1;
+        if (flag < 0 || flag > 2) flag = 1;
+    }
+    return flag;
+}
+bool allow_2cta() { return mode_2cta() != 0; }
+
+// launch `workers` CTAs (CG = 1) or CTA pairs (CG = 2: cluster dimension 2)
+template <int CG, class Kernel>
+int launch_workers(Kernel kernel, int workers, int threads, int smem, cudaStream_t stream, const CUtensorMap& m0, const CUtensorMap& m1,
+                   const ConvParams& p, const char* what) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(workers * CG));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, m0, m1, p) != cudaSuccess) return ls_check_cuda(what);
+    return ls_check_cuda(what);
+}
+
+template <bool AMN, int BN, int STAGES, int CG>
+int launch_t(const CUtensorMap& mw, const CUtensorMap& mx, const ConvParams& p, cudaStream_t stream) {
     static PerDeviceOnce once;
-    constexpr int smem = smem_bytes(STAGES, BN);
-    if (once.ensure_smem(k_conv_tf32<MODE, BMN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
+    constexpr int smem = smem_bytes_t(STAGES, BN, CG);
+    if (once.ensure_smem(k_conv_t<AMN, BN, STAGES, CG>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
     const long long n_items = (long long)p.tiles_m * p.tiles_n;
     if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
-    const int num_sms = current_sm_count();
-    const long long total = n_items * (MODE == MODE_W ? p.splits : 1);
-    const int ctas = total < num_sms ? (int)total : num_sms;
-    k_conv_tf32<MODE, BMN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, p);
-    return ls_check_cuda("k_conv_tf32");
+    const int slots = current_sm_count() / CG;
+    const int workers = n_items < slots ? (int)n_items : slots;
+    return launch_workers<CG>(k_conv_t<AMN, BN, STAGES, CG>, workers, kThreadsT, smem, stream, mw, mx, p, "k_conv_t");
 }
-
-template <int MODE, bool BMN>
-int launch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
-    // stage = 16 KB of A + BN rows of B: 128x256 tiles 4 x 48 KB, 128x128 6 x 32 KB, 128x32 8 x 20 KB (+ 18 KB of patches)
-    if (bn == 256) return launch_s<MODE, BMN, 256, 4>(ma, mb, p, stream);
-    if (bn == 128) return launch_s<MODE, BMN, 128, 6>(ma, mb, p, stream);
-    return launch_s<MODE, BMN, 32, 8>(ma, mb, p, stream);
-}
-
-int pick_bn(int n) { return n <= 32 ? 32 : (n <= 128 ? 128 : 256); }
 
 // ------------------------------------------------------------------------------------------------------------------
-// MODE_F problem description (host)
+// k_conv_t problem description (host)
 // ------------------------------------------------------------------------------------------------------------------
 struct FProblem {
-    Act4 in;                  // A operand
+    Act4 in;                  // activation operand
     int P, Q;                 // iteration grid
     int R, S;                 // taps iterated
     int sy, sx, dy0, dx0, dys, dxs;
@@ -658,80 +670,33 @@ struct FProblem {
     int n_out, act;
 };
 
-int run_f(const FProblem& f, cudaStream_t stream) {
-    ConvParams p{};
-    p.P = f.P; p.Q = f.Q; p.n_img = f.in.N;
-    int bw = pow2_ceil_log2(f.Q);
-    if (bw > 7) bw = 7;
-    while ((1 << bw) * f.sx > 256) --bw;
-    while ((BM >> bw) * f.sy > 256) ++bw;                    // (cannot happen for stride <= 4; kept for clarity)
-    p.bw_log2 = bw;
-    const int BW = 1 << bw, BH = BM >> bw;
-    p.tiles_x = (f.Q + BW - 1) / BW;
-    p.tiles_y = (f.P + BH - 1) / BH;
-    const int BN = pick_bn(f.n_out);
-    p.tiles_m = f.in.N * p.tiles_x * p.tiles_y;
-    p.tiles_n = (f.n_out + BN - 1) / BN;
-    p.splits = 1;
-    p.R = f.R; p.S = f.S; p.chunks = (f.in.C + BK - 1) / BK;
-    p.nkb_total = p.kb_per_split = p.R * p.S * p.chunks;
-    p.a = ActOp{1 << 30, 1, f.sx, f.sy, f.dx0, f.dy0, f.dxs, f.dys};
-    p.b = p.a;
-    p.wp = f.wp; p.wr0 = f.wr0; p.wrs = f.wrs; p.ws0 = f.ws0; p.wss = f.wss; p.wS = f.wS;
-    p.o_sn = f.o_sn; p.o_sh = f.o_sh; p.o_sw = f.o_sw;
-    p.oys = f.oys; p.oyo = f.oyo; p.oxs = f.oxs; p.oxo = f.oxo;
-    p.n_out = f.n_out; p.act = f.act;
-    p.out = f.out; p.pre_out = f.pre; p.bias = f.bias;
-    p.vec_ok = (f.o_sn % 4 == 0 && f.o_sh % 4 == 0 && f.o_sw % 4 == 0 && (reinterpret_cast<uintptr_t>(f.out) & 15) == 0 &&
-                (f.pre == nullptr || (reinterpret_cast<uintptr_t>(f.pre) & 15) == 0)) ? 1 : 0;
-    p.atomic = 0;
-    if (p.nkb_total <= 0 || p.tiles_m <= 0) return ls_fail("conv: empty problem");
-    CUtensorMap ma, mb;
-    if (make_act_map(&ma, f.in, BW, BH, f.sx, f.sy, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    if (f.w_mn) {
-        if (make_w_map(&mb, f.w, f.w_rows, f.w_cols, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
-        return launch<MODE_F, true>(BN, ma, mb, p, stream);
-    }
-    if (make_w_map(&mb, f.w, f.w_rows, f.w_cols, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    return launch<MODE_F, false>(BN, ma, mb, p, stream);
-}
-
-template <bool AMN, int BN, int STAGES>
-int launch_t_s(const CUtensorMap& mw, const CUtensorMap& mx, const ConvParams& p, cudaStream_t stream) {
-    static PerDeviceOnce once;
-    constexpr int smem = smem_bytes_t(STAGES, BN);
-    if (once.ensure_smem(k_conv_t<AMN, BN, STAGES>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
-    const long long n_items = (long long)p.tiles_m * p.tiles_n;
-    if (n_items <= 0 || n_items > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", n_items);
-    const int num_sms = current_sm_count();
-    const int ctas = n_items < num_sms ? (int)n_items : num_sms;
-    k_conv_t<AMN, BN, STAGES><<<ctas, kThreadsT, smem, stream>>>(mw, mx, p);
-    return ls_check_cuda("k_conv_t");
-}
-
-// MODE_T host side: same problem description as MODE_F
 int run_t(const FProblem& f, cudaStream_t stream) {
     ConvParams p{};
     p.P = f.P; p.Q = f.Q; p.n_img = f.in.N;
     const int num_sms = current_sm_count();
-    const int tiles_m = (f.n_out + BM - 1) / BM;
+    const long long px256 = (long long)f.in.N * ((f.P * (long long)f.Q + 255) / 256);     // 256-pixel tiles, roughly
+    // cta_group::2 (256 channels x 256 pixels per CTA pair) when the channel count fills pairs and there is work for all pairs
+    const bool pair = allow_2cta() && f.n_out >= 256 && f.n_out % 256 == 0 && (mode_2cta() == 2 || px256 * (f.n_out / 256) >= num_sms / 2);
+    const int CG = pair ? 2 : 1;
+    const int tiles_m = (f.n_out + BM * CG - 1) / (BM * CG);
     // 256-pixel tiles unless they leave most SMs idle (small feature maps): then 128-pixel tiles double the CTA count
     int BN = 256;
-    {
-        const long long px256 = (long long)f.in.N * ((f.P * (long long)f.Q + 255) / 256);
-        if (px256 * tiles_m < num_sms) BN = 128;
-    }
+    if (!pair && px256 * tiles_m * 5 < num_sms * 3) BN = 128;      // < 60 % of the SMs busy with 256-pixel tiles
+    const int nsub = BN / CG;                                // pixels per CTA box
     int bw = pow2_ceil_log2(f.Q);
-    const int bn_log2 = BN == 256 ? 8 : 7;
-    if (bw > bn_log2) bw = bn_log2;
+    const int nsub_log2 = nsub == 256 ? 8 : 7;
+    if (bw > nsub_log2) bw = nsub_log2;
     if (bw < 5) bw = 5;                                      // the epilogue's 32-pixel chunks must not straddle grid rows
     while ((1 << bw) * f.sx > 256) --bw;
-    while ((BN >> bw) * f.sy > 256) ++bw;
-    if ((1 << bw) * f.sx > 256) return ls_fail("conv: no TMA box for a %d-pixel tile at stride %d", BN, f.sx);
+    if (bw < 5 || (nsub >> bw) * f.sy > 256) return ls_fail("conv: no TMA box for a %d-pixel tile at stride %d", nsub, f.sx);
     p.bw_log2 = bw;
-    const int BW = 1 << bw, BH = BN >> bw;
-    p.tiles_x = (f.Q + BW - 1) / BW;
-    p.tiles_y = (f.P + BH - 1) / BH;
+    const int BW = 1 << bw, BH = nsub >> bw;
+    p.sub_dx = p.sub_dy = 0;
+    if (pair) {                                              // the pair's tile: two boxes side by side, else stacked
+        if (f.Q >= 2 * BW) p.sub_dx = BW; else p.sub_dy = BH;
+    }
+    p.tiles_x = (f.Q + BW + p.sub_dx - 1) / (BW + p.sub_dx);
+    p.tiles_y = (f.P + BH + p.sub_dy - 1) / (BH + p.sub_dy);
     p.tiles_m = tiles_m;
     p.tiles_n = f.in.N * p.tiles_x * p.tiles_y;
     p.splits = 1;
@@ -749,24 +714,16 @@ int run_t(const FProblem& f, cudaStream_t stream) {
     if (make_act_map(&mx, f.in, BW, BH, f.sx, f.sy, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     if (f.w_mn) {
         if (make_w_map(&mw, f.w, f.w_rows, f.w_cols, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
-        return BN == 256 ? launch_t_s<true, 256, 4>(mw, mx, p, stream) : launch_t_s<true, 128, 6>(mw, mx, p, stream);
+        if (pair) return launch_t<true, 256, 6, 2>(mw, mx, p, stream);
+        return BN == 256 ? launch_t<true, 256, 4, 1>(mw, mx, p, stream) : launch_t<true, 128, 6, 1>(mw, mx, p, stream);
     }
     if (make_w_map(&mw, f.w, f.w_rows, f.w_cols, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    return BN == 256 ? launch_t_s<false, 256, 4>(mw, mx, p, stream) : launch_t_s<false, 128, 6>(mw, mx, p, stream);
-}
-
-// orientation switch (A/B measurements): LS_CONV_ORIENT=f keeps pixels on the M side (MODE_F), default = MODE_T
-int run_fwdlike(const FProblem& f, cudaStream_t stream) {
-    static int use_f = -1;
-    if (use_f < 0) {
-        const char* e = getenv("LS_CONV_ORIENT");
-        use_f = (e && (e[0] == 'f' || e[0] == 'F')) ? 1 : 0;
-    }
-    return use_f ? run_f(f, stream) : run_t(f, stream);
+    if (pair) return launch_t<false, 256, 6, 2>(mw, mx, p, stream);
+    return BN == 256 ? launch_t<false, 256, 4, 1>(mw, mx, p, stream) : launch_t<false, 128, 6, 1>(mw, mx, p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// MODE_W problem description (host): out[(tap_r, ch_r), (tap_c, ch_c)] = sum_pixels A[pixel + tap_r][ch_r] * B[pixel + tap_c][ch_c]
+// k_conv_w problem description (host): out[(tap_r, ch_r), (tap_c, ch_c)] = sum_pixels A[pixel + tap_r][ch_r] * B[pixel + tap_c][ch_c]
 // ------------------------------------------------------------------------------------------------------------------
 struct WOperand {
     Act4 t;
@@ -775,26 +732,40 @@ struct WOperand {
     int sx, sy, dx0, dy0;
 };
 
+template <int BN, int STAGES, int CG>
+int launch_w(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
+    static PerDeviceOnce once;
+    constexpr int smem = smem_bytes_w(STAGES, BN, CG);
+    if (once.ensure_smem(k_conv_w<BN, STAGES, CG>, smem) != cudaSuccess) return ls_check_cuda("conv smem attribute");
+    const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
+    if (total <= 0 || total > 0x7fffffffLL) return ls_fail("conv: bad work-list size %lld", total);
+    const int slots = current_sm_count() / CG;
+    const int workers = total < slots ? (int)total : slots;
+    return launch_workers<CG>(k_conv_w<BN, STAGES, CG>, workers, kThreadsW, smem, stream, ma, mb, p, "k_conv_w");
+}
+
 int run_w(const WOperand& A, const WOperand& B, int P, int Q, float* out, long long rs, long long cs, cudaStream_t stream) {
     ConvParams p{};
     p.P = P; p.Q = Q; p.n_img = A.t.N;
     int kw = pow2_ceil_log2(Q);
-    if (kw > 5) kw = 5;
+    if (kw > 6) kw = 6;
     p.bw_log2 = kw;
-    const int KW = 1 << kw, KH = 32 >> kw;
+    const int KW = 1 << kw, KH = BKW >> kw;
     p.tiles_x = (Q + KW - 1) / KW;
     p.tiles_y = (P + KH - 1) / KH;
     p.nkb_total = A.t.N * p.tiles_x * p.tiles_y;
     const int cpa = (A.C + 31) & ~31, cpb = (B.C + 31) & ~31;
     const int M = A.taps * cpa, N = B.taps * cpb;
-    const int BN = pick_bn(N);
-    p.tiles_m = (M + BM - 1) / BM;
+    const int BN = N <= 32 ? 32 : (N <= 128 ? 128 : 256);
+    const bool pair = allow_2cta() && BN == 256 && M >= 256 && M % 256 == 0;
+    const int CG = pair ? 2 : 1;
+    p.tiles_m = (M + BM * CG - 1) / (BM * CG);
     p.tiles_n = (N + BN - 1) / BN;
-    // pixel chunks: equal K-block counts, >= 32 K blocks each (amortises the red.add epilogue), ~8 items per CTA
+    // pixel chunks: equal K-block counts, >= 16 K blocks (1024 pixels) each (amortises the red.add epilogue), ~8 items per worker
     {
         const long long tiles = (long long)p.tiles_m * p.tiles_n;
-        long long want = (8ll * current_sm_count() + tiles - 1) / tiles;       // chunks wanted
-        const long long max_chunks = p.nkb_total / 32 > 0 ? p.nkb_total / 32 : 1;
+        long long want = (8ll * (current_sm_count() / CG) + tiles - 1) / tiles;
+        const long long max_chunks = p.nkb_total / 16 > 0 ? p.nkb_total / 16 : 1;
         if (want > max_chunks) want = max_chunks;
         if (want < 1) want = 1;
         p.kb_per_split = (int)((p.nkb_total + want - 1) / want);
@@ -812,7 +783,11 @@ int run_w(const WOperand& A, const WOperand& B, int P, int Q, float* out, long l
     CUtensorMap ma, mb;
     if (make_act_map(&ma, A.t, KW, KH, A.sx, A.sy, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
     if (make_act_map(&mb, B.t, KW, KH, B.sx, B.sy, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
-    return launch<MODE_W, true>(BN, ma, mb, p, stream);
+    // stage = (128 + BN/CG) channels x 64 pixels x 4 B: 96 KB x 2 (BN 256), 64 KB x 3 (BN 256 pair / BN 128), 40 KB x 5 (BN 32)
+    if (pair) return launch_w<256, 3, 2>(ma, mb, p, stream);
+    if (BN == 256) return launch_w<256, 2, 1>(ma, mb, p, stream);
+    if (BN == 128) return launch_w<128, 3, 1>(ma, mb, p, stream);
+    return launch_w<32, 5, 1>(ma, mb, p, stream);
 }
 
 int validate(const LsConv2d* c) {
@@ -865,7 +840,7 @@ extern "C" int ls_conv2d_forward(const LsConv2d* c, const float* x, const float*
         f.w_rows = c->Cout; f.w_cols = (long long)c->R * c->S * c->Cin; f.w_mn = 0;
         f.wp = c->Cin; f.wr0 = 0; f.wrs = 1; f.ws0 = 0; f.wss = 1; f.wS = c->S;
         f.oys = f.oxs = 1; f.oyo = f.oxo = 0;
-        return run_fwdlike(f, stream);
+        return run_t(f, stream);
     }
     // transposed, kernel == stride: y[n, k*Y + r, k*X + s, :] = x[n, Y, X, :] W[:, r, s, :] ; one 1-tap GEMM per (r, s) class,
     // W = [Cin][R*S*Cout] read MN-major (rows = input channel = k, columns = tap*Cout + output channel)
@@ -877,7 +852,7 @@ extern "C" int ls_conv2d_forward(const LsConv2d* c, const float* x, const float*
     for (int r = 0; r < c->R; ++r)
         for (int s = 0; s < c->S; ++s) {
             f.wr0 = r; f.ws0 = s; f.oyo = r; f.oxo = s;
-            if (run_fwdlike(f, stream)) return -1;
+            if (run_t(f, stream)) return -1;
         }
     return 0;
 }
@@ -901,7 +876,7 @@ extern "C" int ls_conv2d_dgrad(const LsConv2d* c, const float* dy, const float* 
         f.w_rows = c->Cin; f.w_cols = (long long)c->R * c->S * c->Cout; f.w_mn = 0;
         f.wp = c->Cout; f.wr0 = 0; f.wrs = 1; f.ws0 = 0; f.wss = 1; f.wS = c->S;
         f.oys = f.oxs = 1; f.oyo = f.oxo = 0;
-        return run_fwdlike(f, stream);
+        return run_t(f, stream);
     }
     // dx[n,y,x,ci] = sum_{r,s,co} dy[n, (y + pad - r)/st, (x + pad - s)/st, co] W[co, r, s, ci]  (terms with a remainder vanish):
     // one stride-1 gather per residue class (y % st, x % st), taps r = ra + st*i with ra = (py + pad) % st.
@@ -926,7 +901,7 @@ extern "C" int ls_conv2d_dgrad(const LsConv2d* c, const float* dy, const float* 
             f.dy0 = (py + c->pad - ra) / st; f.dx0 = (px + c->pad - sa) / st;
             f.wr0 = ra; f.wrs = st; f.ws0 = sa; f.wss = st;
             f.oyo = py; f.oxo = px;
-            if (run_fwdlike(f, stream)) return -1;
+            if (run_t(f, stream)) return -1;
         }
     return 0;
 }

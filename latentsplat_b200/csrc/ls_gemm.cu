@@ -46,6 +46,8 @@ using namespace lstc;   // mbarrier / TMA / tcgen05 wrappers, make_desc, sts128 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == LS_ACT_RELU) return fmaxf(v, 0.f);
     if (act == LS_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    if (act == LS_ACT_SILU) return v / (1.f + __expf(-v));
+    if (act == LS_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
     return v;
 }
 
@@ -57,7 +59,7 @@ template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
             const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic,
-            int tiles_m, int tiles_n, int splits) {
+            int tiles_m, int tiles_n, int splits, const float* __restrict__ residual, long long ldr, float* __restrict__ pre_out) {
     constexpr int STAGE_BYTES = stage_bytes(BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -162,7 +164,9 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int q = warp - 4;                  // TMEM lane quarter == warp % 4
         const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                            (pre_out == nullptr || (reinterpret_cast<uintptr_t>(pre_out) & 15) == 0);
+        const bool res_vec = (ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0);
         uint32_t local = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
             int tile_m, tile_n, kb0, nkb;
@@ -195,17 +199,31 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 for (int i = 0; i < 8; ++i) {
                     const int row = tile_m * BM + q * 32 + 4 * i + sub_r;
                     const float4 v4 = rows4[i];
-                    float v[4] = {apply_act(v4.x + b4[0], act), apply_act(v4.y + b4[1], act), apply_act(v4.z + b4[2], act),
-                                  apply_act(v4.w + b4[3], act)};
+                    const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
+                    float v[4] = {apply_act(pre[0], act), apply_act(pre[1], act), apply_act(pre[2], act), apply_act(pre[3], act)};
                     if (row < M) {
                         float* dst = C + (long long)row * ldc + col;
                         if (!atomic && vec_ok && col + 3 < N) {
+                            if (residual != nullptr && res_vec) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(residual + (long long)row * ldr + col));
+                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                            } else if (residual != nullptr) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) v[t] += residual[(long long)row * ldr + col + t];
+                            }
                             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                            if (pre_out != nullptr)
+                                *reinterpret_cast<float4*>(pre_out + (long long)row * ldc + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
                         } else {
 #pragma unroll
                             for (int t = 0; t < 4; ++t)
                                 if (col + t < N) {
-                                    if (atomic) atomicAdd(dst + t, v[t]); else dst[t] = v[t];
+                                    if (atomic) {
+                                        atomicAdd(dst + t, v[t]);
+                                    } else {
+                                        dst[t] = residual != nullptr ? v[t] + residual[(long long)row * ldr + col + t] : v[t];
+                                        if (pre_out != nullptr) pre_out[(long long)row * ldc + col + t] = pre[t];
+                                    }
                                 }
                         }
                     }
@@ -276,7 +294,7 @@ template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
                  const float* __restrict__ bias, int M, int N, int K, long long ldc, int act, int kb_per_split, int atomic,
-                 int tiles_m, int tiles_n, int splits) {
+                 int tiles_m, int tiles_n, int splits, const float* __restrict__ residual, long long ldr, float* __restrict__ pre_out) {
     constexpr int BH = BN / 2;                                   // rows of B staged by each CTA
     constexpr int STAGE_BYTES = A_BYTES + BH * BK * 4;
     extern __shared__ uint8_t smem_raw[];
@@ -381,7 +399,9 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int q = warp - 4;
         const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                            (pre_out == nullptr || (reinterpret_cast<uintptr_t>(pre_out) & 15) == 0);
+        const bool res_vec = (ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0);
         uint32_t local = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters, ++local) {
             int tile_m, tile_n, kb0, nkb;
@@ -415,17 +435,31 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int i = 0; i < 8; ++i) {
                     const int row = row_base + 4 * i + sub_r;
                     const float4 v4 = rows4[i];
-                    float v[4] = {apply_act(v4.x + b4[0], act), apply_act(v4.y + b4[1], act), apply_act(v4.z + b4[2], act),
-                                  apply_act(v4.w + b4[3], act)};
+                    const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
+                    float v[4] = {apply_act(pre[0], act), apply_act(pre[1], act), apply_act(pre[2], act), apply_act(pre[3], act)};
                     if (row < M) {
                         float* dst = C + (long long)row * ldc + col;
                         if (!atomic && vec_ok && col + 3 < N) {
+                            if (residual != nullptr && res_vec) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(residual + (long long)row * ldr + col));
+                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                            } else if (residual != nullptr) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) v[t] += residual[(long long)row * ldr + col + t];
+                            }
                             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                            if (pre_out != nullptr)
+                                *reinterpret_cast<float4*>(pre_out + (long long)row * ldc + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
                         } else {
 #pragma unroll
                             for (int t = 0; t < 4; ++t)
                                 if (col + t < N) {
-                                    if (atomic) atomicAdd(dst + t, v[t]); else dst[t] = v[t];
+                                    if (atomic) {
+                                        atomicAdd(dst + t, v[t]);
+                                    } else {
+                                        dst[t] = residual != nullptr ? v[t] + residual[(long long)row * ldr + col + t] : v[t];
+                                        if (pre_out != nullptr) pre_out[(long long)row * ldc + col + t] = pre[t];
+                                    }
                                 }
                         }
                     }
@@ -478,7 +512,8 @@ int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, 
     const int ctas = n_items < num_sms ? n_items : num_sms;
     k_gemm_tf32<A_MN, B_MN, BN, STAGES><<<ctas, kThreads, smem, stream>>>(ma, mb, a->C, a->bias, a->M, a->N, a->K,
                                                                        (long long)a->ldc, a->act, kb_per_split, atomic,
-                                                                       (int)grid.x, (int)grid.y, (int)grid.z);
+                                                                       (int)grid.x, (int)grid.y, (int)grid.z, a->residual,
+                                                                       (long long)a->ldr, a->pre_out);
     return ls_check_cuda("k_gemm_tf32");
 }
 
@@ -496,7 +531,7 @@ int launch_2cta_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs
     const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
     k_gemm_tf32_2cta<A_MN, B_MN, BN, STAGES><<<2 * clusters, kThreads, smem, stream>>>(
         ma, mb, a->C, a->bias, a->M, a->N, a->K, (long long)a->ldc, a->act, kb_per_split, atomic, (int)grid.x, (int)grid.y,
-        (int)grid.z);
+        (int)grid.z, a->residual, (long long)a->ldr, a->pre_out);
     return ls_check_cuda("k_gemm_tf32_2cta");
 }
 
@@ -553,6 +588,7 @@ extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
     split = (nkb + kb_per_split - 1) / kb_per_split;
     const int atomic = (split > 1 || a->accumulate) ? 1 : 0;
     if (atomic && a->act != LS_ACT_NONE) return ls_fail("gemm: activation cannot be fused with split-K / accumulate");
+    if (atomic && (a->residual || a->pre_out)) return ls_fail("gemm: residual / pre_out cannot be combined with split-K / accumulate");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (split > 1 && !a->accumulate) {
         if (cudaMemset2DAsync(a->C, a->ldc * sizeof(float), 0, (size_t)a->N * sizeof(float), (size_t)a->M, stream) != cudaSuccess)

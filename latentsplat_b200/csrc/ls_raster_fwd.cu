@@ -10,12 +10,16 @@
 //     then ONE per-tile shared-memory radix sort of (depth_bits, id) keys instead
 //     of 5 global radix passes over 64-bit (tile|depth) keys; the resulting order
 //     is identical to the stable global sort (ties fall back to ascending id);
-//   * Gaussian records are packed AoS (32 B geometry + 16*k B channels) so the
-//     blend stages them with 16-byte async copies into a double-buffered
-//     shared-memory queue, and colour/feature values come from shared memory
-//     instead of per-contribution global gathers;
-//   * warp-uniform skip of Gaussians that do not reach any pixel of the warp's
-//     16x2 strip (ballot), which is most of a tile list;
+//   * the sort stage also PERMUTES: it writes every tile's queue in list order (a
+//     16-byte cull record x, y, extents, id and the packed 32 B geometry + 16*k B
+//     channel record per entry), so the blend kernels stage 256 queue entries with
+//     ONE 1-D bulk TMA copy per array (cp.async.bulk + mbarrier, double buffered)
+//     instead of 256 threads x (key load + 4 cp.async gathers);
+//   * warp-level compaction: each warp tests 32 DIFFERENT queue entries per
+//     instruction against the extent of its 16x2 pixel strip, ballots, and writes
+//     the survivors' positions to a per-warp list; the alpha math then runs over
+//     survivors only (before: every lane walked the whole queue and rejected per
+//     entry -- 80 % issue-active, mostly on rejected entries);
 //   * feature SH (0.5 + eval_sh, cuda_splatting.py:94-101) evaluated in the
 //     preprocess kernel instead of ~30 eager torch kernels.
 #include <stdarg.h>
@@ -23,6 +27,7 @@
 
 #include "ls_common.cuh"
 #include "ls_host.h"
+#include "ls_tc.cuh"
 
 namespace ls {
 
@@ -240,9 +245,27 @@ __global__ void __launch_bounds__(256) k_scatter_keys(const LsRasterScene sc, co
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 
+// write-out of one sorted queue entry: key, cull record (x, y, extents, id), packed geometry + channel record
+__device__ __forceinline__ void write_entry(uint64_t k, long long dst, uint64_t* __restrict__ keys, const float* __restrict__ geom,
+                                            const float* __restrict__ chan, float* __restrict__ cull, float* __restrict__ rec,
+                                            int cv, bool write_key) {
+    if (write_key) keys[dst] = k;
+    const uint32_t id = (uint32_t)k;
+    const float4* g = reinterpret_cast<const float4*>(geom + (size_t)id * LS_GEOM_STRIDE);
+    const float4 g0 = __ldg(g), g1 = __ldg(g + 1);
+    reinterpret_cast<float4*>(cull)[dst] = make_float4(g0.x, g0.y, g1.w, __uint_as_float(id));
+    float4* r = reinterpret_cast<float4*>(rec) + dst * (2 + cv);
+    r[0] = g0;
+    r[1] = g1;
+    const float4* c = reinterpret_cast<const float4*>(chan) + (size_t)id * cv;
+    for (int q = 0; q < cv; ++q) r[2 + q] = __ldg(c + q);
+}
+
 __global__ void __launch_bounds__(kSortThreads) k_tile_sort(uint64_t* __restrict__ keys, uint64_t* __restrict__ tmp,
                                                             const uint32_t* __restrict__ offsets, int smem_keys,
-                                                            long long capacity) {
+                                                            long long capacity, const float* __restrict__ geom_all,
+                                                            const float* __restrict__ chan_all, float* __restrict__ cull,
+                                                            float* __restrict__ rec, int G, int tiles_per_view, int cv) {
     extern __shared__ __align__(16) uint64_t sbuf[];
     __shared__ uint32_t hist[8][256];
     __shared__ uint32_t base[256];
@@ -254,7 +277,14 @@ __global__ void __launch_bounds__(kSortThreads) k_tile_sort(uint64_t* __restrict
     long long e = offsets[blockIdx.x + 1];
     if (e > capacity) e = capacity;
     const int n = (int)(e - s);
-    if (n <= 1) return;
+    if (n <= 0) return;
+    const int view = blockIdx.x / tiles_per_view;
+    const float* __restrict__ geom = geom_all + (size_t)view * G * LS_GEOM_STRIDE;
+    const float* __restrict__ chan = chan_all + (size_t)view * G * (4 * cv);
+    if (n == 1) {                                     // nothing to sort, but the queue entry must exist
+        if (tid == 0) write_entry(keys[s], s, keys, geom, chan, cull, rec, cv, false);
+        return;
+    }
 
     const bool in_smem = n <= smem_keys;
     uint64_t* a = in_smem ? sbuf : keys + s;
@@ -321,11 +351,9 @@ __global__ void __launch_bounds__(kSortThreads) k_tile_sort(uint64_t* __restrict
         __syncthreads();
         uint64_t* t = a; a = b; b = t;
     }
-    if (in_smem) {
-        for (int i = tid; i < n; i += kSortThreads) keys[s + i] = a[i];
-    } else if (a != keys + s) {
-        for (int i = tid; i < n; i += kSortThreads) keys[s + i] = a[i];
-    }
+    // write-out: sorted keys (unless they already sit in place) + the permuted queue records
+    const bool write_key = a != keys + s;
+    for (int i = tid; i < n; i += kSortThreads) write_entry(a[i], s + i, keys, geom, chan, cull, rec, cv, write_key);
 }
 
 // =========================================================================================
@@ -337,13 +365,17 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
                                                            const LsRasterImages im, const int ncol) {
     constexpr int CS = (NC + 3) & ~3;  // chan_stride
     constexpr int CV = CS / 4;
-    __shared__ __align__(16) float4 s_geom[2][kTilePixels][2];
-    __shared__ __align__(16) float4 s_chan[2][kTilePixels][CV];
+    constexpr int RV = 2 + CV;         // float4 per queue record
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    float4* s_rec = reinterpret_cast<float4*>(s_dyn);                                   // [2][kBatch][RV]
+    float4* s_cull = s_rec + 2 * kBatch * RV;                                           // [2][kBatch]
+    uint8_t* s_list = reinterpret_cast<uint8_t*>(s_cull + 2 * kBatch);                  // [8 warps][kBatch]
+    __shared__ __align__(8) uint64_t s_bar[2];
 
     const int gx = (sc.W + kTile - 1) / kTile, gy = (sc.H + kTile - 1) / kTile;
     const int tile = blockIdx.x, v = blockIdx.y;
     const int tx = tile % gx, ty = tile / gx;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = tx * kTile + (tid & 15), py = ty * kTile + (tid >> 4);
     const bool inside = px < sc.W && py < sc.H;
     const float fxp = (float)px, fyp = (float)py;
@@ -353,28 +385,23 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
     long long e = st.tile_offsets[t + 1];
     if (e > st.capacity) e = st.capacity;
     const int n = (int)(e > s ? e - s : 0);
-    const int nb = (n + kTilePixels - 1) / kTilePixels;
+    const int nb = (n + kBatch - 1) / kBatch;
 
-    const uint64_t* __restrict__ keys = st.keys + s;
-    const float* __restrict__ geom = st.geom + (size_t)v * sc.G * LS_GEOM_STRIDE;
-    const float* __restrict__ chan = st.chan + (size_t)v * sc.G * CS;
-
-    auto prefetch = [&](int b) {
-        const int j = b * kTilePixels + tid;
-        if (j < n) {
-            const uint32_t id = (uint32_t)keys[j];
-            const float* gsrc = geom + (size_t)id * LS_GEOM_STRIDE;
-            cp_async16(&s_geom[b & 1][tid][0], gsrc);
-            cp_async16(&s_geom[b & 1][tid][1], gsrc + 4);
-            const float* csrc = chan + (size_t)id * CS;
-#pragma unroll
-            for (int q = 0; q < CV; ++q) cp_async16(&s_chan[b & 1][tid][q], csrc + 4 * q);
-        }
-        cp_async_commit();
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+    if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_fence_init(); }
+    __syncthreads();
+    // one elected thread stages batch b of the tile's queue: two 1-D bulk copies signalling the buffer's mbarrier
+    auto stage = [&](int b) {
+        const int buf = b & 1, cnt = min(kBatch, n - b * kBatch);
+        const uint32_t bar = bar0 + 8 * buf;
+        const long long first = s + (long long)b * kBatch;
+        mbar_expect_tx(bar, (uint32_t)cnt * (16u + 16u * RV));
+        bulk_load(smem_u32(s_rec + buf * kBatch * RV), reinterpret_cast<const float4*>(st.sorted_rec) + first * RV, (uint32_t)cnt * 16u * RV, bar);
+        bulk_load(smem_u32(s_cull + buf * kBatch), reinterpret_cast<const float4*>(st.sorted_cull) + first, (uint32_t)cnt * 16u, bar);
     };
 
     const float wx = (float)(tx * kTile) + 7.5f;                       // centre of the warp's 16x2 strip
-    const float wy = (float)(ty * kTile + 2 * (tid >> 5)) + 0.5f;
+    const float wy = (float)(ty * kTile + 2 * warp) + 0.5f;
     float T = 1.0f;
     float acc[NC];
 #pragma unroll
@@ -382,19 +409,43 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
     float acc_d = 0.f, acc_a = 0.f;
     uint32_t last = 0;
     bool done = !inside;
+    uint8_t* my_list = s_list + warp * kBatch;
 
-    if (nb > 0) prefetch(0);
-    for (int b = 0; b < nb; ++b) {
-        if (b + 1 < nb) { prefetch(b + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        if (__syncthreads_count(done) == kTilePixels) break;
-        const int cnt = min(kTilePixels, n - b * kTilePixels);
-        const float4(*sg)[2] = s_geom[b & 1];
-        const float4(*sc4)[CV] = s_chan[b & 1];
-        for (int j = 0; j < cnt; ++j) {
-            const float4 g0 = sg[j][0];
-            const float4 g1 = sg[j][1];
-            const float2 ext = unpack_extent(g1.w);
-            if (fabsf(g0.y - wy) > ext.y + 0.5f || fabsf(g0.x - wx) > ext.x + 7.5f) continue;  // warp-uniform
+    int staged = 0;                                                    // batches whose copy has been issued
+    if (tid == 0 && nb > 0) { stage(0); }
+    staged = nb > 0 ? 1 : 0;
+    int b = 0;
+    for (; b < nb; ++b) {
+        const int buf = b & 1;
+        if (b + 1 < nb) {                                              // buffer (b+1)&1 was released by the barrier that ended batch b-1
+            if (tid == 0) stage(b + 1);
+            staged = b + 2;
+        }
+        mbar_wait(bar0 + 8 * buf, (uint32_t)(b >> 1) & 1u);
+        if (__syncthreads_count(done) == kTilePixels) { ++b; break; }
+        const int cnt = min(kBatch, n - b * kBatch);
+        const float4* cull = s_cull + buf * kBatch;
+        const float4* rec = s_rec + buf * kBatch * RV;
+        // ---- phase A: compaction.  32 different queue entries per instruction against the strip's extent
+        int nsurv = 0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int j = k0 + lane;
+            bool keep = false;
+            if (j < cnt) {
+                const float4 c = cull[j];
+                const float2 ext = unpack_extent(c.z);
+                keep = fabsf(c.y - wy) <= ext.y + 0.5f && fabsf(c.x - wx) <= ext.x + 7.5f;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) my_list[nsurv + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+            nsurv += __popc(m);
+        }
+        __syncwarp();
+        // ---- phase B: alpha math over the survivors, in list order
+        for (int i = 0; i < nsurv; ++i) {
+            const int j = my_list[i];
+            const float4 g0 = rec[j * RV], g1 = rec[j * RV + 1];
             const float dx = g0.x - fxp, dy = g0.y - fyp;
             const float p2 = fmaf(g0.z * dx, dx, fmaf(g1.x * dy, dy, g0.w * dx * dy));  // log2 domain, <= 0
             const float alpha = fminf(kAlphaMax, g1.y * ex2_approx(p2));
@@ -408,7 +459,7 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
                     const float wgt = alpha * T;
 #pragma unroll
                     for (int q = 0; q < CV; ++q) {
-                        const float4 cq = sc4[j][q];
+                        const float4 cq = rec[j * RV + 2 + q];
                         if (4 * q + 0 < NC) acc[4 * q + 0] = fmaf(cq.x, wgt, acc[4 * q + 0]);
                         if (4 * q + 1 < NC) acc[4 * q + 1] = fmaf(cq.y, wgt, acc[4 * q + 1]);
                         if (4 * q + 2 < NC) acc[4 * q + 2] = fmaf(cq.z, wgt, acc[4 * q + 2]);
@@ -417,13 +468,14 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
                     acc_d = fmaf(g1.z, wgt, acc_d);
                     acc_a += wgt;
                     T = test_T;
-                    last = (uint32_t)(b * kTilePixels + j + 1);
+                    last = (uint32_t)(b * kBatch + j + 1);
                 }
             }
         }
-        __syncthreads();  // buffer (b&1) is refilled by prefetch(b+2)
+        __syncthreads();  // every warp is done with buffer `buf`: batch b+2 may be staged into it
     }
-    cp_async_wait<0>();
+    // a copy issued but not consumed (early exit) must land before the CTA gives its shared memory back
+    if (b < staged) mbar_wait(bar0 + 8 * (b & 1), (uint32_t)(b >> 1) & 1u);
 
     if (inside) {
         const size_t hw = (size_t)sc.H * sc.W;
@@ -445,9 +497,14 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_fwd(const LsRasterScene s
 }
 
 template <int NC>
-static void launch_blend_fwd(const LsRasterScene& sc, const LsRasterState& st, const LsRasterImages& im, int ncol,
-                             dim3 grid, cudaStream_t stream) {
-    k_blend_fwd<NC><<<grid, kTilePixels, 0, stream>>>(sc, st, im, ncol);
+static int launch_blend_fwd(const LsRasterScene& sc, const LsRasterState& st, const LsRasterImages& im, int ncol,
+                            dim3 grid, cudaStream_t stream) {
+    constexpr int RV = 2 + ((NC + 3) & ~3) / 4;
+    constexpr int smem = blend_smem_bytes(RV);
+    static lstc::PerDeviceOnce once;
+    if (smem > 48 * 1024 && once.ensure_smem(k_blend_fwd<NC>, smem) != cudaSuccess) return ls_check_cuda("blend smem attribute");
+    k_blend_fwd<NC><<<grid, kTilePixels, smem, stream>>>(sc, st, im, ncol);
+    return 0;
 }
 
 }  // namespace ls
@@ -515,6 +572,8 @@ extern "C" int ls_raster_sizes(const LsRasterScene* sc, LsRasterSizes* out) {
     out->tile_slots = (int64_t)sc->n_views * gx * gy;
     out->pixels = (int64_t)sc->n_views * sc->H * sc->W;
     out->grad_record = out->per_view_gaussian * out->grad_stride;
+    out->rec_stride = LS_GEOM_STRIDE + out->chan_stride;
+    out->reserved0 = 0;
     return 0;
 }
 
@@ -554,14 +613,15 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
         int smem_keys = st->sort_smem_keys > 0 ? st->sort_smem_keys : 4096;
         if (smem_keys > 12288) smem_keys = 12288;
         const size_t smem_bytes = (size_t)smem_keys * 2 * sizeof(uint64_t);
-        static thread_local size_t configured = 0;
-        if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
-            if (cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
-                return ls_check_cuda("sort smem attribute");
-            configured = smem_bytes;
-        }
+        // the attribute is per device and the request may grow: setting it is idempotent and cheap, so no cache
+        if (smem_bytes > 48 * 1024 &&
+            cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
+            return ls_check_cuda("sort smem attribute");
+        if (!st->sorted_cull || !st->sorted_rec) return ls_fail("sorted_cull / sorted_rec is NULL");
+        if (st->rec_stride != LS_GEOM_STRIDE + st->chan_stride) return ls_fail("rec_stride %d != %d", st->rec_stride, LS_GEOM_STRIDE + st->chan_stride);
         k_tile_sort<<<n_slots, kSortThreads, smem_bytes, stream>>>(st->keys, st->keys_tmp, st->tile_offsets, smem_keys,
-                                                                    (long long)st->capacity);
+                                                                    (long long)st->capacity, st->geom, st->chan, st->sorted_cull,
+                                                                    st->sorted_rec, sc->G, gx * gy, st->chan_stride / 4);
         if (ls_check_cuda("sort stage")) return -1;
     }
     if (stages & LS_STAGE_BLEND) {
@@ -570,7 +630,7 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
         if (sc->C && !im->feature) return ls_fail("feature image pointer is NULL");
         dim3 grid(gx * gy, sc->n_views);
         switch (nc) {
-#define LS_CASE(N) case N: launch_blend_fwd<N>(*sc, *st, *im, ncol, grid, stream); break;
+#define LS_CASE(N) case N: if (launch_blend_fwd<N>(*sc, *st, *im, ncol, grid, stream)) return -1; break;
             LS_CASE(1) LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
             LS_CASE(9) LS_CASE(10) LS_CASE(11) LS_CASE(12) LS_CASE(13) LS_CASE(14) LS_CASE(15) LS_CASE(16)
 #undef LS_CASE

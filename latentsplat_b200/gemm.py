@@ -16,16 +16,17 @@ from torch import Tensor, nn
 
 from . import _capi
 
-ACT = {"none": _capi.ACT_NONE, "relu": _capi.ACT_RELU, "gelu": _capi.ACT_GELU}
+ACT = {"none": _capi.ACT_NONE, "relu": _capi.ACT_RELU, "gelu": _capi.ACT_GELU, "silu": _capi.ACT_SILU}
 NUM_SMS = 148
 enabled = True          # set False to route CUDA linears through cuBLAS (A/B comparisons)
 
 
 def gemm_tf32(A: Tensor, B: Tensor, *, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
               bias: Optional[Tensor] = None, act: str = "none", out: Optional[Tensor] = None, split_k: int = 0,
-              accumulate: bool = False) -> Tensor:
-    """out[M,N] (+)= op(A)[M,K] @ op(B)[N,K]^T (+ bias) -> act.   A: (M,K) row-major, or (K,M) if a_mn; B likewise.
-    `split_k=0` picks a split that fills the 148 SMs when the output has few tiles (weight gradients)."""
+              accumulate: bool = False, residual: Optional[Tensor] = None, pre_out: Optional[Tensor] = None) -> Tensor:
+    """out[M,N] (+)= act(op(A)[M,K] @ op(B)[N,K]^T (+ bias)) (+ residual).   A: (M,K) row-major, or (K,M) if a_mn; B likewise.
+    `split_k=0` picks a split that fills the 148 SMs when the output has few tiles (weight gradients).
+    `residual` (M,N): added after the activation (a block's skip connection); `pre_out` (M,N): receives the pre-activation."""
     if not (A.is_cuda and B.is_cuda):
         raise RuntimeError("gemm_tf32 needs CUDA tensors: latentsplat_b200 has no CPU fallback")
     assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.dim() == 2 and B.dim() == 2
@@ -37,11 +38,17 @@ def gemm_tf32(A: Tensor, B: Tensor, *, M: int, N: int, K: int, a_mn: bool = Fals
         tiles = ((M + 127) // 128) * ((N + 127) // 128)
         nkb = (K + 31) // 32
         split_k = 1 if tiles >= NUM_SMS else max(1, min(nkb // 4, (2 * NUM_SMS + tiles - 1) // tiles))
-        if act != "none" or (bias is not None and split_k > 1):
+        if act != "none" or (bias is not None and split_k > 1) or residual is not None or pre_out is not None:
             split_k = 1
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.stride(1) == 1 and residual.dtype == torch.float32
+    if pre_out is not None:
+        assert pre_out.shape == (M, N) and pre_out.stride() == out.stride()
     args = _capi.LsGemmArgs(M, N, K, int(a_mn), int(b_mn), ACT[act], int(split_k), int(accumulate), A.stride(0),
                             B.stride(0), out.stride(0), A.data_ptr(), B.data_ptr(), out.data_ptr(),
-                            None if bias is None else bias.data_ptr())
+                            None if bias is None else bias.data_ptr(),
+                            None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
+                            None if pre_out is None else pre_out.data_ptr())
     with torch.cuda.device(A.device):
         _capi.check(_capi.load().ls_gemm_tf32(C.byref(args), torch.cuda.current_stream().cuda_stream), "ls_gemm_tf32")
     _capi.KERNEL_LAUNCHES[0] += 1
@@ -66,20 +73,32 @@ def _aligned(t: Tensor) -> bool:
 
 
 class _LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) (+ residual): bias, ReLU / GELU / SiLU and the skip connection run in the GEMM epilogue; the smooth
+    activations keep their pre-activation (second epilogue output) for the backward pass."""
+
     @staticmethod
-    def forward(ctx, x2d: Tensor, weight: Tensor, bias: Optional[Tensor], act: str):
-        y = gemm_tf32(x2d, weight, M=x2d.shape[0], N=weight.shape[0], K=x2d.shape[1], bias=bias, act=act)
+    def forward(ctx, x2d: Tensor, weight: Tensor, bias: Optional[Tensor], act: str, residual: Optional[Tensor]):
+        M, N = x2d.shape[0], weight.shape[0]
+        pre = torch.empty((M, N), dtype=torch.float32, device=x2d.device) if act in ("gelu", "silu") else None
+        y = gemm_tf32(x2d, weight, M=M, N=N, K=x2d.shape[1], bias=bias, act=act, residual=residual, pre_out=pre)
         ctx.act = act
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x2d, weight, y if act == "relu" else None)
+        # relu: the output's sign IS the mask -- unless a residual was added on top of it
+        if act == "relu" and residual is not None:
+            raise RuntimeError("relu + residual is not wired (no such layer on the path)")
+        ctx.save_for_backward(x2d, weight, y if act == "relu" else pre)
         return y
 
     @staticmethod
     def backward(ctx, gy: Tensor):
-        x2d, weight, y = ctx.saved_tensors
+        x2d, weight, saved = ctx.saved_tensors
         gy = gy.contiguous()
+        g_res = gy if ctx.needs_input_grad[4] else None              # the skip connection passes the gradient through
         if ctx.act == "relu":
-            gy = gy * (y > 0)
+            gy = gy * (saved > 0)
+        elif ctx.act in ("gelu", "silu"):
+            from .conv import act_backward                            # elementwise dy * act'(pre) on our kernel
+            gy = act_backward(gy, saved, ctx.act)
         M, K = x2d.shape
         N = weight.shape[0]
         gx = gw = gb = None
@@ -89,7 +108,7 @@ class _LinearFn(torch.autograd.Function):
             gw = gemm_tf32(gy, x2d, M=N, N=K, K=M, a_mn=True, b_mn=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, g_res
 
 
 class _GroupedLinearFn(torch.autograd.Function):
@@ -132,21 +151,36 @@ def grouped_linear(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     return torch.baddbmm(bias[:, None], x, weight.transpose(1, 2))
 
 
-def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = "none") -> Tensor:
-    """F.linear(+activation) on the tcgen05 GEMM when possible (CUDA fp32, TMA-compatible strides)."""
-    if x.is_cuda and enabled and x.dtype == torch.float32 and weight.dtype == torch.float32 and act != "gelu":
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = "none",
+           residual: Optional[Tensor] = None) -> Tensor:
+    """act(F.linear(x, weight, bias)) (+ residual) on the tcgen05 GEMM when possible (CUDA fp32, TMA-compatible strides);
+    act in "none" | "relu" | "gelu" | "silu".  `residual` has the output's shape."""
+    N = weight.shape[0]
+    if x.is_cuda and enabled and x.dtype == torch.float32 and weight.dtype == torch.float32:
         x2d = x.reshape(-1, x.shape[-1])
         if not x2d.is_contiguous():
             x2d = x2d.contiguous()
-        K, N = x2d.shape[1], weight.shape[0]
+        K = x2d.shape[1]
+        r2d = None
+        if residual is not None:
+            r2d = residual.reshape(-1, N)
+            if not r2d.is_contiguous():
+                r2d = r2d.contiguous()
         if K % 4 == 0 and N % 4 == 0 and _aligned(x2d) and _aligned(weight) and x2d.shape[0] > 0:
-            return _LinearFn.apply(x2d, weight, bias, act).reshape(*x.shape[:-1], N)
+            return _LinearFn.apply(x2d, weight, bias, act, r2d).reshape(*x.shape[:-1], N)
     y = F.linear(x, weight, bias)
-    return F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
+    y = F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else F.silu(y) if act == "silu" else y
+    return y if residual is None else y + residual
 
 
 class Linear(nn.Linear):
-    """nn.Linear whose CUDA path is our tcgen05 TF32 GEMM (parameters: `weight`, `bias`, as nn.Linear)."""
+    """nn.Linear whose CUDA path is our tcgen05 TF32 GEMM (parameters: `weight`, `bias`, as nn.Linear).  `act` fuses the
+    following activation, `residual=` at call time the block's skip connection, into the GEMM epilogue."""
 
-    def forward(self, input: Tensor) -> Tensor:
-        return linear(input, self.weight, self.bias)
+    def __init__(self, *args, act: str = "none", **kwargs):
+        super().__init__(*args, **kwargs)
+        assert act in ACT
+        self.act = act
+
+    def forward(self, input: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        return linear(input, self.weight, self.bias, self.act, residual)

@@ -39,8 +39,9 @@ class BackboneDino(Backbone[BackboneDinoCfg]):
         self.dino = build_dino(cfg.model)
         d = CONFIGS[cfg.model][1]
         # NB: the reference hard-codes 768 (ViT-B); ViT-S checkpoints would not fit it either.
-        self.global_token_mlp = nn.Sequential(Linear(d, d), nn.ReLU(), Linear(d, self.d_out))
-        self.local_token_mlp = nn.Sequential(Linear(d, d), nn.ReLU(), Linear(d, self.d_out))
+        # Linear, ReLU, Linear (:34-43); the ReLU runs in the first GEMM's epilogue, an Identity keeps the Sequential indices
+        self.global_token_mlp = nn.Sequential(Linear(d, d, act="relu"), nn.Identity(), Linear(d, self.d_out))
+        self.local_token_mlp = nn.Sequential(Linear(d, d, act="relu"), nn.Identity(), Linear(d, self.d_out))
 
     @property
     def patch_size(self) -> int:

@@ -21,12 +21,13 @@ from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias g
 class Mlp(nn.Module):
     def __init__(self, dim: int, hidden: int):
         super().__init__()
-        self.fc1 = Linear(dim, hidden)
-        self.act = nn.GELU()
+        self.fc1 = Linear(dim, hidden, act="gelu")          # GELU in the GEMM epilogue (pre-activation kept for backward)
+        self.act = nn.Identity()                             # upstream: nn.GELU() here (no parameters: checkpoint-neutral)
         self.fc2 = Linear(hidden, dim)
 
-    def forward(self, x):
-        return self.fc2(self.act(self.fc1(x)))
+    def forward(self, x, residual=None):
+        """fc2(gelu(fc1(x))) (+ residual): the block's skip connection rides in fc2's epilogue."""
+        return self.fc2(self.act(self.fc1(x)), residual=residual)
 
 
 class _Bf16AttentionCore(torch.autograd.Function):
@@ -73,15 +74,16 @@ class Attention(nn.Module):
         self.qkv = Linear(dim, dim * 3, bias=True)
         self.proj = Linear(dim, dim)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """proj(attention(qkv(x))) (+ residual): the block's skip connection rides in proj's epilogue."""
         B, N, C = x.shape
         qkv = self.qkv(x)
         if x.is_cuda and ATTENTION_BF16:
             # library flash-attention on a bf16 copy of q/k/v (fp32 SDPA lands on an sm_80 SIMT kernel: 30 ms/step)
-            return self.proj(_Bf16AttentionCore.apply(qkv, self.num_heads, self.scale))
+            return self.proj(_Bf16AttentionCore.apply(qkv, self.num_heads, self.scale), residual=residual)
         qkv = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
-        return self.proj(x.transpose(1, 2).reshape(B, N, C))
+        return self.proj(x.transpose(1, 2).reshape(B, N, C), residual=residual)
 
 
 class Block(nn.Module):
@@ -93,8 +95,8 @@ class Block(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x):
-        x = x + self.attn(self.norm1(x))
-        return x + self.mlp(self.norm2(x))
+        x = self.attn(self.norm1(x), residual=x)             # x + attn(norm1(x))
+        return self.mlp(self.norm2(x), residual=x)           # x + mlp(norm2(x))
 
 
 class PatchEmbed(nn.Module):

@@ -22,11 +22,19 @@ class FeedForward(nn.Module):
 
     def __init__(self, dim: int, hidden_dim: int, dropout: float = 0.0) -> None:
         super().__init__()
-        stages = [Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout), Linear(hidden_dim, dim), nn.Dropout(dropout)]
+        # reference: Linear, GELU, Dropout, Linear, Dropout.  The GELU runs in the first Linear's GEMM epilogue (an Identity
+        # keeps the Sequential indices net.0 / net.3 of the checkpoint), the block's skip connection in the second one's.
+        stages = [Linear(dim, hidden_dim, act="gelu"), nn.Identity(), nn.Dropout(dropout), Linear(hidden_dim, dim),
+                  nn.Dropout(dropout)]
         self.net = nn.Sequential(*stages)
+        self.fused_residual = dropout == 0.0          # (x + Dropout(y) != Dropout(x + y) when dropout is active)
 
-    def forward(self, x: Tensor) -> Tensor:
-        return self.net(x)
+    def forward(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        if residual is None or not self.fused_residual:
+            y = self.net(x)
+            return y if residual is None else y + residual
+        h = self.net[2](self.net[1](self.net[0](x)))
+        return self.net[4](self.net[3](h, residual=residual))
 
 
 class PreNorm(nn.Module):
@@ -54,5 +62,5 @@ class Transformer(nn.Module):
     def forward(self, x: Tensor, z: Optional[Tensor] = None, **kwargs) -> Tensor:
         for attn, ff in self.layers:
             x = attn(x, z=z) + x
-            x = ff(x, **kwargs) + x
+            x = ff(x, residual=x) if isinstance(ff.fn, FeedForward) else ff(x, **kwargs) + x
         return x

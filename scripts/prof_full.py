@@ -6,6 +6,7 @@ cfg = dict(bench.CFG, workload='full')
 dev = torch.device('cuda:0')
 torch.backends.cudnn.benchmark = True
 pipe, params = bench.build_pipeline(dev)
+pipe.encoder.backbone.dino = pipe.encoder.backbone.dino if hasattr(pipe.encoder.backbone, "dino") else None
 flat = {k: v.to(dev) for k, v in bench.flatten_batch(bench.make_full_batch(cfg, 0)).items()}
 if len(sys.argv) > 1 and sys.argv[1] == 'tf32':
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -50,6 +51,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 ka = sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)
 tot = sum(e.self_device_time_total for e in ka)
 print(f"Self CUDA total {tot/1e3:.1f} ms")
+print("---- aten ops (self device time) ----")
+for e in [e for e in ka if e.key.startswith('aten::')][:45]:
+    print(f"{e.self_device_time_total/1e3:9.2f} ms {100*e.self_device_time_total/tot:5.1f}% {e.count:5d}x  {e.key[:110]}")
+print("---- kernels ----")
 ka = [e for e in ka if not e.key.startswith('aten::') and e.key not in ('FWD','BWD') and 'Backward' not in e.key and not e.key.startswith('_') and 'autograd' not in e.key]
 for e in ka[:50]:
     print(f"{e.self_device_time_total/1e3:9.2f} ms {100*e.self_device_time_total/tot:5.1f}% {e.count:5d}x  {e.key[:110]}")

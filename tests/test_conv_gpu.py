@@ -37,6 +37,8 @@ CONV_CASES = [
     (2, 40, 8, 8, 72, 1, 1, 0),          # 1x1 shortcut, channel tails
     (1, 8, 256, 256, 16, 3, 1, 1),       # full-width rows (BW = 128)
     (2, 4, 64, 64, 96, 8, 8, 0),         # DINO patch embedding: 8x8 stride 8 on a (padded) RGB image
+    (2, 256, 16, 16, 256, 3, 1, 1),      # 256 channels both ways: the cta_group::2 kernels (forward, dgrad, wgrad) when forced
+    (1, 256, 32, 40, 512, 4, 2, 1),      # strided, two channel pairs, ragged width
 ]
 
 

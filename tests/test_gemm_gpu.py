@@ -316,3 +316,24 @@ def test_col_sum_matches_torch(cuda, rows, cols, ld):
     got, want = col_sum(x).double(), x.double().sum(dim=0)
     assert got.shape == want.shape
     assert (got - want).abs().max().item() <= 1e-5 * x.abs().double().sum(dim=0).max().item() + 1e-6
+
+
+@pytest.mark.parametrize("act", ["none", "gelu", "silu"])
+def test_linear_fused_activation_and_residual(cuda, act):
+    """gemm.linear(act=, residual=): act(x W^T + b) + residual in ONE GEMM epilogue (+ the pre-activation kept for backward);
+    output and all four gradients against float64 torch."""
+    from latentsplat_b200.gemm import linear
+    g = torch.Generator(cuda).manual_seed(8)
+    x = torch.randn(3, 333, 128, device=cuda, generator=g, requires_grad=True)
+    w = (torch.randn(256, 128, device=cuda, generator=g) / 128 ** 0.5).requires_grad_(True)
+    b = torch.randn(256, device=cuda, generator=g, requires_grad=True)
+    r = torch.randn(3, 333, 256, device=cuda, generator=g, requires_grad=True)
+    wt = torch.randn(3, 333, 256, device=cuda, generator=g)
+    y = linear(x, w, b, act=act, residual=r)
+    gx, gw, gb, gr = torch.autograd.grad(y, (x, w, b, r), wt)
+    xd, wd, bd, rd = (t.detach().double().requires_grad_(True) for t in (x, w, b, r))
+    fn = {"none": lambda t: t, "gelu": torch.nn.functional.gelu, "silu": torch.nn.functional.silu}[act]
+    ref = fn(torch.nn.functional.linear(xd, wd, bd)) + rd
+    rx, rw, rb, rr = torch.autograd.grad(ref, (xd, wd, bd, rd), wt.double())
+    for a, e, name, tol in ((y, ref.detach(), "y", 2e-2), (gx, rx, "dx", 2e-2), (gw, rw, "dW", 2e-2), (gb, rb, "db", 1e-3), (gr, rr, "dres", 1e-6)):
+        assert (a.double() - e).abs().max().item() <= tol * e.abs().max().item() + 1e-6, f"{name}: {(a.double() - e).abs().max().item():.3e}"
