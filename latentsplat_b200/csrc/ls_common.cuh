@@ -216,6 +216,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 // over the FLAT (row, element) index -- consecutive lanes touch consecutive addresses inside a row piece -- through a
 // small per-warp shared buffer (32 x 25 floats; pitch 25 is odd, so the per-lane row reads are conflict-free).
 constexpr int kStagePitch = 25;
+constexpr int kChunk = 24;       // floats per row and pass of the backward SH staging: 8 colour coefficients = 3 whole sectors
 
 __device__ __forceinline__ void stage_load(float* __restrict__ buf, const float* __restrict__ base, int row_len, int c0,
                                            int len, int nrows, int lane) {

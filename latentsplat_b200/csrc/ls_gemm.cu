@@ -36,9 +36,9 @@ constexpr int BM = 128, BK = 32;              // BK fp32 = 128 B = one swizzle r
 constexpr int UMMA_K = 8;                    // 32 B of tf32 per instruction
 constexpr int A_BYTES = BM * BK * 4;
 __host__ __device__ constexpr int stage_bytes(int bn) { return A_BYTES + bn * BK * 4; }
-constexpr int kThreads = 256;
-constexpr int PITCH = 36;                                   // floats; 144-B rows: conflict-free float4 access
-constexpr int PATCH_BYTES = 4 * 32 * PITCH * 4;              // one 32 x 32 transpose patch per epilogue warp
+constexpr int kThreads = 384;                               // warps 0-3: producer, MMA issuer, TMEM allocator, (idle); 4-11: epilogue
+constexpr int kEpiWarps = 8;
+constexpr int PATCH_BYTES = kEpiWarps * 32 * 32 * 4;         // one XOR-swizzled 32 x 32 transpose patch (4 KB) per epilogue warp
 constexpr int smem_bytes(int stages, int bn) { return stages * stage_bytes(bn) + PATCH_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/; }
 
 using namespace lstc;   // mbarrier / TMA / tcgen05 wrappers, make_desc, sts128 / lds128 (ls_tc.cuh)
@@ -49,6 +49,91 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == LS_ACT_SILU) return v / (1.f + __expf(-v));
     if (act == LS_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
     return v;
+}
+
+// One epilogue warp's share of one output tile.  The accumulator arrives "one row per lane" (tcgen05.ld 32x32b); writing it
+// out like that would touch 32 different rows per store instruction, so the warp transposes each 32 x 32 chunk through a
+// private 4 KB shared-memory patch (16-byte units XOR-swizzled with the row: conflict-free both ways) and stores 4 rows x 128
+// contiguous bytes per instruction.  EIGHT epilogue warps share a tile: warp w reads TMEM lanes (w % 4) * 32.. and takes the
+// column chunks of parity (w - 4) / 4 -- with four warps the erf of a fused GELU (+54 % on the DINO fc1 shape) and above all
+// the skip-connection read (3x: a dependent DRAM round trip per row and chunk) serialised behind the tensor core.  The
+// residual rows of a chunk are therefore requested BEFORE the accumulator is fetched and transposed.
+template <int BN>
+__device__ __forceinline__ void epilogue_chunks(const uint32_t tmem_acc, const uint32_t patch_s, const int lane, const int half,
+                                                const int row_base, const int col_base, const int M, const int N,
+                                                float* __restrict__ C, const long long ldc, const float* __restrict__ bias,
+                                                const int act, const int atomic, const float* __restrict__ residual,
+                                                const long long ldr, float* __restrict__ pre_out, const bool vec_ok,
+                                                const bool res_vec) {
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    const bool fast = !atomic && vec_ok;
+    const bool pre_res = fast && residual != nullptr && res_vec;
+#pragma unroll 1
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        const int col0 = col_base + c0;
+        if (col0 >= N) break;                                   // warp-uniform
+        const int col = col0 + sub_c;
+        float4 res4[8];
+        if (pre_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = row_base + 4 * i + sub_r;
+                res4[i] = (row < M && col + 3 < N) ? __ldg(reinterpret_cast<const float4*>(residual + (long long)row * ldr + col))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        uint32_t r[32];
+        tc_ld32(tmem_acc + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            sts128(patch_s + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4), __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias != nullptr) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (col + t < N) b4[t] = bias[col + t];
+        }
+        float4 rows4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + sub_r;
+            rows4[i] = lds128(patch_s + rr * 128 + ((((lane & 7) ^ (rr & 7))) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + sub_r;
+            const float4 v4 = rows4[i];
+            const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
+            float v[4] = {apply_act(pre[0], act), apply_act(pre[1], act), apply_act(pre[2], act), apply_act(pre[3], act)};
+            if (row < M) {
+                float* dst = C + (long long)row * ldc + col;
+                if (fast && col + 3 < N) {
+                    if (pre_res) {
+                        v[0] += res4[i].x; v[1] += res4[i].y; v[2] += res4[i].z; v[3] += res4[i].w;
+                    } else if (residual != nullptr) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) v[t] += residual[(long long)row * ldr + col + t];
+                    }
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (pre_out != nullptr)
+                        *reinterpret_cast<float4*>(pre_out + (long long)row * ldc + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (col + t < N) {
+                            if (atomic) {
+                                atomicAdd(dst + t, v[t]);
+                            } else {
+                                dst[t] = residual != nullptr ? v[t] + residual[(long long)row * ldr + col + t] : v[t];
+                                if (pre_out != nullptr) pre_out[(long long)row * ldc + col + t] = pre[t];
+                            }
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // Persistent: each CTA walks the work list  item = blockIdx.x + i * gridDim.x  (item -> n-tile fastest, then m-tile,
@@ -63,7 +148,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     constexpr int STAGE_BYTES = stage_bytes(BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                    // 4 x 32 x 36 floats
+    float* patches = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                    // 8 x 4 KB swizzled patches
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PATCH_BYTES);    // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
@@ -81,7 +166,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -157,13 +242,9 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tc_commit(tfull0 + 8 * acc);            // accumulator complete
         }
     } else if (warp >= 4) {
-        // ------------------------------ epilogue ----------------------------------
-        // The accumulator arrives "one row per lane" (tcgen05.ld 32x32b).  Writing it out like that would touch 32
-        // different rows per store instruction; each warp therefore transposes its 32 x 32 chunk through a private
-        // 4.5 KB shared-memory patch and stores 4 rows x 128 contiguous bytes per instruction.
-        const int q = warp - 4;                  // TMEM lane quarter == warp % 4
-        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        // ------------------------------ epilogue (8 warps) ------------------------
+        const int q = warp & 3, half = (warp - 4) >> 2;          // TMEM lane quarter == warp % 4; even / odd column chunks
+        const uint32_t patch_s = smem_u32(patches) + (uint32_t)(warp - 4) * 4096u;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                             (pre_out == nullptr || (reinterpret_cast<uintptr_t>(pre_out) & 15) == 0);
         const bool res_vec = (ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0);
@@ -174,65 +255,12 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
             mbar_wait(tfull0 + 8 * acc, acc_ph);
             tc_fence_after();
-            const bool add_bias = bias != nullptr && kb0 == 0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int col0 = tile_n * BN + c0;
-                if (col0 >= N) break;                                   // warp-uniform
-                uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                __syncwarp();
-                const int col = col0 + sub_c;
-                float b4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (add_bias) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) if (col + t < N) b4[t] = bias[col + t];
-                }
-                float4 rows4[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = tile_m * BM + q * 32 + 4 * i + sub_r;
-                    const float4 v4 = rows4[i];
-                    const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
-                    float v[4] = {apply_act(pre[0], act), apply_act(pre[1], act), apply_act(pre[2], act), apply_act(pre[3], act)};
-                    if (row < M) {
-                        float* dst = C + (long long)row * ldc + col;
-                        if (!atomic && vec_ok && col + 3 < N) {
-                            if (residual != nullptr && res_vec) {
-                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(residual + (long long)row * ldr + col));
-                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-                            } else if (residual != nullptr) {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) v[t] += residual[(long long)row * ldr + col + t];
-                            }
-                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                            if (pre_out != nullptr)
-                                *reinterpret_cast<float4*>(pre_out + (long long)row * ldc + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-                                if (col + t < N) {
-                                    if (atomic) {
-                                        atomicAdd(dst + t, v[t]);
-                                    } else {
-                                        dst[t] = residual != nullptr ? v[t] + residual[(long long)row * ldr + col + t] : v[t];
-                                        if (pre_out != nullptr) pre_out[(long long)row * ldc + col + t] = pre[t];
-                                    }
-                                }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            epilogue_chunks<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), patch_s, lane, half,
+                                tile_m * BM + q * 32, tile_n * BN, M, N, C, ldc, (bias != nullptr && kb0 == 0) ? bias : nullptr, act,
+                                atomic, residual, ldr, pre_out, vec_ok, res_vec);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // 4 arrivals release the accumulator
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // 8 arrivals release the accumulator
         }
     }
     tc_fence_before();
@@ -319,7 +347,7 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -395,10 +423,9 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_commit_2sm(tfull0 + 8 * acc);         // accumulator complete, both CTAs
         }
     } else if (warp >= 4) {
-        // ------------------------------ epilogue (both CTAs, own 128 rows) --------------------
-        const int q = warp - 4;
-        const uint32_t patch_s = smem_u32(patches + q * 32 * PITCH);
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        // ------------------------------ epilogue (both CTAs, own 128 rows, 8 warps each) ------
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const uint32_t patch_s = smem_u32(patches) + (uint32_t)(warp - 4) * 4096u;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                             (pre_out == nullptr || (reinterpret_cast<uintptr_t>(pre_out) & 15) == 0);
         const bool res_vec = (ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0);
@@ -409,66 +436,12 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t acc = local & 1, acc_ph = (local >> 1) & 1;
             mbar_wait(tfull0 + 8 * acc, acc_ph);
             tc_fence_after();
-            const bool add_bias = bias != nullptr && kb0 == 0;
-            const int row_base = tile_m * 2 * BM + (int)rank * BM + q * 32;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int col0 = tile_n * BN + c0;
-                if (col0 >= N) break;
-                uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    sts128(patch_s + (lane * PITCH + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                __syncwarp();
-                const int col = col0 + sub_c;
-                float b4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (add_bias) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) if (col + t < N) b4[t] = bias[col + t];
-                }
-                float4 rows4[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rows4[i] = lds128(patch_s + ((4 * i + sub_r) * PITCH + sub_c) * 4);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = row_base + 4 * i + sub_r;
-                    const float4 v4 = rows4[i];
-                    const float pre[4] = {v4.x + b4[0], v4.y + b4[1], v4.z + b4[2], v4.w + b4[3]};
-                    float v[4] = {apply_act(pre[0], act), apply_act(pre[1], act), apply_act(pre[2], act), apply_act(pre[3], act)};
-                    if (row < M) {
-                        float* dst = C + (long long)row * ldc + col;
-                        if (!atomic && vec_ok && col + 3 < N) {
-                            if (residual != nullptr && res_vec) {
-                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(residual + (long long)row * ldr + col));
-                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-                            } else if (residual != nullptr) {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) v[t] += residual[(long long)row * ldr + col + t];
-                            }
-                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                            if (pre_out != nullptr)
-                                *reinterpret_cast<float4*>(pre_out + (long long)row * ldc + col) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-                                if (col + t < N) {
-                                    if (atomic) {
-                                        atomicAdd(dst + t, v[t]);
-                                    } else {
-                                        dst[t] = residual != nullptr ? v[t] + residual[(long long)row * ldr + col + t] : v[t];
-                                        if (pre_out != nullptr) pre_out[(long long)row * ldc + col + t] = pre[t];
-                                    }
-                                }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            epilogue_chunks<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), patch_s, lane, half,
+                                tile_m * 2 * BM + (int)rank * BM + q * 32, tile_n * BN, M, N, C, ldc,
+                                (bias != nullptr && kb0 == 0) ? bias : nullptr, act, atomic, residual, ldr, pre_out, vec_ok, res_vec);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader(tempty0 + 8 * acc);    // 8 arrivals (2 CTAs x 4 warps) release it
+            if (lane == 0) mbar_arrive_leader(tempty0 + 8 * acc);    // 16 arrivals (2 CTAs x 8 warps) release it
         }
     }
     tc_fence_before();

@@ -21,6 +21,7 @@
 namespace lsnh {
 
 constexpr int kThreads = 256;
+constexpr int kUnroll = 4;        // pixels per thread and loop trip (loads issued back to back)
 
 __device__ __forceinline__ float silu(float u) { return u / (1.f + __expf(-u)); }
 __device__ __forceinline__ float dsilu(float u, float g) {
@@ -72,21 +73,33 @@ __global__ void __launch_bounds__(kThreads) k_gn_nhwc_sums(const float* __restri
     if (prow < rows) {
         const float* xp = x + ((long long)n * HW) * C + c;
         const float* gp = BWD ? dy + ((long long)n * HW) * C + c : nullptr;
-        for (long long p = lo + prow; p < hi; p += rows) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(xp + p * C));
-            const float xs[4] = {v.x, v.y, v.z, v.w};
-            if (!BWD) {
+        // kUnroll pixels per thread and trip: all loads of a trip are issued before the first use (bytes in flight, not
+        // occupancy, is what keeps an HBM-bound streaming kernel fed: 2 x 4 x 16 B per thread here)
+        for (long long p0 = lo + prow; p0 < hi; p0 += (long long)kUnroll * rows) {
+            float4 v[kUnroll], d[kUnroll];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { a0[k] += xs[k]; a1[k] = fmaf(xs[k], xs[k], a1[k]); }
-            } else {
-                const float4 d = __ldg(reinterpret_cast<const float4*>(gp + p * C));
-                const float ds_[4] = {d.x, d.y, d.z, d.w};
+            for (int u = 0; u < kUnroll; ++u) {
+                const long long p = p0 + (long long)u * rows;
+                const bool ok = p < hi;
+                v[u] = ok ? __ldg(reinterpret_cast<const float4*>(xp + p * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BWD) d[u] = ok ? __ldg(reinterpret_cast<const float4*>(gp + p * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float xh = (xs[k] - mean[k]) * rstd[k];
-                    const float ds = ACT ? dsilu(fmaf(xh, gm[k], bt[k]), ds_[k]) : ds_[k];
-                    a0[k] += ds;
-                    a1[k] = fmaf(ds, xh, a1[k]);
+            for (int u = 0; u < kUnroll; ++u) {
+                if (p0 + (long long)u * rows >= hi) break;
+                const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                if (!BWD) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { a0[k] += xs[k]; a1[k] = fmaf(xs[k], xs[k], a1[k]); }
+                } else {
+                    const float ds_[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float xh = (xs[k] - mean[k]) * rstd[k];
+                        const float ds = ACT ? dsilu(fmaf(xh, gm[k], bt[k]), ds_[k]) : ds_[k];
+                        a0[k] += ds;
+                        a1[k] = fmaf(ds, xh, a1[k]);
+                    }
                 }
             }
         }
@@ -122,11 +135,22 @@ __global__ void __launch_bounds__(kThreads) k_gn_nhwc_apply(const float* __restr
     if (hi > HW) hi = HW;
     const float* xp = x + ((long long)n * HW) * C + c;
     float* yp = y + ((long long)n * HW) * C + c;
-    for (long long p = lo + prow; p < hi; p += rows) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(xp + p * C));
-        v.x = fmaf(a[0], v.x, b[0]); v.y = fmaf(a[1], v.y, b[1]); v.z = fmaf(a[2], v.z, b[2]); v.w = fmaf(a[3], v.w, b[3]);
-        if (ACT) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
-        *reinterpret_cast<float4*>(yp + p * C) = v;
+    for (long long p0 = lo + prow; p0 < hi; p0 += (long long)kUnroll * rows) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long p = p0 + (long long)u * rows;
+            if (p < hi) v[u] = __ldg(reinterpret_cast<const float4*>(xp + p * C));
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long p = p0 + (long long)u * rows;
+            if (p >= hi) break;
+            float4 w = v[u];
+            w.x = fmaf(a[0], w.x, b[0]); w.y = fmaf(a[1], w.y, b[1]); w.z = fmaf(a[2], w.z, b[2]); w.w = fmaf(a[3], w.w, b[3]);
+            if (ACT) { w.x = silu(w.x); w.y = silu(w.y); w.z = silu(w.z); w.w = silu(w.w); }
+            *reinterpret_cast<float4*>(yp + p * C) = w;
+        }
     }
 }
 
@@ -164,18 +188,30 @@ __global__ void __launch_bounds__(kThreads) k_gn_nhwc_bwd_apply(const float* __r
     const float* xp = x + ((long long)n * HW) * C + c;
     const float* gp = dy + ((long long)n * HW) * C + c;
     float* op = dx + ((long long)n * HW) * C + c;
-    for (long long p = lo + prow; p < hi; p += rows) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(xp + p * C));
-        const float4 d = __ldg(reinterpret_cast<const float4*>(gp + p * C));
-        const float xs[4] = {v.x, v.y, v.z, v.w}, ds_[4] = {d.x, d.y, d.z, d.w};
-        float r[4];
+    for (long long p0 = lo + prow; p0 < hi; p0 += (long long)kUnroll * rows) {
+        float4 v[kUnroll], d[kUnroll];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float xh = (xs[k] - mean[k]) * rstd[k];
-            const float ds = ACT ? dsilu(fmaf(xh, gm[k], bt[k]), ds_[k]) : ds_[k];
-            r[k] = rstd[k] * (fmaf(gm[k], ds, -pm[k]) - xh * qm[k]);
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long p = p0 + (long long)u * rows;
+            if (p < hi) {
+                v[u] = __ldg(reinterpret_cast<const float4*>(xp + p * C));
+                d[u] = __ldg(reinterpret_cast<const float4*>(gp + p * C));
+            }
         }
-        *reinterpret_cast<float4*>(op + p * C) = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long p = p0 + (long long)u * rows;
+            if (p >= hi) break;
+            const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ds_[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+            float r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xh = (xs[k] - mean[k]) * rstd[k];
+                const float ds = ACT ? dsilu(fmaf(xh, gm[k], bt[k]), ds_[k]) : ds_[k];
+                r[k] = rstd[k] * (fmaf(gm[k], ds, -pm[k]) - xh * qm[k]);
+            }
+            *reinterpret_cast<float4*>(op + p * C) = make_float4(r[0], r[1], r[2], r[3]);
+        }
     }
 }
 

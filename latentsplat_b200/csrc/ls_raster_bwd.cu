@@ -8,14 +8,17 @@
 //   * per-pixel state is a scalar: with g = dL/dpixel, the lineage's per-channel
 //     `accum_rec[ch]` recurrence is linear, so A = sum_ch accum_rec[ch]*g[ch] obeys the
 //     same recurrence with sum_ch c[ch]*g[ch]; registers drop from 3*NC to NC+4;
-//   * the 7+NC per-Gaussian partial sums of a warp are reduced with shuffles and
-//     leave the SM as ONE red.global.add instruction of 7+NC lanes into a packed
+//   * the 7+NC per-Gaussian partial sums of a warp are reduced with a transposing
+//     shuffle butterfly and leave the SM as 16-byte red.global.add.v4.f32 into a packed
 //     64-byte gradient record, instead of (9+NC) atomics per pixel-Gaussian pair;
-//   * warp-uniform skip of Gaussians that contribute to none of the warp's pixels;
+//   * the tile queues arrive through 1-D bulk TMA copies of the permuted-after-sort
+//     records, and each warp compacts the queue against its 16x2 strip before the
+//     replay (see ls_raster_fwd.cu);
 //   * depth and alpha (mask) are differentiable channels; all views in one launch;
 //   * gradients of inputs shared by the views of a scene are accumulated in-kernel.
 #include "ls_common.cuh"
 #include "ls_host.h"
+#include "ls_tc.cuh"
 
 namespace ls {
 
@@ -27,17 +30,19 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
                                                            const LsRasterGrads gr, const int ncol) {
     constexpr int CS = (NC + 3) & ~3;
     constexpr int CV = CS / 4;
-    constexpr int K = 7 + NC;  // values reduced per Gaussian
-    extern __shared__ __align__(16) float4 s_dyn[];
-    float4(*s_geom)[kTilePixels][2] = reinterpret_cast<float4(*)[kTilePixels][2]>(s_dyn);
-    float4(*s_chan)[kTilePixels][CV] = reinterpret_cast<float4(*)[kTilePixels][CV]>(s_dyn + 2 * kTilePixels * 2);
-    uint32_t(*s_id)[kTilePixels] = reinterpret_cast<uint32_t(*)[kTilePixels]>(s_dyn + 2 * kTilePixels * (2 + CV));
+    constexpr int RV = 2 + CV;         // float4 per queue record
+    constexpr int K = 7 + NC;          // values reduced per Gaussian
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    float4* s_rec = reinterpret_cast<float4*>(s_dyn);                                   // [2][kBatch][RV]
+    float4* s_cull = s_rec + 2 * kBatch * RV;                                           // [2][kBatch]
+    uint8_t* s_list = reinterpret_cast<uint8_t*>(s_cull + 2 * kBatch);                  // [8 warps][kBatch]
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_max;
 
     const int gx = (sc.W + kTile - 1) / kTile, gy = (sc.H + kTile - 1) / kTile;
     const int tile = blockIdx.x, v = blockIdx.y;
     const int tx = tile % gx, ty = tile / gx;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = tx * kTile + (tid & 15), py = ty * kTile + (tid >> 4);
     const bool inside = px < sc.W && py < sc.H;
     const float fxp = (float)px, fyp = (float)py;
@@ -73,7 +78,8 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
                 if (c < NC) bg_dot = fmaf(bg[c], g[c], bg_dot);
         }
     }
-    if (tid == 0) s_max = 0;
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+    if (tid == 0) { s_max = 0; mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_fence_init(); }
     __syncthreads();
     {
         uint32_t m = last;
@@ -87,49 +93,57 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
     __syncthreads();
     const int n = (int)s_max;  // list entries any pixel of the tile used
     if (n == 0) return;
-    const int nb = (n + kTilePixels - 1) / kTilePixels;
+    const int nb = (n + kBatch - 1) / kBatch;
 
-    const uint64_t* __restrict__ keys = st.keys + s;
-    const float* __restrict__ geom = st.geom + (size_t)v * sc.G * LS_GEOM_STRIDE;
-    const float* __restrict__ chan = st.chan + (size_t)v * sc.G * CS;
-    float* __restrict__ rec = gr.dL_drecord + (size_t)v * sc.G * gr.grad_stride;
+    float* __restrict__ rec_out = gr.dL_drecord + (size_t)v * sc.G * gr.grad_stride;
 
-    auto prefetch = [&](int b, int buf) {
-        const int j = b * kTilePixels + tid;
-        if (j < n) {
-            const uint32_t id = (uint32_t)keys[j];
-            s_id[buf][tid] = id;
-            const float* gsrc = geom + (size_t)id * LS_GEOM_STRIDE;
-            cp_async16(&s_geom[buf][tid][0], gsrc);
-            cp_async16(&s_geom[buf][tid][1], gsrc + 4);
-            const float* csrc = chan + (size_t)id * CS;
-#pragma unroll
-            for (int q = 0; q < CV; ++q) cp_async16(&s_chan[buf][tid][q], csrc + 4 * q);
-        }
-        cp_async_commit();
+    // batches are consumed back to front; `it` counts consumed batches (buffer = it & 1, barrier phase = (it >> 1) & 1)
+    auto stage = [&](int b, int buf) {
+        const int cnt = min(kBatch, n - b * kBatch);
+        const uint32_t bar = bar0 + 8 * buf;
+        const long long first = s + (long long)b * kBatch;
+        mbar_expect_tx(bar, (uint32_t)cnt * (16u + 16u * RV));
+        bulk_load(smem_u32(s_rec + buf * kBatch * RV), reinterpret_cast<const float4*>(st.sorted_rec) + first * RV, (uint32_t)cnt * 16u * RV, bar);
+        bulk_load(smem_u32(s_cull + buf * kBatch), reinterpret_cast<const float4*>(st.sorted_cull) + first, (uint32_t)cnt * 16u, bar);
     };
 
     const float wx = (float)(tx * kTile) + 7.5f;                       // centre of the warp's 16x2 strip
-    const float wy = (float)(ty * kTile + 2 * (tid >> 5)) + 0.5f;
+    const float wy = (float)(ty * kTile + 2 * warp) + 0.5f;
     float T = T_final;
     float A = 0.f, last_alpha = 0.f, last_cg = 0.f;
     const float half_w = 0.5f * (float)sc.W, half_h = 0.5f * (float)sc.H;
+    uint8_t* my_list = s_list + warp * kBatch;
 
     int it = 0;
-    prefetch(nb - 1, 0);
+    if (tid == 0) stage(nb - 1, 0);
     for (int b = nb - 1; b >= 0; --b, ++it) {
         const int buf = it & 1;
-        if (b > 0) { prefetch(b - 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
-        const int cnt = min(kTilePixels, n - b * kTilePixels);
-        const float4(*sg)[2] = s_geom[buf];
-        const float4(*sc4)[CV] = s_chan[buf];
-        for (int j = cnt - 1; j >= 0; --j) {
-            const uint32_t pos = (uint32_t)(b * kTilePixels + j);
-            const float4 g0 = sg[j][0];
-            const float4 g1 = sg[j][1];
-            const float2 ext = unpack_extent(g1.w);
-            if (fabsf(g0.y - wy) > ext.y + 0.5f || fabsf(g0.x - wx) > ext.x + 7.5f) continue;  // warp-uniform
+        if (b > 0 && tid == 0) stage(b - 1, buf ^ 1);                  // released by the barrier that ended the previous round
+        mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        const int cnt = min(kBatch, n - b * kBatch);
+        const float4* cull = s_cull + buf * kBatch;
+        const float4* rec = s_rec + buf * kBatch * RV;
+        // ---- phase A: compaction (ascending list order), as in the forward kernel
+        int nsurv = 0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int j = k0 + lane;
+            bool keep = false;
+            if (j < cnt) {
+                const float4 c = cull[j];
+                const float2 ext = unpack_extent(c.z);
+                keep = fabsf(c.y - wy) <= ext.y + 0.5f && fabsf(c.x - wx) <= ext.x + 7.5f;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) my_list[nsurv + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+            nsurv += __popc(m);
+        }
+        __syncwarp();
+        // ---- phase B: back-to-front replay over the survivors
+        for (int i = nsurv - 1; i >= 0; --i) {
+            const int j = my_list[i];
+            const uint32_t pos = (uint32_t)(b * kBatch + j);
+            const float4 g0 = rec[j * RV], g1 = rec[j * RV + 1];
             const float dx = g0.x - fxp, dy = g0.y - fyp;
             const float p2 = fmaf(g0.z * dx, dx, fmaf(g1.x * dy, dy, g0.w * dx * dy));
             const float Gv = ex2_approx(p2);
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
                 float cg = fmaf(g1.z, g_d, g_a);  // depth * g_d + 1 * g_a
 #pragma unroll
                 for (int q = 0; q < CV; ++q) {
-                    const float4 cq = sc4[j][q];
+                    const float4 cq = rec[j * RV + 2 + q];
                     if (4 * q + 0 < NC) { cg = fmaf(cq.x, g[4 * q + 0], cg); val[7 + 4 * q + 0] = wgt * g[4 * q + 0]; }
                     if (4 * q + 1 < NC) { cg = fmaf(cq.y, g[4 * q + 1], cg); val[7 + 4 * q + 1] = wgt * g[4 * q + 1]; }
                     if (4 * q + 2 < NC) { cg = fmaf(cq.z, g[4 * q + 2], cg); val[7 + 4 * q + 2] = wgt * g[4 * q + 2]; }
@@ -171,11 +185,12 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
                 val[5] = Gv * dL_dalpha;
                 val[6] = wgt * g_d;
             }
-            // Warp reduction of K values in ~K shuffles instead of 5K: a transposing butterfly.  At each step
-            // a lane keeps one half of its values and ships the other half to its partner, so the value
-            // count halves while the lane distance halves; after 4 steps lane L holds the partial sum of
-            // value L>>1 over its 16-lane group, a last xor-1 add completes it.  Even lanes then issue ONE
-            // red.global.add over the packed gradient record (<= 64 B, one L2 line).
+            // Warp reduction of K values in ~K shuffles instead of 5K: a transposing butterfly.  At each step a lane keeps
+            // one half of its values and ships the other half to its partner, so the value count halves while the lane
+            // distance halves; after the halving steps lane L holds the partial sum of value L >> kShift over its lane
+            // group, the remaining xor-adds complete it.  Three more shuffles gather 4 consecutive values into every
+            // (4 << kShift)-th lane, which issues ONE 16-byte red.global.add.v4.f32 into the packed gradient record
+            // (K scalar atomics before: 2.4 M red requests per step in ncu r01).
             constexpr int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
             float w_[KP];
 #pragma unroll
@@ -190,32 +205,32 @@ __global__ void __launch_bounds__(kTilePixels) k_blend_bwd(const LsRasterScene s
                     w_[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
             }
-            // remaining lane bits that were not consumed by the halving (KP = 16 -> bit 0; KP = 8 -> bits 1,0)
             float tot = w_[0];
             if (KP <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             if (KP <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-            constexpr int kShift = KP == 32 ? 0 : (KP == 16 ? 1 : 2);
+            constexpr int kShift = KP == 32 ? 0 : (KP == 16 ? 1 : 2);          // value index = lane >> kShift
+            const float v1 = __shfl_down_sync(0xffffffffu, tot, 1 << kShift);
+            const float v2 = __shfl_down_sync(0xffffffffu, tot, 2 << kShift);
+            const float v3 = __shfl_down_sync(0xffffffffu, tot, 3 << kShift);
             const int vidx = lane >> kShift;
-            if ((lane & ((1 << kShift) - 1)) == 0 && vidx < K)
-                atomicAdd(rec + (size_t)s_id[buf][j] * gr.grad_stride + vidx, tot);
+            if ((lane & ((4 << kShift) - 1)) == 0 && vidx < gr.grad_stride) {   // grad_stride = round_up4(K): whole float4 groups
+                const uint32_t id = __float_as_uint(cull[j].w);
+                lstc::red_add_v4(rec_out + (size_t)id * gr.grad_stride + vidx, tot, v1, v2, v3);
+            }
         }
-        __syncthreads();
+        __syncthreads();  // every warp is done with buffer `buf`
     }
 }
 
 template <int NC>
-static void launch_blend_bwd(const LsRasterScene& sc, const LsRasterState& st, const LsRasterGrads& gr, int ncol,
-                             dim3 grid, cudaStream_t stream) {
-    constexpr int CV = ((NC + 3) & ~3) / 4;
-    constexpr size_t smem = (size_t)2 * kTilePixels * ((2 + CV) * sizeof(float4) + sizeof(uint32_t));
-    if (smem > 48 * 1024) {
-        static bool configured = false;  // per instantiation; attribute is idempotent
-        if (!configured) {
-            cudaFuncSetAttribute(k_blend_bwd<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = true;
-        }
-    }
+static int launch_blend_bwd(const LsRasterScene& sc, const LsRasterState& st, const LsRasterGrads& gr, int ncol,
+                            dim3 grid, cudaStream_t stream) {
+    constexpr int RV = 2 + ((NC + 3) & ~3) / 4;
+    constexpr int smem = blend_smem_bytes(RV);
+    static lstc::PerDeviceOnce once;
+    if (smem > 48 * 1024 && once.ensure_smem(k_blend_bwd<NC>, smem) != cudaSuccess) return ls_check_cuda("blend bwd smem attribute");
     k_blend_bwd<NC><<<grid, kTilePixels, smem, stream>>>(sc, st, gr, ncol);
+    return 0;
 }
 
 // =========================================================================================
@@ -239,11 +254,26 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
     // lanes never return early: the SH rows and their gradients move warp-cooperatively (stage_load / stage_store)
     const bool alive = i < sc.G && st.radii[vi] > 0;
     const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
-    if (alive_mask == 0u) return;                               // warp-uniform
     const int s_idx = v / sc.views_per_scene;
     const size_t si = (size_t)s_idx * sc.G + i;
     const size_t si0 = (size_t)s_idx * sc.G + i0;
+    // several views per scene: gradients of the shared inputs accumulate with atomics into buffers the host zero-filled.
+    // one view per scene: every row is written exactly once -- culled Gaussians write their zeros here, no memset passes.
     const bool at = sc.views_per_scene > 1;
+    if (at && alive_mask == 0u) return;                         // warp-uniform
+    const uint32_t row_mask = at ? alive_mask : (nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+    if (!at && i < sc.G && !alive) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gr.dL_dmeans3D[3 * si + k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gr.dL_dcov3D[6 * si + k] = 0.f;
+        gr.dL_dopacity[si] = 0.f;
+        if (gr.dL_dmeans2D) { gr.dL_dmeans2D[3 * vi] = 0.f; gr.dL_dmeans2D[3 * vi + 1] = 0.f; gr.dL_dmeans2D[3 * vi + 2] = 0.f; }
+        if (sc.color_mode == LS_COLOR_PRECOMP)
+            for (int ch = 0; ch < 3; ++ch) gr.dL_dcolor_in[3 * si + ch] = 0.f;
+        if (sc.feature_mode == LS_FEATURE_PRECOMP)
+            for (int ch = 0; ch < sc.C; ++ch) gr.dL_dfeature_in[si * sc.C + ch] = 0.f;
+    }
 
     float p[3] = {0.f, 0.f, 0.f}, dmean[3] = {0.f, 0.f, 0.f};
     const float scale = sc.scene_scale ? sc.scene_scale[v] : 1.0f;
@@ -347,68 +377,75 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
             for (int ch = 0; ch < 3; ++ch) accum(gr.dL_dcolor_in + 3 * si + ch, r[7 + ch], at);
         }
     } else if (sc.color_mode == LS_COLOR_SH) {
-        const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1);
+        const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1), row = 3 * n;
+        const int pitch = gr.color_grad_pitch > 0 ? gr.color_grad_pitch : row;
+        const int row_out = gr.color_grad_pitch > 0 ? min(pitch, (row + 7) & ~7) : row;   // pad columns get zeros: whole sectors
         float gc[3] = {0.f, 0.f, 0.f};
         if (alive) {
             const uint8_t cl = st.clamped[vi];
             gc[0] = (cl & 1) ? 0.f : r[7]; gc[1] = (cl & 2) ? 0.f : r[8]; gc[2] = (cl & 4) ? 0.f : r[9];
         }
-        const float* __restrict__ sh0 = sc.color + si0 * (size_t)(n * 3);          // the warp's 32 rows
-        float* dsh0 = gr.dL_dcolor_in + si0 * (size_t)(n * 3);
-        for (int k0 = 0; k0 < n; k0 += 5) {                                        // 5 coefficients (15 floats) per pass
-            const int cnt = min(5, n - k0);
-            stage_load(stage, sh0, n * 3, k0 * 3, cnt * 3, nrows, lane);
-            float out[15];
-            if (alive) {
+        const float* __restrict__ sh0 = sc.color + si0 * (size_t)row;              // the warp's 32 rows
+        float* dsh0 = gr.dL_dcolor_in + si0 * (size_t)pitch;
+        for (int c0 = 0; c0 < row_out; c0 += kChunk) {                             // 8 coefficients (24 floats = 3 sectors) per pass
+            const int len_in = max(0, min(kChunk, row - c0)), len_out = min(kChunk, row_out - c0);
+            if (len_in > 0) stage_load(stage, sh0, row, c0, len_in, nrows, lane);
+            const int k0 = c0 / 3;
+            float out[kChunk];
 #pragma unroll
-                for (int kk = 0; kk < 5; ++kk) {
-                    if (kk < cnt) {
-                        const int k = k0 + kk;
-                        float sg = 0.f;
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            out[3 * kk + ch] = basis[k] * gc[ch];
-                            sg = fmaf(mine[3 * kk + ch], gc[ch], sg);
-                        }
-                        ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
-                        ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
-                        ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
-                    }
+            for (int e = 0; e < kChunk; ++e) {
+                float o = 0.f;
+                if (alive && e < len_in) {
+                    const int k = k0 + e / 3;
+                    const float gch = gc[e % 3];
+                    o = basis[k] * gch;
+                    const float sg = mine[e] * gch;
+                    ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
+                    ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
+                    ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
                 }
+                out[e] = o;
             }
             __syncwarp();                                                          // everyone has read its sh chunk
-            if (alive) {
 #pragma unroll
-                for (int e = 0; e < 15; ++e)
-                    if (e < 3 * cnt) mine[e] = out[e];
-            }
-            stage_store(stage, dsh0, n * 3, k0 * 3, cnt * 3, alive_mask, at, lane);
+            for (int e = 0; e < kChunk; ++e)
+                if (e < len_out) mine[e] = out[e];
+            stage_store(stage, dsh0, pitch, c0, len_out, row_mask, at, lane);
         }
     }
     if (sc.feature_mode == LS_FEATURE_PRECOMP) {
         if (alive)
             for (int ch = 0; ch < sc.C; ++ch) accum(gr.dL_dfeature_in + si * sc.C + ch, r[7 + ncol + ch], at);
     } else if (sc.feature_mode == LS_FEATURE_SH) {
-        const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1);
-        const float* __restrict__ fs0 = sc.feature + si0 * (size_t)(sc.C * n);
-        float* dfs0 = gr.dL_dfeature_in + si0 * (size_t)(sc.C * n);
-        const int cpc = max(1, kStagePitch / n);                                   // whole channels per pass
-        for (int c0 = 0; c0 < sc.C; c0 += cpc) {
-            const int nch = min(cpc, sc.C - c0);
-            stage_load(stage, fs0, sc.C * n, c0 * n, nch * n, nrows, lane);
-            if (alive) {
-                for (int cc = 0; cc < nch; ++cc) {
-                    const float gf = r[7 + ncol + c0 + cc];
-                    for (int k = 0; k < n; ++k) {
-                        const float sg = mine[cc * n + k] * gf;                    // read the coefficient ...
-                        mine[cc * n + k] = basis[k] * gf;                          // ... then overwrite its slot with its gradient
-                        ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
-                        ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
-                        ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
-                    }
+        const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1), row = sc.C * n;
+        const int pitch = gr.feature_grad_pitch > 0 ? gr.feature_grad_pitch : row;
+        const int row_out = gr.feature_grad_pitch > 0 ? min(pitch, (row + 7) & ~7) : row;
+        const uint32_t magic = (65536u + (uint32_t)n - 1u) / (uint32_t)n;          // f / n for f < 800, n <= 25
+        const float* __restrict__ fs0 = sc.feature + si0 * (size_t)row;
+        float* dfs0 = gr.dL_dfeature_in + si0 * (size_t)pitch;
+        for (int c0 = 0; c0 < row_out; c0 += kChunk) {                             // flat (channel, coefficient) index, 24 per pass
+            const int len_in = max(0, min(kChunk, row - c0)), len_out = min(kChunk, row_out - c0);
+            if (len_in > 0) stage_load(stage, fs0, row, c0, len_in, nrows, lane);
+            float out[kChunk];
+#pragma unroll
+            for (int e = 0; e < kChunk; ++e) {
+                float o = 0.f;
+                if (alive && e < len_in) {
+                    const int f = c0 + e, ch = (int)(((uint32_t)f * magic) >> 16), k = f - ch * n;
+                    const float gf = r[7 + ncol + ch];
+                    o = basis[k] * gf;
+                    const float sg = mine[e] * gf;
+                    ddir[0] = fmaf(dbasis[k][0], sg, ddir[0]);
+                    ddir[1] = fmaf(dbasis[k][1], sg, ddir[1]);
+                    ddir[2] = fmaf(dbasis[k][2], sg, ddir[2]);
                 }
+                out[e] = o;
             }
-            stage_store(stage, dfs0, sc.C * n, c0 * n, nch * n, alive_mask, at, lane);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < kChunk; ++e)
+                if (e < len_out) mine[e] = out[e];
+            stage_store(stage, dfs0, pitch, c0, len_out, row_mask, at, lane);
         }
     }
     if (!alive) return;                                        // no warp-level operation below this line
@@ -445,7 +482,7 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
         cudaMemsetAsync(gr->dL_drecord, 0, sizeof(float) * VG * gr->grad_stride, stream);
         dim3 grid(gx * gy, sc->n_views);
         switch (nc) {
-#define LS_CASE(N) case N: launch_blend_bwd<N>(*sc, *st, *gr, ncol, grid, stream); break;
+#define LS_CASE(N) case N: if (launch_blend_bwd<N>(*sc, *st, *gr, ncol, grid, stream)) return -1; break;
             LS_CASE(1) LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
             LS_CASE(9) LS_CASE(10) LS_CASE(11) LS_CASE(12) LS_CASE(13) LS_CASE(14) LS_CASE(15) LS_CASE(16)
 #undef LS_CASE
@@ -454,16 +491,24 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
         if (ls_check_cuda("backward blend")) return -1;
     }
     if (!(stages & LS_BWD_GEOMETRY)) return 0;
-    cudaMemsetAsync(gr->dL_dmeans3D, 0, sizeof(float) * SG * 3, stream);
-    cudaMemsetAsync(gr->dL_dcov3D, 0, sizeof(float) * SG * 6, stream);
-    cudaMemsetAsync(gr->dL_dopacity, 0, sizeof(float) * SG, stream);
-    if (gr->dL_dmeans2D) cudaMemsetAsync(gr->dL_dmeans2D, 0, sizeof(float) * VG * 3, stream);
-    if (sc->color_mode == LS_COLOR_PRECOMP) cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * 3, stream);
-    if (sc->color_mode == LS_COLOR_SH)
-        cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * 3 * (sc->sh_degree + 1) * (sc->sh_degree + 1), stream);
-    if (sc->feature_mode == LS_FEATURE_PRECOMP) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C, stream);
-    if (sc->feature_mode == LS_FEATURE_SH)
-        cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1), stream);
+    const size_t cpitch = gr->color_grad_pitch > 0 ? (size_t)gr->color_grad_pitch : (size_t)3 * (sc->sh_degree + 1) * (sc->sh_degree + 1);
+    const size_t fpitch = gr->feature_grad_pitch > 0 ? (size_t)gr->feature_grad_pitch
+                                                     : (size_t)sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1);
+    if (sc->color_mode == LS_COLOR_SH && gr->color_grad_pitch > 0 && gr->color_grad_pitch < 3 * (sc->sh_degree + 1) * (sc->sh_degree + 1))
+        return ls_fail("color_grad_pitch %d is shorter than a coefficient row", gr->color_grad_pitch);
+    if (sc->feature_mode == LS_FEATURE_SH && gr->feature_grad_pitch > 0 &&
+        gr->feature_grad_pitch < sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1))
+        return ls_fail("feature_grad_pitch %d is shorter than a coefficient row", gr->feature_grad_pitch);
+    if (sc->views_per_scene > 1) {          // shared inputs accumulate with atomics; one view per scene writes every row itself
+        cudaMemsetAsync(gr->dL_dmeans3D, 0, sizeof(float) * SG * 3, stream);
+        cudaMemsetAsync(gr->dL_dcov3D, 0, sizeof(float) * SG * 6, stream);
+        cudaMemsetAsync(gr->dL_dopacity, 0, sizeof(float) * SG, stream);
+        if (gr->dL_dmeans2D) cudaMemsetAsync(gr->dL_dmeans2D, 0, sizeof(float) * VG * 3, stream);
+        if (sc->color_mode == LS_COLOR_PRECOMP) cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * 3, stream);
+        if (sc->color_mode == LS_COLOR_SH) cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * cpitch, stream);
+        if (sc->feature_mode == LS_FEATURE_PRECOMP) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C, stream);
+        if (sc->feature_mode == LS_FEATURE_SH) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * fpitch, stream);
+    }
     dim3 grid2((sc->G + 255) / 256, sc->n_views);
     k_preprocess_bwd<<<grid2, 256, 0, stream>>>(*sc, *st, *gr);
     return ls_check_cuda("backward");

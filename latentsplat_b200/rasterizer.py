@@ -62,6 +62,8 @@ class _Buffers:
         self.stats = torch.zeros(4, dtype=torch.int32, device=device)
         self.keys = None
         self.keys_tmp = None
+        self.sorted_cull = None     # (capacity, 4): x, y, extents, id   -- the tile queues in list order, written by the sort
+        self.sorted_rec = None      # (capacity, rec_stride): geometry + channel record
         self.capacity = 0
         self.final_T = e(V, H, W)
         self.n_contrib = e(V, H, W, dtype=torch.int32)
@@ -72,12 +74,15 @@ class _Buffers:
         n = max(self.capacity, 1)
         self.keys = torch.empty(n, dtype=torch.int64, device=device)
         self.keys_tmp = torch.empty(n, dtype=torch.int64, device=device)
+        self.sorted_cull = torch.empty((n, 4), dtype=torch.float32, device=device)
+        self.sorted_rec = torch.empty((n, self.sizes.rec_stride), dtype=torch.float32, device=device)
 
     def as_struct(self) -> _capi.LsRasterState:
         return _capi.LsRasterState(
             _ptr(self.geom), _ptr(self.chan), _ptr(self.radii), _ptr(self.tiles_touched), _ptr(self.clamped),
             _ptr(self.tile_count), _ptr(self.tile_offsets), _ptr(self.stats), _ptr(self.keys), _ptr(self.keys_tmp),
-            self.capacity, _ptr(self.final_T), _ptr(self.n_contrib), self.sizes.chan_stride, self.sort_smem_keys)
+            self.capacity, _ptr(self.final_T), _ptr(self.n_contrib), self.sizes.chan_stride, self.sort_smem_keys,
+            _ptr(self.sorted_cull), _ptr(self.sorted_rec), self.sizes.rec_stride, 0)
 
 
 def _make_scene(V, vps, G, H, W, Cf, color_mode, sh_degree, feature_mode, fdeg, means3D, cov3D, opacity, color,
@@ -155,16 +160,35 @@ class RasterCall:
             self.forward_stage(_capi.STAGE_ALL)
         return self.images
 
+    @staticmethod
+    def _padded_rows(like: Tensor):
+        """Gradient buffer for per-Gaussian coefficient rows (S, G, a, b): rows of a*b floats padded to a multiple of 8 floats
+        (whole 32-byte sectors, see LsRasterGrads.color_grad_pitch).  Returns (buffer (S, G, pitch), view shaped like `like`,
+        pitch); rows of <= 4 floats (precomputed colours / features) stay dense."""
+        S, G = like.shape[:2]
+        row = like[0, 0].numel()
+        if like.dim() != 4 or row <= 4 or row % 8 == 0:
+            buf = torch.empty_like(like)
+            return buf, buf, 0
+        pitch = (row + 7) // 8 * 8
+        buf = torch.empty((S, G, pitch), dtype=like.dtype, device=like.device)
+        return buf, buf[:, :, :row].unflatten(2, tuple(like.shape[2:])), pitch
+
     def alloc_grads(self, want_means2D: bool):
         H, W, vps, color_mode, sh_degree, feature_mode, fdeg, Cf, V, S, G = self.cfg
         dev = self.device
         with torch.cuda.device(dev):
+            cbuf = cview = fbuf = fview = None
+            self.color_pitch = self.feature_pitch = 0
+            if self.color is not None:
+                cbuf, cview, self.color_pitch = self._padded_rows(self.color)
+            if self.feature is not None:
+                fbuf, fview, self.feature_pitch = self._padded_rows(self.feature)
+            self.grad_buf = dict(color=cbuf, feature=fbuf)
             self.grad_out = dict(
                 record=torch.empty((V, G, self.buf.sizes.grad_stride), device=dev),
                 means3D=torch.empty_like(self.means3D), cov3D=torch.empty_like(self.cov3D),
-                opacity=torch.empty_like(self.opacity),
-                color=torch.empty_like(self.color) if self.color is not None else None,
-                feature=torch.empty_like(self.feature) if self.feature is not None else None,
+                opacity=torch.empty_like(self.opacity), color=cview, feature=fview,
                 means2D=torch.empty((V, G, 3), device=dev) if want_means2D else None)
         return self.grad_out
 
@@ -172,7 +196,8 @@ class RasterCall:
         o = self.grad_out
         grads = _capi.LsRasterGrads(_ptr(g_color), _ptr(g_feature), _ptr(g_alpha), _ptr(g_depth), _ptr(o["record"]),
                                     self.buf.sizes.grad_stride, 0, _ptr(o["means3D"]), _ptr(o["cov3D"]),
-                                    _ptr(o["opacity"]), _ptr(o["color"]), _ptr(o["feature"]), _ptr(o["means2D"]))
+                                    _ptr(o["opacity"]), _ptr(self.grad_buf["color"]), _ptr(self.grad_buf["feature"]),
+                                    _ptr(o["means2D"]), self.color_pitch, self.feature_pitch)
         st = self.buf.as_struct()
         with torch.cuda.device(self.device):
             _capi.check(self.lib.ls_raster_backward(C.byref(self.scene), C.byref(st), C.byref(grads), stages,
