@@ -54,6 +54,20 @@ LS_API int ls_conv2d_dgrad(const LsConv2d* c, const float* dy, const float* w, f
  * pixel dimension and combined with red.global.add.                                                              */
 LS_API int ls_conv2d_wgrad(const LsConv2d* c, const float* dy, const float* x, float* dw, void* stream);
 
+/* ---- nearest-2x up-sampling followed by a 3x3 / stride 1 / pad 1 convolution -------------------------------------
+ * diffusers' Upsample2D, the three up-samplers of the VAE decoder the reference wraps (autoencoder_kl.py:119-122 ->
+ * Decoder.up_blocks[i].upsamplers[0]: F.interpolate(scale_factor=2, mode="nearest") then Conv2d(C, C, 3, padding=1)).
+ * Per output parity class the 3x3 filter on the up-sampled image collapses to 2x2 taps with summed weights on the LOW
+ * resolution input: 16 instead of 36 tap-MACs per input pixel and no up-sampled tensor in HBM.  `c` describes the
+ * low-resolution input (N, H, W, Cin) and the 3x3 filter; y / dy are (N, 2H, 2W, Cout).
+ * wk: caller-owned workspace of ls_upconv2x_workspace() floats, written by forward (folded weights) and read by dgrad;
+ * scratch (wgrad): 16*Cout*Cin floats.                                                                               */
+LS_API int ls_upconv2x_workspace(const LsConv2d* c, int64_t* floats);
+LS_API int ls_upconv2x_forward(const LsConv2d* c, const float* x, const float* w, const float* bias, float* y, float* wk,
+                               void* stream);
+LS_API int ls_upconv2x_dgrad(const LsConv2d* c, const float* dy, const float* wk, float* dx, void* stream);
+LS_API int ls_upconv2x_wgrad(const LsConv2d* c, const float* dy, const float* x, float* dw, float* scratch, void* stream);
+
 /* ---- small NHWC helpers that ride along with the convolutions ------------------------------------------------- */
 /* dx = dy * act'(pre)  (elementwise; the backward of a fused epilogue activation)                                */
 LS_API int ls_act_backward(const float* dy, const float* pre, float* dx, int64_t n, int32_t act, void* stream);

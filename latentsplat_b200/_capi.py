@@ -82,6 +82,23 @@ class LsConv2d(C.Structure):             # include/ls_conv.h
     _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "transposed")]
 
 
+class LsGaussianHead(C.Structure):      # include/ls_ghead.h
+    _fields_ = [("rays", C.c_int64)] + \
+               [(n, C.c_int32) for n in ("rays_per_view", "width", "height", "samples", "buckets", "d_color", "d_feature",
+                                         "deterministic")] + \
+               [(n, C.c_float) for n in ("scale_min", "scale_max", "opacity_exponent", "inv_gpp")] + \
+               [(n, C.c_void_p) for n in ("dlog", "raw", "u", "extrinsics", "intrinsics", "near", "far")]
+
+
+class LsGaussianHeadOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("means", "covariances", "opacity", "color_sh", "feature_sh", "index")]
+
+
+class LsGaussianHeadGrad(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("index", "d_means", "d_covariances", "d_opacity", "d_color_sh", "d_feature_sh",
+                                          "d_dlog", "d_raw")]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
@@ -94,7 +111,9 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_epipolar_gather_forward", "ls_epipolar_gather_backward", "ls_groupnorm_forward", "ls_groupnorm_backward",
            "ls_layernorm_forward", "ls_layernorm_backward", "ls_conv_bias_add", "ls_conv_bias_grad", "ls_col_sum",
            "ls_groupnorm_nhwc_forward", "ls_groupnorm_nhwc_backward",
-           "ls_conv2d_out_size", "ls_conv2d_forward", "ls_conv2d_dgrad", "ls_conv2d_wgrad", "ls_act_backward")
+           "ls_conv2d_out_size", "ls_conv2d_forward", "ls_conv2d_dgrad", "ls_conv2d_wgrad", "ls_act_backward",
+           "ls_upconv2x_workspace", "ls_upconv2x_forward", "ls_upconv2x_dgrad", "ls_upconv2x_wgrad",
+           "ls_gaussian_head_forward", "ls_gaussian_head_backward")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -162,6 +181,18 @@ def load() -> C.CDLL:
     lib.ls_conv2d_dgrad.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 4
     lib.ls_conv2d_wgrad.restype = C.c_int
     lib.ls_conv2d_wgrad.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 4
+    lib.ls_upconv2x_workspace.restype = C.c_int
+    lib.ls_upconv2x_workspace.argtypes = [C.POINTER(LsConv2d), C.POINTER(C.c_int64)]
+    lib.ls_upconv2x_forward.restype = C.c_int
+    lib.ls_upconv2x_forward.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 6
+    lib.ls_upconv2x_dgrad.restype = C.c_int
+    lib.ls_upconv2x_dgrad.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 4
+    lib.ls_upconv2x_wgrad.restype = C.c_int
+    lib.ls_upconv2x_wgrad.argtypes = [C.POINTER(LsConv2d)] + [C.c_void_p] * 5
+    lib.ls_gaussian_head_forward.restype = C.c_int
+    lib.ls_gaussian_head_forward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadOut), C.c_void_p]
+    lib.ls_gaussian_head_backward.restype = C.c_int
+    lib.ls_gaussian_head_backward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadGrad), C.c_void_p]
     lib.ls_act_backward.restype = C.c_int
     lib.ls_act_backward.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p]
     lib.ls_col_sum.restype = C.c_int

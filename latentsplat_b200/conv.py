@@ -99,6 +99,62 @@ class _ConvFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None
 
 
+class _UpConvFn(torch.autograd.Function):
+    """conv3x3(upsample_nearest_2x(x)) + bias without the up-sampled tensor: four 2x2 convolutions with folded weights on the
+    low-resolution input (ls_upconv2x_*, include/ls_conv.h).  x (N, C, H, W) -> (N, Cout, 2H, 2W)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]):
+        x, w = _cl(x), _cl(weight)
+        N, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        desc = _capi.LsConv2d(N, H, W, Cin, Cout, 3, 3, 1, 1, 0)
+        lib = _capi.load()
+        n = C.c_int64()
+        _capi.check(lib.ls_upconv2x_workspace(C.byref(desc), C.byref(n)), "ls_upconv2x_workspace")
+        wk = torch.empty(n.value, dtype=torch.float32, device=x.device)
+        y = torch.empty((N, Cout, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=CL)
+        with torch.cuda.device(x.device):
+            _capi.check(lib.ls_upconv2x_forward(C.byref(desc), x.data_ptr(), w.data_ptr(), None if bias is None else bias.data_ptr(),
+                                                y.data_ptr(), wk.data_ptr(), _stream()), "ls_upconv2x_forward")
+        _capi.KERNEL_LAUNCHES[0] += 5
+        ctx.desc, ctx.has_bias = desc, bias is not None
+        ctx.save_for_backward(x, w, wk)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy: Tensor):
+        x, w, wk = ctx.saved_tensors
+        desc, lib = ctx.desc, _capi.load()
+        gy = _cl(gy)
+        gx = gw = gb = None
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                _capi.check(lib.ls_upconv2x_dgrad(C.byref(desc), gy.data_ptr(), wk.data_ptr(), gx.data_ptr(), _stream()),
+                            "ls_upconv2x_dgrad")
+                _capi.KERNEL_LAUNCHES[0] += 1
+            if ctx.needs_input_grad[1]:
+                gw = torch.empty_like(w)
+                scratch = torch.empty(16 * desc.Cout * desc.Cin, dtype=torch.float32, device=x.device)
+                _capi.check(lib.ls_upconv2x_wgrad(C.byref(desc), gy.data_ptr(), x.data_ptr(), gw.data_ptr(), scratch.data_ptr(),
+                                                  _stream()), "ls_upconv2x_wgrad")
+                _capi.KERNEL_LAUNCHES[0] += 5
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            from .gemm import col_sum
+            gb = col_sum(gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1]))
+        return gx, gw, gb
+
+
+def upsample2x_conv3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), weight, bias, padding=1) on the folded-weight kernels."""
+    if not x.is_cuda:
+        raise RuntimeError("upsample2x_conv3x3 needs CUDA tensors: latentsplat_b200 has no CPU fallback")
+    return _UpConvFn.apply(x, weight, bias)
+
+
 def _pad_channels(t: Tensor, dim: int, n: int) -> Tensor:
     if n == 0:
         return t
@@ -161,6 +217,14 @@ class Conv2d(nn.Conv2d):
         if self._native(input):
             return conv2d(input, self.weight, self.bias, _int_pair(self.stride), _int_pair(self.padding), self.act)
         return _apply_act(super().forward(input), self.act)
+
+    def forward_upsampled2x(self, input: Tensor) -> Tensor:
+        """self(F.interpolate(input, scale_factor=2, mode="nearest")) -- fused (no up-sampled tensor, 2.25x fewer flops) for the
+        3x3 / stride 1 / pad 1 case on CUDA, the explicit two-step sequence otherwise."""
+        if (self._native(input) and self.act == "none" and tuple(self.kernel_size) == (3, 3) and _int_pair(self.stride) == 1
+                and _int_pair(self.padding) == 1 and self.in_channels % 4 == 0 and self.out_channels % 4 == 0):
+            return upsample2x_conv3x3(input, self.weight, self.bias)
+        return self.forward(F.interpolate(input, scale_factor=2.0, mode="nearest"))
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
     float* stage = s_stage[threadIdx.x >> 5];
     float* mine = stage + lane * kStagePitch;
     const int i0 = i - lane, nrows = min(32, sc.G - i0);       // this warp's 32 consecutive Gaussians
+    if (nrows <= 0) return;                                     // warp-uniform: the grid's tail beyond G
     const size_t vi = (size_t)v * sc.G + i;
     // lanes never return early: the SH rows and their gradients move warp-cooperatively (stage_load / stage_store)
     const bool alive = i < sc.G && st.radii[vi] > 0;

@@ -29,6 +29,7 @@ from .epipolar.depth_predictor_monocular import DepthPredictorMonocular
 from .epipolar.epipolar_transformer import EpipolarTransformer, EpipolarTransformerCfg
 from .shims import apply_bounds_shim, apply_patch_shim
 from latentsplat_b200.gemm import Linear, grouped_linear  # nn.Linear / F.linear with tcgen05 TF32 GEMMs on CUDA
+from latentsplat_b200 import gaussian_head  # fused depth sampling + Gaussian adapter (sm_100a kernel)
 from latentsplat_b200.conv import Conv2d  # tcgen05 implicit-GEMM convolutions (NHWC) with fused bias + activation
 
 
@@ -141,6 +142,9 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
             features = features + self.high_resolution_skip(images).unflatten(0, (b, v))
 
         features = features.flatten(3).transpose(2, 3)                     # b v c h w -> b v (h w) c
+        fused = self._fused_tail(features, context, global_step, deterministic, (h, w), visualization_dump)
+        if fused is not None:
+            return fused
         depths, densities = self.depth_predictor(features, context["near"], context["far"], deterministic,
                                                  1 if deterministic else self.cfg.gaussians_per_pixel)
 
@@ -170,6 +174,35 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         return VariationalGaussians(g.means.flatten(1, 4), g.covariances.flatten(1, 4),
                                     (opacity_multiplier * g.opacities).flatten(1, 4),
                                     g.color_harmonics.flatten(1, 4), feature_harmonics)
+
+    def _fused_tail(self, features: Tensor, context: dict, global_step: int, deterministic: bool, image_shape,
+                    visualization_dump: Optional[dict]) -> Optional[VariationalGaussians]:
+        """depth predictor -> xy offsets -> opacity mapping -> Gaussian adapter as ONE kernel each way
+        (latentsplat_b200.gaussian_head) after the two Linear heads; None when the configuration needs the explicit sequence
+        below (CPU tensors, visualisation dumps, hooks on the pdf / offset modules, transmittance or opacity heads)."""
+        dp, ga, cfg = self.depth_predictor, self.gaussian_adapter, self.cfg
+        spp = 1 if deterministic else cfg.gaussians_per_pixel
+        if (visualization_dump is not None or not FOLD_HARMONICS or dp.to_pdf._forward_hooks or dp.to_offset._forward_hooks
+                or not gaussian_head.supported(features, features, dp.num_samples, cfg.num_surfaces, spp, dp.use_transmittance,
+                                               cfg.predict_opacity)):
+            return None
+        b, v, r, _ = features.shape
+        dlog = dp.projection(features)                                                          # (b, v, r, 2 * buckets)
+        if not gaussian_head.supported(dlog, dlog, dp.num_samples, cfg.num_surfaces, spp, dp.use_transmittance, cfg.predict_opacity):
+            return None
+        raw = self._gaussian_head(features, context["extrinsics"][..., :3, :3])                 # (b, v, r, 2 + adapter.d_in)
+        # the reference's draw: torch.rand over (*pdf.shape[:-1], num_samples) = (b, v, r, srf, spp)
+        u = None if deterministic else torch.rand((b, v, r, cfg.num_surfaces, spp), device=features.device).reshape(b, v, r, spp)
+        om = cfg.opacity_mapping
+        exponent = 2.0 ** (om.initial + min(global_step / om.warm_up, 1) * (om.final - om.initial))
+        d_color, d_feature = 3 * ga.d_color_sh, ga.n_feature_channels * ga.d_feature_sh
+        means, cov, opac, csh, fsh, _ = gaussian_head.gaussian_head(
+            dlog, raw, u, context["extrinsics"], context["intrinsics"], context["near"], context["far"], image_shape, spp,
+            d_color, d_feature, ga.cfg.gaussian_scale_min, ga.cfg.gaussian_scale_max, exponent, cfg.gaussians_per_pixel)
+        feature_harmonics = fsh.unflatten(-1, (ga.n_feature_channels, ga.d_feature_sh))
+        feature_harmonics = DiagonalGaussianDistribution(
+            **{"params" if self.variational else "mean": feature_harmonics}, dim=-2)
+        return VariationalGaussians(means, cov, opac, csh.unflatten(-1, (3, ga.d_color_sh)), feature_harmonics)
 
     def get_data_shim(self):
         def data_shim(batch: dict) -> dict:

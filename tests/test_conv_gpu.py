@@ -125,6 +125,28 @@ def test_conv_transpose2d_forward_backward(cuda, N, Cin, H, W, Cout, k):
     assert (gb.double() - rb).abs().max().item() <= 1e-4 * rb.abs().max().item() + 1e-4
 
 
+@pytest.mark.parametrize("N,C,H,W,Cout", [(2, 32, 16, 16, 64), (1, 256, 8, 12, 256), (2, 64, 7, 33, 32)])
+def test_upsample2x_conv3x3_matches_interpolate_then_conv(cuda, N, C, H, W, Cout):
+    """The VAE up-sampler (nearest 2x, then 3x3 conv) with the up-sampling folded into the filter: output and all gradients
+    against float64 F.interpolate + F.conv2d."""
+    from latentsplat_b200.conv import upsample2x_conv3x3
+    g = torch.Generator(cuda).manual_seed(6)
+    x = torch.randn(N, C, H, W, device=cuda, generator=g).contiguous(memory_format=CL).requires_grad_(True)
+    w = (torch.randn(Cout, C, 3, 3, device=cuda, generator=g) / np.sqrt(9 * C)).contiguous(memory_format=CL).requires_grad_(True)
+    b = torch.randn(Cout, device=cuda, generator=g).requires_grad_(True)
+    y = upsample2x_conv3x3(x, w, b)
+    gy = torch.randn(y.shape, device=cuda, generator=g).contiguous(memory_format=CL)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), gy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    ref = F.conv2d(F.interpolate(xd, scale_factor=2.0, mode="nearest"), wd, bd, 1, 1)
+    rx, rw, rb = torch.autograd.grad(ref, (xd, wd, bd), gy.double())
+    assert y.shape == ref.shape
+    _check(y, ref.detach(), 9 * C, _rms(x), _rms(w), "upconv forward")
+    _check(gx, rx, 36 * Cout, _rms(gy), _rms(w), "upconv dgrad")
+    _check(gw, rw, 4 * N * H * W, _rms(gy), _rms(x), "upconv wgrad")
+    assert (gb.double() - rb).abs().max().item() <= 1e-4 * rb.abs().max().item() + 1e-4
+
+
 def test_conv_modules_match_torch_modules(cuda):
     """Conv2d / ConvTranspose2d modules (channel padding for RGB / 7-channel / 1-channel layers, NCHW inputs)."""
     from latentsplat_b200 import conv
