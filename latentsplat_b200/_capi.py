@@ -99,6 +99,12 @@ class LsGaussianHeadGrad(C.Structure):
                                           "d_dlog", "d_raw")]
 
 
+class LsFmha(C.Structure):              # include/ls_fmha.h
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("L", C.c_int32), ("D", C.c_int32), ("scale", C.c_float), ("reserved0", C.c_int32),
+                ("ld_q", C.c_int64), ("ld_k", C.c_int64), ("ld_v", C.c_int64), ("ld_o", C.c_int64),
+                ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("lse", C.c_void_p)]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
@@ -113,7 +119,7 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_groupnorm_nhwc_forward", "ls_groupnorm_nhwc_backward",
            "ls_conv2d_out_size", "ls_conv2d_forward", "ls_conv2d_dgrad", "ls_conv2d_wgrad", "ls_act_backward",
            "ls_upconv2x_workspace", "ls_upconv2x_forward", "ls_upconv2x_dgrad", "ls_upconv2x_wgrad",
-           "ls_gaussian_head_forward", "ls_gaussian_head_backward")
+           "ls_gaussian_head_forward", "ls_gaussian_head_backward", "ls_fmha_forward", "ls_fmha_backward")
 
 _lib = None
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
@@ -193,6 +199,10 @@ def load() -> C.CDLL:
     lib.ls_gaussian_head_forward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadOut), C.c_void_p]
     lib.ls_gaussian_head_backward.restype = C.c_int
     lib.ls_gaussian_head_backward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadGrad), C.c_void_p]
+    lib.ls_fmha_forward.restype = C.c_int
+    lib.ls_fmha_forward.argtypes = [C.POINTER(LsFmha), C.c_void_p]
+    lib.ls_fmha_backward.restype = C.c_int
+    lib.ls_fmha_backward.argtypes = [C.POINTER(LsFmha)] + [C.c_void_p] * 6
     lib.ls_act_backward.restype = C.c_int
     lib.ls_act_backward.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p]
     lib.ls_col_sum.restype = C.c_int
