@@ -9,11 +9,12 @@ Workloads (`--workload`, named in config.workload):
         context views 256x256, full encoder (DINO ViT-B/8 + epipolar transformer) -> 393 216 variational Gaussians
         per scene -> sample -> splat V_t target views -> latent sample -> 1/8 rescale -> VAE decoder with skip
         injection -> PatchGAN logits (generator term, discriminator frozen); loss = 10 mse(colour) + l1(decoded image)
-        + hinge generator term; backward to every weight; fused Adam step; for N > 1 an NCCL all-reduce of the flat
-        gradient buffer.  fp32 weights/activations.  Ours (sm_100a, libls_raster.so): rasterizer fwd+bwd, every Linear
-        (tcgen05 TF32 GEMM), epipolar gather + depth encoding, weight-absorbed cross-attention, GroupNorm+SiLU, LayerNorm,
-        conv bias epilogues and bias gradients.  Library: cuDNN convolutions (TF32, as the reference's torch defaults),
-        the DINO / VAE-mid attention cores, remaining elementwise glue.
+        + hinge generator term; backward to every weight; fused Adam step; for N > 1 a bucketed NCCL all-reduce of the
+        flat gradient buffer overlapped with backward.  fp32 weights/activations, NHWC.  Ours (sm_100a, libls_raster.so):
+        rasterizer fwd+bwd, every Linear (tcgen05 TF32 GEMM), every convolution (tcgen05 implicit GEMM), the attention
+        cores (tcgen05 flash attention; GEMM + softmax for the VAE mid block), epipolar gather + depth encoding,
+        weight-absorbed cross-attention, fused depth/Gaussian-adapter tail, GroupNorm+SiLU, LayerNorm.  Library: PatchGAN
+        BatchNorm, the antialiased rescale, fused Adam, remaining elementwise glue.
   splat the rasterizer path alone: B scenes x G=65 536 Gaussians (colour SH deg 4 + C=4 feature SH deg 2) through
         DecoderSplattingCUDA fwd+bwd with scalar loss heads (the round-1 kernel workload; roofline stages).
 One step = one such batch; value = target views / s over all ranks.
@@ -49,9 +50,11 @@ def workload_name(cfg) -> str:
         return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views {H}x{W}, "
                 f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
                 "views -> VAE kl-f8 decoder with skips -> PatchGAN logits; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
-                "(tcgen05 TF32 GEMM fwd/dgrad/wgrad), epipolar gather + depth encoding, weight-absorbed epipolar cross-attention, "
-                "GroupNorm+SiLU, LayerNorm; library: cuDNN convolutions (TF32), DINO / VAE-mid attention cores (bf16 flash / "
-                "mem-efficient SDPA), remaining elementwise glue (torch)")
+                "(tcgen05 TF32 GEMM fwd/dgrad/wgrad with bias/GELU/residual epilogues), every convolution (tcgen05 implicit GEMM over "
+                "NHWC, fprop/dgrad/wgrad, transposed + fused 2x-upsample forms), DINO / image self-attention (tcgen05 flash attention "
+                "fwd+bwd), VAE mid attention (GEMM + row softmax), epipolar gather + depth encoding, weight-absorbed epipolar "
+                "cross-attention, fused depth-sampling + Gaussian-adapter tail, GroupNorm+SiLU (NCHW+NHWC), LayerNorm; library: "
+                "PatchGAN BatchNorm (cuDNN), antialiased 1/8 rescale, fused Adam, remaining elementwise glue (torch)")
     return (f"splat_{'fwd_only' if FWD_ONLY else 'fwd_bwd'}: B={cfg['B']} scenes/GPU x V_t={cfg['V_t']} target views {H}x{W}, "
             f"G={cfg['G']} feature Gaussians/scene (colour SH deg {cfg['color_sh_degree']} + C={cfg['C']} feature SH "
             f"deg {cfg['feature_sh_degree']}), DecoderSplattingCUDA {'forward' if FWD_ONLY else 'fwd+bwd'} with scalar loss heads "
@@ -383,9 +386,13 @@ def run_full(args, cfg):
     pipe, params = build_pipeline(device, seed=0)          # identical replicas on every rank
     n_params = sum(p.numel() for p in params)
     # one flat gradient buffer (views as .grad): a single NCCL all-reduce per step, zeroed inside the graph
-    from latentsplat_b200.parallel import FlatGradients
+    from latentsplat_b200.parallel import BucketedAllReduce, FlatGradients
     fgrads = FlatGradients(params)
     flat_grad = fgrads.flat
+    # N > 1: bucketed all-reduce launched by gradient hooks DURING backward on a communication stream, captured into the
+    # step's CUDA graph together with the kernels (LS_BENCH_ALLREDUCE=after: one exposed all-reduce behind the graph)
+    overlap = world > 1 and os.environ.get("LS_BENCH_ALLREDUCE", "overlap") == "overlap"
+    reducer = BucketedAllReduce(fgrads, bucket_bytes=32 << 20) if overlap else None
     opt = torch.optim.Adam(params, lr=1.5e-5, fused=True, capturable=True)
 
     batch = make_full_batch(cfg, rank)
@@ -399,7 +406,11 @@ def run_full(args, cfg):
         flat_grad.zero_()
         out = pipe(unflatten_batch(inp), global_step=0, discriminate=True)
         loss = full_loss(out, inp["target.image"])
+        if reducer is not None:
+            reducer.begin()
         loss.backward()
+        if reducer is not None:
+            reducer.finish()
         return {"loss": loss.detach()}
 
     def opt_step(_inp=None):
@@ -447,7 +458,8 @@ def run_full(args, cfg):
 
     def step():
         r = g_fb.replay()
-        fgrads.all_reduce_mean()               # no-op at world size 1
+        if reducer is None:
+            fgrads.all_reduce_mean()           # no-op at world size 1
         g_opt.replay()
         return r
 
@@ -498,15 +510,19 @@ def run_full(args, cfg):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
             "data": "synthetic",
             "config": {"workload": workload_name(cfg), "global_batch": world * cfg["B"],
-                       "precision": "fp32 weights/activations in HBM; Linear layers = tcgen05 kind::tf32 (ours); convolutions = "
-                                    "cuDNN TF32 (torch default, as the reference); DINO attention core = bf16 flash SDPA (library); "
-                                    "rasterizer fp32", "views_per_step_per_gpu": views_per_step,
+                       "precision": "fp32 weights/activations in HBM (NHWC); Linear layers, convolutions (implicit GEMM) and the "
+                                    "attention cores = our tcgen05 kind::tf32 kernels with fp32 accumulation in TMEM (the reference's "
+                                    "cuDNN convolutions are TF32 too); norms / softmax / rasterizer fp32; nothing below TF32",
+                       "views_per_step_per_gpu": views_per_step,
                        "gaussians_per_scene": 2 * H * W * 3, "num_rendered_per_step": num_rendered,
                        "parameters_updated": n_params, "parallelism": f"dp{world}",
                        "l2": "flushed between timed steps (256 MiB write), flush outside the per-step CUDA events",
                        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
-                       "execution": "fwd+bwd in one CUDA graph, Adam in a second; flat-gradient NCCL all-reduce between them "
-                                    f"when n_gpus > 1; rasterizer sync-free ({capacity} key slots, overflow flag checked)",
+                       "execution": "fwd+bwd in one CUDA graph, Adam in a second; for n_gpus > 1 the flat gradient is all-reduced in "
+                                    + ("32 MiB buckets launched by gradient hooks during backward on a communication stream, "
+                                       "captured inside the graph (only the last bucket is exposed)" if reducer is not None else
+                                       "one NCCL all-reduce between the two graphs")
+                                    + f"; rasterizer sync-free ({capacity} key slots, overflow raises RasterCapacityError)",
                        "eager_exact_ms_per_step": eager_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "stages": stages,
@@ -529,15 +545,17 @@ def gpu_baseline_full(pipe, fwd_bwd, opt_step, dev_flat, timed_loop, views_per_s
     -- executed eagerly (no CUDA graph) with the reference's per-view rasterizer loop and its host syncs
     (cuda_splatting.py:124-162), on OUR rasterizer kernels (labelled accordingly)."""
     import torch
-    from latentsplat_b200 import attention, conv, epipolar_gather, gemm, norm
+    from latentsplat_b200 import attention, conv, epipolar_gather, fmha, gaussian_head, gemm, norm
     from latentsplat_b200.model.decoder import cuda_splatting
     from latentsplat_b200.model.encoder import encoder_epipolar
     from latentsplat_b200.model.encoder.backbone import dino_vit
     saved = (gemm.enabled, conv.ENABLED, norm.ENABLED, attention.ABSORB, attention.ENABLED, epipolar_gather.ENABLED,
              dino_vit.ATTENTION_BF16, encoder_epipolar.FOLD_HARMONICS, cuda_splatting.PER_VIEW_LOOP,
              torch.backends.cuda.matmul.allow_tf32, pipe.decoder.raster_capacity)
+    saved_new = (fmha.ENABLED, gaussian_head.ENABLED)
     try:
         gemm.enabled = conv.ENABLED = norm.ENABLED = attention.ABSORB = attention.ENABLED = epipolar_gather.ENABLED = False
+        fmha.ENABLED = gaussian_head.ENABLED = False
         dino_vit.ATTENTION_BF16 = encoder_epipolar.FOLD_HARMONICS = False
         cuda_splatting.PER_VIEW_LOOP = True
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -554,6 +572,7 @@ def gpu_baseline_full(pipe, fwd_bwd, opt_step, dev_flat, timed_loop, views_per_s
         (gemm.enabled, conv.ENABLED, norm.ENABLED, attention.ABSORB, attention.ENABLED, epipolar_gather.ENABLED,
          dino_vit.ATTENTION_BF16, encoder_epipolar.FOLD_HARMONICS, cuda_splatting.PER_VIEW_LOOP,
          torch.backends.cuda.matmul.allow_tf32, pipe.decoder.raster_capacity) = saved
+        fmha.ENABLED, gaussian_head.ENABLED = saved_new
     ms /= steps
     return {"value": views_per_step / (ms / 1000), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "kind": "reference math on our rasterizer: same modules/weights, all own encoder/decoder kernels off (cuBLAS fp32 "
@@ -612,33 +631,102 @@ def full_stage_profile(pipe, dev_flat, cfg, fwd_bwd):
                        "kernel_ms": ms[dom], "note": "blend kernels are instruction-issue bound (DESIGN.md section 4)"}
     stages["raster_roofline"] = raster_roofline
 
-    # Dominant kernel of OUR code in the full step: the tcgen05 TF32 GEMM (all Linear layers; ~20 ms of the step vs
-    # ~4 ms of rasterizer kernels).  Timed live on its largest instance, the DINO MLP up-projection.
+    # Dominant kernels of the full step: the tcgen05 implicit-GEMM convolutions (VAE decoder 3x3, epipolar 7x7, PatchGAN) and the
+    # tcgen05 TF32 GEMM (all Linear layers).  Each is timed live on its largest instance and reported next to the IN-STEP
+    # aggregate of its whole family (sum of algorithmic FLOPs / sum of kernel time over one step, tensor_family_aggregate).
+    from latentsplat_b200.conv import conv2d
     from latentsplat_b200.gemm import gemm_tf32
+    tf32_peak, tf32_src = tf32_peak_tflops()
+
+    def time_it(fn, reps=10):
+        for _ in range(3):
+            fn()
+        times = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return sum(times) / len(times)
+
     M, N, K = cfg["B"] * 2 * ((H // 8) * (W // 8) + 1), 3072, 768
     A, Bm, out = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda"), torch.empty(M, N, device="cuda")
-    for _ in range(3):
-        gemm_tf32(A, Bm, M=M, N=N, K=K, out=out)
-    times = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); gemm_tf32(A, Bm, M=M, N=N, K=K, out=out); e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    g_ms = sum(times) / len(times)
-    flops = 2.0 * M * N * K
-    tf32_peak, tf32_src = tf32_peak_tflops()
-    traffic = None
-    prof = ROOT / "profiles" / "r01_full_ncu_traffic.json"
+    g_ms = time_it(lambda: gemm_tf32(A, Bm, M=M, N=N, K=K, out=out))
+    g_flops = 2.0 * M * N * K
+    # the VAE decoder's widest 3x3 convolution at full resolution: (B*V_t, 128, 256, 256) -> 128 channels
+    cn, cc = V, 128
+    cx = torch.randn(cn, cc, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    cw = torch.randn(cc, cc, 3, 3, device="cuda").contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        c_ms = time_it(lambda: conv2d(cx, cw, None, 1, 1))
+    c_flops = 2.0 * cn * H * W * cc * 9 * cc
+    families = tensor_family_aggregate(fwd_bwd, dev_flat)
+    traffic = {}
+    prof = ROOT / "profiles" / "r02_full_ncu_traffic.json"
     if prof.exists():
-        traffic = json.loads(prof.read_text()).get("gemm_dino_fc1", {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": f"k_gemm_tf32 (DINO fc1 {M}x{N}x{K}, TMA + tcgen05.mma kind::tf32)",
-                "achieved": flops / (g_ms / 1000) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": flops / (g_ms / 1000) / 1e12 / tf32_peak, "traffic": traffic, "peak_source": tf32_src,
-                "algorithmic_flops_per_launch": flops, "kernel_ms": g_ms,
-                "note": "dominant kernel of OUR code in this step; cuDNN convolutions (library) are the largest share overall"}
+        traffic = json.loads(prof.read_text())
+    conv_inst = {"kernel": f"k_conv_t (3x3 s1 {cc}->{cc} @ {cn}x{H}x{W} NHWC, 4-D TMA boxes + tcgen05.mma kind::tf32)",
+                 "achieved": c_flops / (c_ms / 1000) / 1e12, "frac": c_flops / (c_ms / 1000) / 1e12 / tf32_peak,
+                 "algorithmic_flops_per_launch": c_flops, "kernel_ms": c_ms,
+                 "traffic": traffic.get("conv_3x3_128", {}).get("dram_bytes_per_launch")}
+    gemm_inst = {"kernel": f"k_gemm_tf32 (DINO fc1 {M}x{N}x{K} + GELU epilogue shape, TMA + tcgen05.mma kind::tf32)",
+                 "achieved": g_flops / (g_ms / 1000) / 1e12, "frac": g_flops / (g_ms / 1000) / 1e12 / tf32_peak,
+                 "algorithmic_flops_per_launch": g_flops, "kernel_ms": g_ms,
+                 "traffic": traffic.get("gemm_dino_fc1", {}).get("dram_bytes_per_launch")}
+    conv_ms = (families or {}).get("conv", {}).get("ms", 0.0)
+    gemm_ms = (families or {}).get("gemm", {}).get("ms", 0.0)
+    dom = conv_inst if conv_ms >= gemm_ms else gemm_inst
+    roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": tf32_src,
+                "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"], "kernel_ms": dom["kernel_ms"],
+                "instances": {"conv": conv_inst, "gemm": gemm_inst},
+                "in_step_aggregate": families,
+                "note": "dominant family of the step chosen by in-step kernel time; `achieved` = its largest instance timed alone "
+                        "(CUDA events, L2 flushed), `in_step_aggregate` = sum flops / sum kernel time of every launch of each family "
+                        "inside one step (CUPTI)"}
     return roofline, stages
+
+
+def tensor_family_aggregate(fwd_bwd, dev_flat):
+    """In-step aggregate of our tensor-core kernel families: sum of algorithmic FLOPs (counted by the Python wrappers,
+    latentsplat_b200._capi.FLOPS) / sum of kernel durations (CUPTI activity records of one eager step through torch.profiler;
+    the events of the timed loop cannot separate kernels inside the CUDA graph).  Returns {family: {...}} or None."""
+    import torch
+    from latentsplat_b200 import _capi
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        fwd_bwd(dev_flat)
+        torch.cuda.synchronize()
+        before = dict(_capi.FLOPS)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fwd_bwd(dev_flat)
+            torch.cuda.synchronize()
+        flops = {k: _capi.FLOPS[k] - before[k] for k in before}
+        fam = {"gemm": ("k_gemm_tf32",), "conv": ("k_conv_t", "k_conv_w"), "fmha": ("k_fmha_",)}
+        us = {k: 0.0 for k in fam}
+        launches = {k: 0 for k in fam}
+        total_us = 0.0
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+                continue
+            dur = float(getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0) or 0.0)
+            total_us += dur
+            for k, names in fam.items():
+                if any(n in ev.name for n in names):
+                    us[k] += dur
+                    launches[k] += 1
+        peak, _ = tf32_peak_tflops()
+        out = {}
+        for k in fam:
+            if us[k] > 0:
+                tfs = flops[k] / (us[k] * 1e-6) / 1e12
+                out[k] = {"ms": us[k] / 1000, "launches": launches[k], "tflop": flops[k] / 1e12, "achieved": tfs,
+                          "unit": "TFLOP/s", "peak": peak, "frac": tfs / peak}
+        out["all_kernels_ms"] = total_us / 1000
+        return out
+    except Exception as e:                                                       # CUPTI unavailable (e.g. under ncu)
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def tf32_peak_tflops():

@@ -44,6 +44,15 @@ LS_API int ls_fmha_forward(const LsFmha* a, void* stream /* cudaStream_t */);
 /* dq, dk, dv: same addressing as q, k, v (ld_q, ld_k, ld_v), every element written.  delta (B, H, L) scratch. */
 LS_API int ls_fmha_backward(const LsFmha* a, const float* d_o, float* dq, float* dk, float* dv, float* delta, void* stream);
 
+/* Wide single-head attention (the VAE mid block of src/model/autoencoder/autoencoder_kl.py:99-107: 1024 tokens x 512
+ * channels, one head): the score matrix is small, so it is materialised by ls_gemm_tf32 (S = Q K^T, O = P V and the four
+ * gradient GEMMs, all without transposed copies) and these two kernels do the row softmax in place.
+ *   forward:  x[r, :] <- softmax(scale * x[r, :])
+ *   backward: dp[r, :] <- scale * p[r, :] * (dp[r, :] - sum_j p[r, j] dp[r, j])       (dS from dP)
+ * rows x cols fp32, row stride ld (floats); cols <= 4096, cols % 4 == 0, ld % 4 == 0, 16-byte aligned. */
+LS_API int ls_softmax_rows_forward(float* x, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream);
+LS_API int ls_softmax_rows_backward(const float* p, float* dp, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,14 @@ extern "C" {
 #define LS_GEOM_STRIDE 8          /* floats per Gaussian geometry record                 */
 #define LS_MAX_VALUE_CHANNELS 16  /* colour (0|3) + feature channels blended in one pass */
 
-enum { LS_COLOR_NONE = 0, LS_COLOR_PRECOMP = 1, LS_COLOR_SH = 2 };
+enum { LS_COLOR_NONE = 0, LS_COLOR_PRECOMP = 1,
+       LS_COLOR_SH = 2,       /* colour SH in the basis of the in-tree src/misc/sh_utils.py:42-97 (b1..3 = -C1 x, +C1 y, -C1 z) */
+       LS_COLOR_SH_3DGS = 3   /* [EXT] colour SH in the coefficient order of graphdeco-inria/diff-gaussian-rasterization
+                                 (b1..3 = -C1 y, +C1 z, -C1 x): the in-tree polynomials at (y, z, x), except k = 14 where the
+                                 in-tree file has z(zz - xx) and 3DGS z(xx - yy); degree 4 is an extension.  The reference
+                                 hands `shs` to its fork's CUDA (cuda_splatting.py:91,146), whose basis cannot be inspected
+                                 here; LS_SH_BASIS=intree|3dgs selects between the two candidates in the Python layer.   */
+};
 enum { LS_FEATURE_NONE = 0, LS_FEATURE_PRECOMP = 1, LS_FEATURE_SH = 2 };
 /* forward stages (bit mask); each may be launched separately so that a profiler can bracket it */
 enum { LS_STAGE_GEOMETRY = 1,  /* preprocess + per-tile count + exclusive scan (writes stats[0..2]) */

@@ -106,7 +106,7 @@ class LsFmha(C.Structure):              # include/ls_fmha.h
 
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4
-COLOR_NONE, COLOR_PRECOMP, COLOR_SH = 0, 1, 2
+COLOR_NONE, COLOR_PRECOMP, COLOR_SH, COLOR_SH_3DGS = 0, 1, 2, 3
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
 STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15
 BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
@@ -119,9 +119,12 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_groupnorm_nhwc_forward", "ls_groupnorm_nhwc_backward",
            "ls_conv2d_out_size", "ls_conv2d_forward", "ls_conv2d_dgrad", "ls_conv2d_wgrad", "ls_act_backward",
            "ls_upconv2x_workspace", "ls_upconv2x_forward", "ls_upconv2x_dgrad", "ls_upconv2x_wgrad",
-           "ls_gaussian_head_forward", "ls_gaussian_head_backward", "ls_fmha_forward", "ls_fmha_backward")
+           "ls_gaussian_head_forward", "ls_gaussian_head_backward", "ls_fmha_forward", "ls_fmha_backward",
+           "ls_softmax_rows_forward", "ls_softmax_rows_backward")
 
 _lib = None
+# algorithmic FLOPs handed to our tensor-core kernels, per family (bench.py: in-step aggregate = d FLOPS / d kernel time)
+FLOPS = {"gemm": 0.0, "conv": 0.0, "fmha": 0.0}
 KERNEL_LAUNCHES = [0]   # running count of OUR kernel launches (bench.py reports the per-step delta as gpu_launches)
 
 
@@ -203,6 +206,10 @@ def load() -> C.CDLL:
     lib.ls_fmha_forward.argtypes = [C.POINTER(LsFmha), C.c_void_p]
     lib.ls_fmha_backward.restype = C.c_int
     lib.ls_fmha_backward.argtypes = [C.POINTER(LsFmha)] + [C.c_void_p] * 6
+    lib.ls_softmax_rows_forward.restype = C.c_int
+    lib.ls_softmax_rows_forward.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p]
+    lib.ls_softmax_rows_backward.restype = C.c_int
+    lib.ls_softmax_rows_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p]
     lib.ls_act_backward.restype = C.c_int
     lib.ls_act_backward.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p]
     lib.ls_col_sum.restype = C.c_int

@@ -69,6 +69,9 @@ class _ConvFn(torch.autograd.Function):
                                               None if bias is None else bias.data_ptr(), y.data_ptr(),
                                               None if pre is None else pre.data_ptr(), ACT[act], _stream()), "ls_conv2d_forward")
         _capi.KERNEL_LAUNCHES[0] += R * S if transposed else 1
+        # algorithmic MACs: every (output pixel, Cout, tap, Cin) of a convolution = every (input pixel, ...) of a transposed one
+        ctx.flops = 2.0 * N * (H * W if transposed else oh.value * ow.value) * Cout * R * S * Cin
+        _capi.FLOPS["conv"] += ctx.flops
         ctx.desc, ctx.act, ctx.has_bias = desc, act, bias is not None
         ctx.save_for_backward(x, w, pre if keep_pre else (y if act != "none" else None))
         return y
@@ -88,11 +91,13 @@ class _ConvFn(torch.autograd.Function):
                 _capi.check(lib.ls_conv2d_dgrad(C.byref(desc), gy.data_ptr(), w.data_ptr(), gx.data_ptr(), _stream()),
                             "ls_conv2d_dgrad")
                 _capi.KERNEL_LAUNCHES[0] += 1 if desc.transposed else desc.stride * desc.stride
+                _capi.FLOPS["conv"] += ctx.flops
             if ctx.needs_input_grad[1]:
                 gw = torch.empty_like(w)
                 _capi.check(lib.ls_conv2d_wgrad(C.byref(desc), gy.data_ptr(), x.data_ptr(), gw.data_ptr(), _stream()),
                             "ls_conv2d_wgrad")
                 _capi.KERNEL_LAUNCHES[0] += 1
+                _capi.FLOPS["conv"] += ctx.flops
         if ctx.has_bias and ctx.needs_input_grad[2]:
             from .gemm import col_sum
             gb = col_sum(gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1]))
@@ -119,6 +124,8 @@ class _UpConvFn(torch.autograd.Function):
             _capi.check(lib.ls_upconv2x_forward(C.byref(desc), x.data_ptr(), w.data_ptr(), None if bias is None else bias.data_ptr(),
                                                 y.data_ptr(), wk.data_ptr(), _stream()), "ls_upconv2x_forward")
         _capi.KERNEL_LAUNCHES[0] += 5
+        ctx.flops = 2.0 * N * H * W * 16 * Cout * Cin       # executed: 4 parity classes x 2x2 folded taps (the unfolded form does 36)
+        _capi.FLOPS["conv"] += ctx.flops
         ctx.desc, ctx.has_bias = desc, bias is not None
         ctx.save_for_backward(x, w, wk)
         return y
@@ -136,12 +143,14 @@ class _UpConvFn(torch.autograd.Function):
                 _capi.check(lib.ls_upconv2x_dgrad(C.byref(desc), gy.data_ptr(), wk.data_ptr(), gx.data_ptr(), _stream()),
                             "ls_upconv2x_dgrad")
                 _capi.KERNEL_LAUNCHES[0] += 1
+                _capi.FLOPS["conv"] += ctx.flops
             if ctx.needs_input_grad[1]:
                 gw = torch.empty_like(w)
                 scratch = torch.empty(16 * desc.Cout * desc.Cin, dtype=torch.float32, device=x.device)
                 _capi.check(lib.ls_upconv2x_wgrad(C.byref(desc), gy.data_ptr(), x.data_ptr(), gw.data_ptr(), scratch.data_ptr(),
                                                   _stream()), "ls_upconv2x_wgrad")
                 _capi.KERNEL_LAUNCHES[0] += 5
+                _capi.FLOPS["conv"] += ctx.flops
         if ctx.has_bias and ctx.needs_input_grad[2]:
             from .gemm import col_sum
             gb = col_sum(gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1]))

@@ -18,6 +18,7 @@ constexpr float kTMin = 0.0001f;            // [EXT] early stop
 
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int n_color(int color_mode) { return color_mode == LS_COLOR_NONE ? 0 : 3; }
+__host__ __device__ inline bool color_is_sh(int color_mode) { return color_mode == LS_COLOR_SH || color_mode == LS_COLOR_SH_3DGS; }
 
 // ---- exact-order arithmetic (mirrors oracle/raster_oracle.c FMA/MUL/ADD) ----------------
 // Everything that decides sort keys, radii and tile rectangles uses these, so the
@@ -156,6 +157,17 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
         db[23][0] = -6.f * c41 * xy * z; db[23][1] = c41 * z * (zz - 3.f * xx); db[23][2] = 3.f * c41 * y * (zz - xx);
         db[24][0] = c48 * 4.f * x * (xx - 3.f * zz); db[24][1] = 0.f; db[24][2] = c48 * 4.f * z * (zz - 3.f * xx);
     }
+}
+
+// [EXT] stock-3DGS colour SH (graphdeco computeColorFromSH, degrees 0..3) in terms of the basis above: coefficient k of 3DGS at
+// direction (x, y, z) is the in-tree polynomial k at (X, Y, Z) = (y, z, x) -- for every k except 14, where the in-tree file has
+// z (zz - xx) (sh_utils.py:83) and 3DGS has z (xx - yy) = Y (ZZ - XX).  Call after sh_basis(deg, y, z, x, ...).
+template <bool kGrad>
+__device__ __forceinline__ void sh_patch_3dgs(int deg, float X, float Y, float Z, float* __restrict__ b, float (*__restrict__ db)[3]) {
+    if (deg < 3) return;
+    const float c35 = 1.445305721320277f;
+    b[14] = c35 * Y * (Z * Z - X * X);
+    if (kGrad) { db[14][0] = -2.f * c35 * X * Y; db[14][1] = c35 * (Z * Z - X * X); db[14][2] = 2.f * c35 * Y * Z; }
 }
 
 // geometry record slot 7: two fp16 half-extents (x, y) of the alpha >= 1/255 region, rounded up

@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
 
     // colour / feature inputs
     const int ncol = n_color(sc.color_mode);
-    const bool need_dir = sc.color_mode == LS_COLOR_SH || sc.feature_mode == LS_FEATURE_SH;
+    const bool color_sh = color_is_sh(sc.color_mode), permuted = sc.color_mode == LS_COLOR_SH_3DGS;
+    const bool need_dir = color_sh || sc.feature_mode == LS_FEATURE_SH;
     float u[3] = {0.f, 0.f, 0.f}, inv = 0.f;
     float ddir[3] = {0.f, 0.f, 0.f};
     float basis[25];
@@ -368,16 +369,20 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
         const float d0 = p[0] - cp[0], d1 = p[1] - cp[1], d2 = p[2] - cp[2];
         inv = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
         u[0] = d0 * inv; u[1] = d1 * inv; u[2] = d2 * inv;
-        const int deg = max(sc.color_mode == LS_COLOR_SH ? sc.sh_degree : 0,
-                            sc.feature_mode == LS_FEATURE_SH ? sc.feature_sh_degree : 0);
-        sh_basis<true>(deg, u[0], u[1], u[2], basis, dbasis);
+        if (permuted) {            // [EXT] 3DGS coefficient order: in-tree polynomials at (y, z, x); ddir is un-permuted after the colour loop
+            sh_basis<true>(sc.sh_degree, u[1], u[2], u[0], basis, dbasis);
+            sh_patch_3dgs<true>(sc.sh_degree, u[1], u[2], u[0], basis, dbasis);
+        } else {
+            const int deg = max(color_sh ? sc.sh_degree : 0, sc.feature_mode == LS_FEATURE_SH ? sc.feature_sh_degree : 0);
+            sh_basis<true>(deg, u[0], u[1], u[2], basis, dbasis);
+        }
     }
     if (sc.color_mode == LS_COLOR_PRECOMP) {
         if (alive) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) accum(gr.dL_dcolor_in + 3 * si + ch, r[7 + ch], at);
         }
-    } else if (sc.color_mode == LS_COLOR_SH) {
+    } else if (color_sh) {
         const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1), row = 3 * n;
         const int pitch = gr.color_grad_pitch > 0 ? gr.color_grad_pitch : row;
         const int row_out = gr.color_grad_pitch > 0 ? min(pitch, (row + 7) & ~7) : row;   // pad columns get zeros: whole sectors
@@ -413,6 +418,11 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
                 if (e < len_out) mine[e] = out[e];
             stage_store(stage, dsh0, pitch, c0, len_out, row_mask, at, lane);
         }
+    }
+    if (permuted) {                                            // gradients w.r.t. (y, z, x) back to (x, y, z)
+        const float gx_ = ddir[2], gy_ = ddir[0], gz_ = ddir[1];
+        ddir[0] = gx_; ddir[1] = gy_; ddir[2] = gz_;
+        if (sc.feature_mode == LS_FEATURE_SH && alive) sh_basis<true>(sc.feature_sh_degree, u[0], u[1], u[2], basis, dbasis);
     }
     if (sc.feature_mode == LS_FEATURE_PRECOMP) {
         if (alive)
@@ -495,7 +505,7 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
     const size_t cpitch = gr->color_grad_pitch > 0 ? (size_t)gr->color_grad_pitch : (size_t)3 * (sc->sh_degree + 1) * (sc->sh_degree + 1);
     const size_t fpitch = gr->feature_grad_pitch > 0 ? (size_t)gr->feature_grad_pitch
                                                      : (size_t)sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1);
-    if (sc->color_mode == LS_COLOR_SH && gr->color_grad_pitch > 0 && gr->color_grad_pitch < 3 * (sc->sh_degree + 1) * (sc->sh_degree + 1))
+    if (color_is_sh(sc->color_mode) && gr->color_grad_pitch > 0 && gr->color_grad_pitch < 3 * (sc->sh_degree + 1) * (sc->sh_degree + 1))
         return ls_fail("color_grad_pitch %d is shorter than a coefficient row", gr->color_grad_pitch);
     if (sc->feature_mode == LS_FEATURE_SH && gr->feature_grad_pitch > 0 &&
         gr->feature_grad_pitch < sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1))
@@ -506,7 +516,7 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
         cudaMemsetAsync(gr->dL_dopacity, 0, sizeof(float) * SG, stream);
         if (gr->dL_dmeans2D) cudaMemsetAsync(gr->dL_dmeans2D, 0, sizeof(float) * VG * 3, stream);
         if (sc->color_mode == LS_COLOR_PRECOMP) cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * 3, stream);
-        if (sc->color_mode == LS_COLOR_SH) cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * cpitch, stream);
+        if (color_is_sh(sc->color_mode)) cudaMemsetAsync(gr->dL_dcolor_in, 0, sizeof(float) * SG * cpitch, stream);
         if (sc->feature_mode == LS_FEATURE_PRECOMP) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C, stream);
         if (sc->feature_mode == LS_FEATURE_SH) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * fpitch, stream);
     }

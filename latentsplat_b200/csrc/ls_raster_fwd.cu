@@ -90,18 +90,24 @@ __global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, cons
     // ---- colour / feature values of this Gaussian for this view -----------------------
     const int ncol = n_color(sc.color_mode);
     float* crec = st.chan + vi * st.chan_stride;
-    const bool need_dir = sc.color_mode == LS_COLOR_SH || sc.feature_mode == LS_FEATURE_SH;
+    const bool color_sh = color_is_sh(sc.color_mode), permuted = sc.color_mode == LS_COLOR_SH_3DGS;
+    const bool need_dir = color_sh || sc.feature_mode == LS_FEATURE_SH;
     float basis[25];
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
     if (need_dir) {
         const float* cp = sc.campos + 3 * v;
-        float d0 = p[0] - cp[0], d1 = p[1] - cp[1], d2 = p[2] - cp[2];
+        d0 = p[0] - cp[0]; d1 = p[1] - cp[1]; d2 = p[2] - cp[2];
         const float inv = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
         d0 *= inv; d1 *= inv; d2 *= inv;
-        const int deg = max(sc.color_mode == LS_COLOR_SH ? sc.sh_degree : 0,
-                            sc.feature_mode == LS_FEATURE_SH ? sc.feature_sh_degree : 0);
-        sh_basis<false>(deg, d0, d1, d2, basis, nullptr);
+        if (permuted) {            // [EXT] 3DGS order: in-tree polynomials at (y, z, x), k = 14 patched; features keep the in-tree basis
+            sh_basis<false>(sc.sh_degree, d1, d2, d0, basis, nullptr);
+            sh_patch_3dgs<false>(sc.sh_degree, d1, d2, d0, basis, nullptr);
+        } else {
+            const int deg = max(color_sh ? sc.sh_degree : 0, sc.feature_mode == LS_FEATURE_SH ? sc.feature_sh_degree : 0);
+            sh_basis<false>(deg, d0, d1, d2, basis, nullptr);
+        }
     }
-    if (sc.color_mode == LS_COLOR_SH) {
+    if (color_sh) {
         const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1);
         const float* __restrict__ sh = sc.color + si * (size_t)(n * 3);
         float r = 0.f, g = 0.f, b = 0.f;
@@ -119,6 +125,7 @@ __global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, cons
     if (sc.feature_mode == LS_FEATURE_PRECOMP) {
         for (int c = 0; c < sc.C; ++c) crec[ncol + c] = sc.feature[si * sc.C + c];
     } else if (sc.feature_mode == LS_FEATURE_SH) {
+        if (permuted) sh_basis<false>(sc.feature_sh_degree, d0, d1, d2, basis, nullptr);
         const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1);
         const float* __restrict__ fs = sc.feature + si * (size_t)(sc.C * n);
         for (int c = 0; c < sc.C; ++c) {
@@ -537,7 +544,7 @@ int ls_validate_scene(const LsRasterScene* sc) {
     if (!sc) return ls_fail("scene is NULL");
     if (sc->n_views <= 0 || sc->G < 0 || sc->H <= 0 || sc->W <= 0) return ls_fail("bad sizes V=%d G=%d H=%d W=%d", sc->n_views, sc->G, sc->H, sc->W);
     if (sc->views_per_scene <= 0 || sc->n_views % sc->views_per_scene) return ls_fail("n_views %d not a multiple of views_per_scene %d", sc->n_views, sc->views_per_scene);
-    if (sc->color_mode < 0 || sc->color_mode > 2) return ls_fail("bad color_mode %d", sc->color_mode);
+    if (sc->color_mode < 0 || sc->color_mode > LS_COLOR_SH_3DGS) return ls_fail("bad color_mode %d", sc->color_mode);
     if (sc->feature_mode < 0 || sc->feature_mode > 2) return ls_fail("bad feature_mode %d", sc->feature_mode);
     if (sc->C < 0 || (sc->feature_mode == LS_FEATURE_NONE) != (sc->C == 0)) return ls_fail("feature_mode %d inconsistent with C=%d", sc->feature_mode, sc->C);
     if (sc->sh_degree < 0 || sc->sh_degree > 4 || sc->feature_sh_degree < 0 || sc->feature_sh_degree > 4) return ls_fail("SH degree out of range (0..4)");

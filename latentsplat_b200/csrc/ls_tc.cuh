@@ -27,9 +27,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 24)) __trap();   // a protocol bug must fail loudly, never hang the device
+    if (mbar_try_wait(bar, parity)) return;
+    // a protocol bug must fail loudly, never hang the device: trap after 4 s of wall time (a try_wait may itself block for a
+    // hardware-dependent while, so a spin count alone bounds nothing)
+    const uint64_t t0 = global_timer_ns();
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins)
+        if ((spins & 255u) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");

@@ -52,6 +52,7 @@ def gemm_tf32(A: Tensor, B: Tensor, *, M: int, N: int, K: int, a_mn: bool = Fals
     with torch.cuda.device(A.device):
         _capi.check(_capi.load().ls_gemm_tf32(C.byref(args), torch.cuda.current_stream().cuda_stream), "ls_gemm_tf32")
     _capi.KERNEL_LAUNCHES[0] += 1
+    _capi.FLOPS["gemm"] += 2.0 * M * N * K
     return out
 
 

@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
+from latentsplat_b200 import fmha  # attention cores on our kernels (CUDA)
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200.norm import GroupNorm, group_norm_tokens  # GroupNorm with the following SiLU fused in (sm_100a kernels on CUDA)
 from latentsplat_b200.conv import Conv2d  # nn.Conv2d on the tcgen05 implicit-GEMM kernels (NHWC / channels_last on CUDA)
@@ -55,7 +56,10 @@ class Attention(nn.Module):
         gn = self.group_norm
         t = group_norm_tokens(t, gn.num_groups, gn.weight, gn.bias, gn.eps)
         q, k, v = self.to_q(t), self.to_k(t), self.to_v(t)
-        t = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        if fmha.wide_supported(q, k, v):
+            t = fmha.attention_wide(q, k, v, c ** -0.5)        # scores through our GEMM + in-place row softmax
+        else:
+            t = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
         t = self.to_out[1](self.to_out[0](t))
         # x first: the sum inherits x's memory format, so the residual stream keeps one layout up the decoder
         return x + t.reshape(b, h, w, c).permute(0, 3, 1, 2)

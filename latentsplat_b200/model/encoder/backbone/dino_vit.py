@@ -13,6 +13,7 @@ import math
 import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
+from latentsplat_b200 import fmha  # tcgen05 flash-attention core (CUDA)
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 from latentsplat_b200.norm import LayerNorm  # nn.LayerNorm on our warp-per-row kernel on CUDA
 from latentsplat_b200.conv import Conv2d  # nn.Conv2d with the bias add / bias gradient on our kernels (CUDA)
@@ -78,8 +79,11 @@ class Attention(nn.Module):
         """proj(attention(qkv(x))) (+ residual): the block's skip connection rides in proj's epilogue."""
         B, N, C = x.shape
         qkv = self.qkv(x)
+        if fmha.supported(qkv, self.num_heads):
+            # our tcgen05 flash-attention core, reading the packed fp32 projection in place (TF32 operands)
+            return self.proj(fmha.attention_packed(qkv, self.num_heads, self.scale), residual=residual)
         if x.is_cuda and ATTENTION_BF16:
-            # library flash-attention on a bf16 copy of q/k/v (fp32 SDPA lands on an sm_80 SIMT kernel: 30 ms/step)
+            # A/B arm (fmha.ENABLED = False): library flash-attention on a bf16 copy of q/k/v
             return self.proj(_Bf16AttentionCore.apply(qkv, self.num_heads, self.scale), residual=residual)
         qkv = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
@@ -109,7 +113,7 @@ class PatchEmbed(nn.Module):
         return self.proj(x).flatten(2).transpose(1, 2)
 
 
-ATTENTION_BF16 = True     # DINO self-attention core in bf16 flash-attention on CUDA (q/k/v projections stay TF32/fp32)
+ATTENTION_BF16 = True     # comparator only: library bf16 flash-attention, used when latentsplat_b200.fmha.ENABLED is False
 
 CONFIGS = {"dino_vits16": (16, 384, 12, 6), "dino_vits8": (8, 384, 12, 6),
            "dino_vitb16": (16, 768, 12, 12), "dino_vitb8": (8, 768, 12, 12)}

@@ -8,6 +8,7 @@ import torch
 from torch import nn
 
 from latentsplat_b200 import attention as fused
+from latentsplat_b200 import fmha
 from latentsplat_b200.gemm import Linear  # nn.Linear with tcgen05 TF32 GEMMs on CUDA
 
 
@@ -28,7 +29,11 @@ class Attention(nn.Module):
 
     def forward(self, x, z=None):
         if z is None:
-            q, k, v = self.to_qkv(x).chunk(3, dim=-1)
+            qkv = self.to_qkv(x)
+            if not self.attend._forward_hooks and fmha.supported(qkv, self.heads):
+                # self-attention (ImageSelfAttention: 4 heads x 128): tcgen05 flash-attention core on the packed projection
+                return self.to_out(fmha.attention_packed(qkv, self.heads, self.scale))
+            q, k, v = qkv.chunk(3, dim=-1)
         else:
             q = self.to_q(x)
             # Epipolar cross-attention: one query per ray.  (1) weight-absorbed form: to_kv is folded into the query and

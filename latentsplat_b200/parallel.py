@@ -59,6 +59,86 @@ class FlatGradients:
         return total
 
 
+class BucketedAllReduce:
+    """Gradient averaging overlapped with the backward pass (the job DDP's reducer does for the reference, src/main.py:98).
+
+    The flat buffer of a `FlatGradients` is cut into contiguous buckets in parameter order.  A post-accumulate hook on every
+    parameter counts its bucket down; the moment a bucket is complete its all-reduce is enqueued on a communication stream that
+    first waits for the stream the gradient was produced on.  Backward reaches the modules in reverse order, so the decoder /
+    discriminator buckets travel while the encoder is still differentiating and only the last bucket (the first ViT blocks) is
+    exposed.  `finish()` sends whatever is left (parameters that took no part in this step keep their zero-filled slices) and
+    makes the current stream wait for the communication stream.
+
+    Everything is stream-ordered and free of host syncs, so the whole begin() .. backward .. finish() sequence can be captured
+    into a CUDA graph (NCCL collectives are capturable): the replay then overlaps NVLink traffic with the remaining kernels
+    with no Python in between.  The same code runs on gloo (CPU tests): there the collectives are synchronous."""
+
+    def __init__(self, fgrads: FlatGradients, bucket_bytes: int = 32 << 20, group=None):
+        self.fgrads, self.group = fgrads, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.cuda = fgrads.flat.is_cuda
+        self.comm = torch.cuda.Stream(fgrads.flat.device) if self.cuda else None
+        self.avg = self.cuda                                   # NCCL averages inside the collective; gloo: SUM then divide
+        self.buckets: List[List[int]] = []                     # [start, end, n_params]
+        self.bucket_of = {}
+        off, start, count = 0, 0, 0
+        limit = max(1, bucket_bytes // fgrads.flat.element_size())
+        for p in fgrads.params:
+            self.bucket_of[id(p)] = len(self.buckets)
+            off += p.numel()
+            count += 1
+            if off - start >= limit:
+                self.buckets.append([start, off, count])
+                start, count = off, 0
+        if count:
+            self.buckets.append([start, off, count])
+        self.remaining = [b[2] for b in self.buckets]
+        self.sent = [False] * len(self.buckets)
+        self.active = False
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in fgrads.params] if self.world > 1 else []
+
+    def begin(self) -> None:
+        """Call before the backward pass of every step (inside the captured function when the step is a CUDA graph)."""
+        self.remaining = [b[2] for b in self.buckets]
+        self.sent = [False] * len(self.buckets)
+        self.active = self.world > 1
+
+    def _send(self, i: int) -> None:
+        self.sent[i] = True
+        seg = self.fgrads.flat[self.buckets[i][0]:self.buckets[i][1]]
+        if self.cuda:
+            self.comm.wait_stream(torch.cuda.current_stream(seg.device))      # the gradients of this bucket are complete
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(seg, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+            seg.div_(self.world)
+
+    def _hook(self, p: nn.Parameter) -> None:
+        if not self.active:
+            return
+        i = self.bucket_of[id(p)]
+        self.remaining[i] -= 1
+        if self.remaining[i] == 0 and not self.sent[i]:
+            self._send(i)
+
+    def finish(self) -> None:
+        """After backward: reduce the buckets that never completed and join the communication stream."""
+        if not self.active:
+            return
+        self.active = False
+        for i in range(len(self.buckets) - 1, -1, -1):
+            if not self.sent[i]:
+                self._send(i)
+        if self.cuda:
+            torch.cuda.current_stream(self.fgrads.flat.device).wait_stream(self.comm)
+
+    def remove(self) -> None:
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+
 def shard_batch(batch: dict, rank: int, world: int) -> dict:
     """Rows rank::world of every tensor's leading (scene) dimension -- scene pairs never interact (SURVEY.md 8e)."""
     return {k: (shard_batch(v, rank, world) if isinstance(v, dict) else v[rank::world]) for k, v in batch.items()}

@@ -12,6 +12,7 @@ No CPU path exists: tensors must live on a CUDA device and the library must be b
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import NamedTuple, Optional
 
 import torch
@@ -19,7 +20,92 @@ from torch import Tensor, nn
 
 from . import _capi
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_views", "RasterDebug", "RasterCall"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_views", "RasterDebug", "RasterCall",
+           "RasterCapacityError", "check_overflow", "reserve_overflow_slots"]
+
+
+class RasterCapacityError(RuntimeError):
+    """A sync-free (`capacity=`) rasterizer call needed more (tile, Gaussian) slots than it was given: the affected tiles were
+    rendered from truncated lists, so the images / gradients of that call are wrong."""
+
+
+class _OverflowGuard:
+    """Makes the overflow flag of the sync-free mode (stats[2], ls_raster.h) an error instead of a number somebody may read.
+
+    Every capacity-mode forward enqueues a 16-byte copy of its `stats` into pinned host memory right behind its kernels (no
+    synchronisation).  The copies are examined whenever the host next touches the rasterizer -- the next forward or backward
+    call, `GraphedStep.replay()`, or an explicit `check_overflow()` -- and the first completed one with the flag set raises
+    RasterCapacityError: at most one step late, never silently.  Inside a CUDA-graph capture the copy becomes a node of the
+    graph writing to a buffer that lives as long as the process, so every replay refreshes it."""
+
+    def __init__(self):
+        self.pending = []       # eager: (event, pinned stats, capacity)
+        self.resident = []      # captured in a CUDA graph: (pinned stats, capacity)
+        self.free = []
+
+    def reserve(self, n: int) -> None:
+        """Pinned buffers cannot be allocated during a stream capture: GraphedStep reserves some beforehand."""
+        while len(self.free) < n:
+            self.free.append(torch.zeros(4, dtype=torch.int32).pin_memory())
+
+    def watch(self, stats: Tensor, capacity: int) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            if not self.free:
+                raise RuntimeError("sync-free rasterizer call inside a CUDA-graph capture without reserved overflow slots: "
+                                   "call latentsplat_b200.rasterizer.reserve_overflow_slots() before capturing")
+            host = self.free.pop()
+            host.copy_(stats, non_blocking=True)
+            self.resident.append((host, capacity))
+            return
+        host = self.free.pop() if self.free else torch.zeros(4, dtype=torch.int32).pin_memory()
+        host.copy_(stats, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(stats.device))
+        self.pending.append((event, host, capacity))
+
+    @staticmethod
+    def _raise(host: Tensor, capacity: int) -> None:
+        needed = int(host[0])
+        host[2] = 0
+        raise RasterCapacityError(f"rasterizer key capacity overflow: a call needed {needed} (tile, Gaussian) slots but was given "
+                                  f"{capacity}; its images and gradients are truncated -- raise `capacity` / recalibrate")
+
+    def poll(self, block: bool = False) -> None:
+        if torch.cuda.is_current_stream_capturing():         # no event queries during a capture; the replay path polls
+            return
+        keep = []
+        failed = None
+        for event, host, capacity in self.pending:
+            if block:
+                event.synchronize()
+            if not event.query():
+                keep.append((event, host, capacity))
+            elif int(host[2]) and failed is None:
+                failed = (host, capacity)
+            else:
+                self.free.append(host)
+        self.pending = keep
+        if failed is None:
+            for host, capacity in self.resident:
+                if int(host[2]):
+                    failed = (host, capacity)
+                    break
+        if failed is not None:
+            self._raise(*failed)
+
+
+_GUARD = _OverflowGuard()
+
+
+def reserve_overflow_slots(n: int = 8) -> None:
+    """Pre-allocate the pinned flag buffers that sync-free calls captured into a CUDA graph will write to."""
+    _GUARD.reserve(n)
+
+
+def check_overflow(block: bool = False) -> None:
+    """Raise RasterCapacityError if any completed sync-free rasterizer call overflowed its key capacity.  `block=True` first waits
+    for the outstanding calls (use at the end of an epoch / before trusting a result); the default never synchronises."""
+    _GUARD.poll(block)
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
@@ -151,13 +237,16 @@ class RasterCall:
         return self.num_rendered
 
     def forward(self):
+        _GUARD.poll()                       # earlier sync-free calls that overflowed raise here (never silently truncated)
         if self.capacity is None:           # exact: one 4-byte D2H sync per batched call
             self.forward_stage(_capi.STAGE_GEOMETRY)
             self.size_keys()
             self.forward_stage(_capi.STAGE_RENDER)
         else:                               # sync-free (CUDA-graph capturable): caller-chosen capacity;
-            self.buf.alloc_keys(int(self.capacity), self.device)   # stats[2] flags an overflow
+            self.buf.alloc_keys(int(self.capacity), self.device)   # stats[2] flags an overflow -> _OverflowGuard
             self.forward_stage(_capi.STAGE_ALL)
+            with torch.cuda.device(self.device):
+                _GUARD.watch(self.buf.stats, int(self.capacity))
         return self.images
 
     @staticmethod
@@ -227,10 +316,21 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_color, g_feature, g_alpha, g_depth, _g_radii):
         call: RasterCall = ctx.call
+        _GUARD.poll()
         gc = lambda t: None if t is None else t.to(torch.float32).contiguous()
         o = call.alloc_grads(ctx.has_means2D)
         call.backward_stage(_capi.BWD_ALL, gc(g_color), gc(g_feature), gc(g_alpha), gc(g_depth))
         return (o["means3D"], o["cov3D"], o["opacity"], o["color"], o["feature"], o["means2D"]) + (None,) * 16
+
+
+def _color_sh_mode() -> int:
+    """Which real-SH convention the colour `shs` use.  The reference passes them to its fork's CUDA (cuda_splatting.py:91,146),
+    whose source is absent [EXT]; the two candidates are the in-tree src/misc/sh_utils.py basis (default, what its features use)
+    and the graphdeco 3DGS coefficient order.  LS_SH_BASIS=intree|3dgs picks one; read per call so tests can flip it."""
+    basis = os.environ.get("LS_SH_BASIS", "intree").lower()
+    if basis not in ("intree", "3dgs"):
+        raise ValueError(f"LS_SH_BASIS must be 'intree' or '3dgs', got {basis!r}")
+    return _capi.COLOR_SH_3DGS if basis == "3dgs" else _capi.COLOR_SH
 
 
 def _normalize(means3D, cov3D, opacities, *, viewmatrix, projmatrix, campos, tanfov, image_height, image_width,
@@ -246,7 +346,7 @@ def _normalize(means3D, cov3D, opacities, *, viewmatrix, projmatrix, campos, tan
     if S == 0 or V % S:
         raise ValueError(f"{V} views cannot be split over {S} scenes")
     if shs is not None:
-        color, color_mode = shs, _capi.COLOR_SH
+        color, color_mode = shs, _color_sh_mode()
         n = shs.shape[2]
         if (sh_degree + 1) ** 2 > n:
             raise ValueError(f"sh_degree {sh_degree} needs {(sh_degree + 1) ** 2} coefficients, got {n}")

@@ -13,6 +13,8 @@ from typing import Callable, Dict
 import torch
 from torch import Tensor
 
+from .rasterizer import check_overflow, reserve_overflow_slots
+
 
 class GraphedStep:
     """`fn(inputs: dict[str, Tensor]) -> dict[str, Tensor]` captured into one CUDA graph.
@@ -25,6 +27,7 @@ class GraphedStep:
                  warmup: int = 3):
         self.fn = fn
         self.static_in = {k: v.clone() for k, v in example_inputs.items()}
+        reserve_overflow_slots()              # pinned flag buffers for the rasterizer calls about to be captured
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -41,6 +44,9 @@ class GraphedStep:
             self.static_in[k].copy_(v, non_blocking=True)
 
     def replay(self) -> Dict[str, Tensor]:
+        # a captured sync-free rasterizer call copies its overflow flag to pinned memory inside the graph: an overflow of an
+        # earlier replay raises here (rasterizer._OverflowGuard), one step late at most
+        check_overflow()
         self.graph.replay()
         return self.static_out
 

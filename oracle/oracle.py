@@ -75,6 +75,13 @@ def _lib(prec: str) -> C.CDLL:
     return _LIBS[prec]
 
 
+def set_color_sh_basis(name: str) -> None:
+    """'intree' (default) or '3dgs': the convention of the colour SH inside the rasterizer ([EXT], raster_oracle.c)."""
+    assert name in ("intree", "3dgs")
+    for prec in ("f32", "f64"):
+        getattr(_lib(prec), f"oracle_set_color_sh_basis_{prec}")(int(name == "3dgs"))
+
+
 def _ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
 
@@ -176,15 +183,15 @@ def backward(r: OracleRender, *, dL_dcolor=None, dL_dfeature=None, dL_dalpha=Non
     return g
 
 
-def sh_eval(deg: int, sh: np.ndarray, dirs: np.ndarray, prec="f64") -> np.ndarray:
-    """sh: (N, n_ch, n_coeff) as in sh_utils.eval_sh; dirs: (N,3) unit. Returns (N, n_ch)."""
+def sh_eval(deg: int, sh: np.ndarray, dirs: np.ndarray, prec="f64", order: str = "intree") -> np.ndarray:
+    """sh: (N, n_ch, n_coeff) as in sh_utils.eval_sh; dirs: (N,3) unit. Returns (N, n_ch).  order='3dgs': [EXT] stock 3DGS order."""
     creal, npreal = _real(prec)
     lib = _lib(prec)
     sh = np.ascontiguousarray(np.swapaxes(np.asarray(sh, dtype=npreal), 1, 2))  # -> (N, n_coeff, n_ch)
     dirs = np.ascontiguousarray(dirs, dtype=npreal)
     N, ncoef, nch = sh.shape
     out = np.zeros((N, nch), npreal)
-    fn = getattr(lib, f"oracle_sh_eval_{prec}")
+    fn = getattr(lib, f"oracle_sh_eval_{prec}" if order == "intree" else f"oracle_sh_eval_3dgs_{prec}")
     for n in range(N):
         fn(int(deg), int(nch), _ptr(sh[n], creal), _ptr(dirs[n], creal), _ptr(out[n], creal))
     return out

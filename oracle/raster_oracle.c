@@ -25,9 +25,11 @@
  *                                    mask(1,H,W), depth(1,H,W), _),
  *         decoder_splatting_cuda.py:45-47  feature background is 0 and the
  *                                    mask is the accumulated alpha;
- *   (2) the colour-SH basis of the in-tree src/misc/sh_utils.py:42-97
- *       (degree <= 4; note its x/y/z roles differ from stock 3DGS), pinned by
- *       tests/golden/sh_eval.npz generated from that file;
+ *   (2) the SH polynomials of the in-tree src/misc/sh_utils.py:42-97 (degree <= 4), pinned by
+ *       tests/golden/sh_eval.npz generated from that file.  The reference applies that function to the
+ *       FEATURES only (cuda_splatting.py:97); colour `shs` go to the fork's CUDA, so WHICH basis the colours
+ *       use inside the rasterizer is [EXT]: in-tree order by default, stock-3DGS order (the same polynomials
+ *       at (y, z, x), k = 14 patched) through oracle_set_color_sh_basis(1) -- see g_color_sh_3dgs below;
  *   (3) the published algorithm of the lineage the fork descends from
  *       (graphdeco-inria/diff-gaussian-rasterization: 16x16 tiles, near cull
  *       z_view <= 0.2, tan-fov clamp 1.3, +0.3 px^2 dilation, 3-sigma radius
@@ -173,12 +175,42 @@ static void sh_basis(int deg, real x, real y, real z, real *b, real (*db)[3]) {
     }
 }
 
+/* [EXT] Which convention the colour `shs` use inside the rasterizer: 0 = the in-tree basis above (default), 1 = the
+ * coefficient order of graphdeco-inria/diff-gaussian-rasterization (b1..3 = -C1 y, +C1 z, -C1 x; ...), see sh_patch_3dgs.
+ * The fork's CUDA is not in /root/reference, so neither can be confirmed; the product
+ * exposes the same switch (LS_COLOR_SH / LS_COLOR_SH_3DGS, env LS_SH_BASIS).  Features always use the in-tree basis
+ * (cuda_splatting.py:97 calls the in-tree eval_sh).                                                                     */
+static int g_color_sh_3dgs = 0;
+/* 3DGS coefficient k at (x, y, z) = in-tree polynomial k at (X, Y, Z) = (y, z, x) for every k of degrees 0..3 except k = 14:
+ * sh_utils.py:83 has z (zz - xx) there, 3DGS z (xx - yy) = Y (ZZ - XX).  Degree 4 is not defined by 3DGS; the permuted
+ * in-tree polynomials are used (an extension).  Apply after sh_basis(deg, y, z, x, ...).                                */
+static void sh_patch_3dgs(int deg, real X, real Y, real Z, real *b, real (*db)[3]) {
+    if (deg < 3) return;
+    const real c35 = (real)SH_C3[5];
+    b[14] = c35 * Y * (Z * Z - X * X);
+    if (db) { db[14][0] = R(-2.0) * c35 * X * Y; db[14][1] = c35 * (Z * Z - X * X); db[14][2] = R(2.0) * c35 * Y * Z; }
+}
+void FN(oracle_set_color_sh_basis)(int use_3dgs) { g_color_sh_3dgs = use_3dgs != 0; }
+
 /* Evaluate n_ch channels of SH (layout sh[k*n_ch + c], i.e. (n_coeff, n_ch)) at
  * unit direction d; result[c] = sum_k basis_k * sh[k][c].  Test helper for the
  * golden SH vectors; also used by the colour path below.                     */
 void FN(oracle_sh_eval)(int deg, int n_ch, const real *sh, const real *dir, real *out) {
     real b[25];
     sh_basis(deg, dir[0], dir[1], dir[2], b, NULL);
+    const int n = (deg + 1) * (deg + 1);
+    for (int c = 0; c < n_ch; ++c) {
+        real r = 0;
+        for (int k = 0; k < n; ++k) r += b[k] * sh[k * n_ch + c];
+        out[c] = r;
+    }
+}
+
+/* Same as oracle_sh_eval in the 3DGS coefficient order ([EXT] switch above); dir is the true (x, y, z). */
+void FN(oracle_sh_eval_3dgs)(int deg, int n_ch, const real *sh, const real *dir, real *out) {
+    real b[25];
+    sh_basis(deg, dir[1], dir[2], dir[0], b, NULL);
+    sh_patch_3dgs(deg, dir[1], dir[2], dir[0], b, NULL);
     const int n = (deg + 1) * (deg + 1);
     for (int c = 0; c < n_ch; ++c) {
         real r = 0;
@@ -372,7 +404,18 @@ int FN(oracle_forward)(const OracleIn *in, OracleOut *out, int n_threads) {
             d[0] *= inv; d[1] *= inv; d[2] *= inv;
             const int n = (in->sh_degree + 1) * (in->sh_degree + 1);
             real col[3];
-            FN(oracle_sh_eval)(in->sh_degree, 3, in->shs + (size_t)i * n * 3, d, col);
+            if (g_color_sh_3dgs) {
+                real bas[25];
+                sh_basis(in->sh_degree, d[1], d[2], d[0], bas, NULL);
+                sh_patch_3dgs(in->sh_degree, d[1], d[2], d[0], bas, NULL);
+                for (int c = 0; c < 3; ++c) {
+                    real acc = 0;
+                    for (int k = 0; k < n; ++k) acc += bas[k] * in->shs[((size_t)i * n + k) * 3 + c];
+                    col[c] = acc;
+                }
+            } else {
+                FN(oracle_sh_eval)(in->sh_degree, 3, in->shs + (size_t)i * n * 3, d, col);
+            }
             for (int k = 0; k < 3; ++k) {
                 col[k] += R(0.5);
                 out->clamped[3 * i + k] = col[k] < 0;
@@ -677,7 +720,12 @@ int FN(oracle_backward)(const OracleIn *in, const OracleOut *out, OracleGrad *gr
             const real inv = R(1.0) / SQRT(len2);
             const real u[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
             real bas[25], dbas[25][3];
-            sh_basis(in->sh_degree, u[0], u[1], u[2], bas, dbas);
+            if (g_color_sh_3dgs) {
+                sh_basis(in->sh_degree, u[1], u[2], u[0], bas, dbas);
+                sh_patch_3dgs(in->sh_degree, u[1], u[2], u[0], bas, dbas);
+            } else {
+                sh_basis(in->sh_degree, u[0], u[1], u[2], bas, dbas);
+            }
             real gc[3];
             for (int k = 0; k < 3; ++k) gc[k] = out->clamped[3 * i + k] ? 0 : gr->dL_dcolors[3 * i + k];
             real ddir[3] = {0, 0, 0};
@@ -689,6 +737,10 @@ int FN(oracle_backward)(const OracleIn *in, const OracleOut *out, OracleGrad *gr
                     sg += sh[k * 3 + ch] * gc[ch];
                 }
                 for (int a3 = 0; a3 < 3; ++a3) ddir[a3] += dbas[k][a3] * sg;
+            }
+            if (g_color_sh_3dgs) {   /* gradients w.r.t. (y, z, x) back to (x, y, z) */
+                const real gx_ = ddir[2], gy_ = ddir[0], gz_ = ddir[1];
+                ddir[0] = gx_; ddir[1] = gy_; ddir[2] = gz_;
             }
             /* through the normalisation u = d/|d| */
             const real dot = u[0] * ddir[0] + u[1] * ddir[1] + u[2] * ddir[2];

@@ -136,7 +136,25 @@ def test_sync_free_capacity_mode_and_cuda_graph_step(cuda):
     dec.raster_capacity = None
     ref2 = fn(x2)
     assert torch.equal(out2["color"], ref2["color"])
-    # too small a capacity is flagged, not silently accepted
+    # too small a capacity is an ERROR at the next host contact with the rasterizer, not a number somebody may read
+    from latentsplat_b200.rasterizer import RasterCapacityError, check_overflow
+    check_overflow(block=True)                               # everything so far fitted
+    dec.raster_capacity = n // 2
+    fn(x)                                                    # (the truncated call itself is asynchronous)
+    assert int(dec.last_raster.stats[2].item()) == 1 and int(dec.last_raster.stats[0].item()) == n
+    with pytest.raises(RasterCapacityError, match=f"needed {n} "):
+        check_overflow(block=True)
+    check_overflow(block=True)                               # reported once
     dec.raster_capacity = n // 2
     fn(x)
-    assert int(dec.last_raster.stats[2].item()) == 1 and int(dec.last_raster.stats[0].item()) == n
+    torch.cuda.synchronize()
+    dec.raster_capacity = None
+    with pytest.raises(RasterCapacityError):                 # the next forward call trips over the earlier overflow by itself
+        fn(x)
+    # ... and inside a CUDA graph: the flag copy is a node of the graph, the replay after the overflowing one raises
+    dec.raster_capacity = n // 2
+    small = GraphedStep(fn, x, warmup=0)
+    small.replay()
+    torch.cuda.synchronize()
+    with pytest.raises(RasterCapacityError):
+        small.replay()

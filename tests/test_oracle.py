@@ -178,3 +178,26 @@ def test_backward_matches_finite_differences(color):
             num = (loss(dp) - loss(dm)) / (2 * h)
             ana = g[gname].reshape(x.shape)[idx]
             assert ana == pytest.approx(num, rel=2e-4, abs=1e-6), f"{key}{idx}: analytic {ana} vs numeric {num}"
+
+
+def test_colour_sh_3dgs_order_matches_the_published_polynomials():
+    """[EXT] switch of raster_oracle.c: order='3dgs' (in-tree polynomials at (y, z, x), k = 14 patched) equals the stock 3DGS
+    colour-SH evaluation (computeColorFromSH of graphdeco-inria/diff-gaussian-rasterization, degrees 0..3, written out here)."""
+    rng = np.random.default_rng(3)
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    for _ in range(20):
+        dvec = rng.standard_normal(3)
+        x, y, z = dvec / np.linalg.norm(dvec)
+        sh = rng.standard_normal((16, 3))
+        want = C0 * sh[0] - C1 * y * sh[1] + C1 * z * sh[2] - C1 * x * sh[3]
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        want = want + C2[0] * xy * sh[4] + C2[1] * yz * sh[5] + C2[2] * (2 * zz - xx - yy) * sh[6] + C2[3] * xz * sh[7] \
+            + C2[4] * (xx - yy) * sh[8]
+        want = want + C3[0] * y * (3 * xx - yy) * sh[9] + C3[1] * xy * z * sh[10] + C3[2] * y * (4 * zz - xx - yy) * sh[11] \
+            + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[12] + C3[4] * x * (4 * zz - xx - yy) * sh[13] \
+            + C3[5] * z * (xx - yy) * sh[14] + C3[6] * x * (xx - 3 * yy) * sh[15]
+        got = oracle.sh_eval(3, sh.T[None], np.array([[x, y, z]]), prec="f64", order="3dgs")[0]     # (1, n_ch, n_coeff), (1, 3)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13)

@@ -430,3 +430,28 @@ def test_forward_matches_oracle_at_stress_size_512_250k(cuda):
     _check_binning(r, dbg)
     _check_images(out, r, has_color=True, C=4)
     assert (r.flip_bound > 0).mean() < 0.02
+
+
+def test_colour_sh_basis_switch_3dgs_matches_oracle(cuda, monkeypatch):
+    """[EXT] switch: LS_SH_BASIS=3dgs evaluates the colour SH in the stock 3DGS coefficient order (the in-tree polynomials at
+    (y, z, x)); forward and backward against the oracle in the same mode, and the default mode must differ from it."""
+    d = helpers.raster_case(G=3000, H=64, W=64, seed=77, C=2, color="sh", sh_degree=3, s_px=(1.0, 5.0), opacity=(0.05, 0.5))
+    w = _grad_weights(d, 2, 11)
+    out_intree, _, _ = _run_gpu(d, cuda)
+    monkeypatch.setenv("LS_SH_BASIS", "3dgs")
+    oracle.set_color_sh_basis("3dgs")
+    try:
+        r = oracle.forward(**d, n_threads=0, margin_eps=2e-5)
+        g_ref = oracle.backward(r, dL_dcolor=w["color"], dL_dfeature=w["feature"], dL_dalpha=w["alpha"], dL_ddepth=w["depth"],
+                                n_threads=1)
+    finally:
+        oracle.set_color_sh_basis("intree")
+    out, dbg, g = _run_gpu(d, cuda, grads=w)
+    _check_binning(r, dbg)
+    _check_images(out, r, has_color=True, C=2)
+    ok = r.marginal == 0
+    _assert_grad(g["shs"][ok], g_ref["dL_dshs"][ok], "shs (3dgs order)")
+    _assert_grad(g["means3D"][ok], g_ref["dL_dmeans3D"][ok], "means3D (3dgs order)")
+    _assert_grad(g["features"][ok], g_ref["dL_dfeatures"][ok], "features")
+    diff = (out[0] - out_intree[0]).abs().max().item()
+    assert diff > 1e-3, "the two conventions must give different colours for degree >= 1"
