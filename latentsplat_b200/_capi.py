@@ -106,6 +106,7 @@ class LsFmha(C.Structure):              # include/ls_fmha.h
 
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4
+MAX_VALUE_CHANNELS = 16          # LS_MAX_VALUE_CHANNELS (include/ls_raster.h): colour + feature channels blended in one pass
 COLOR_NONE, COLOR_PRECOMP, COLOR_SH, COLOR_SH_3DGS = 0, 1, 2, 3
 FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
 STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15

@@ -20,7 +20,7 @@ def encoder_cfg() -> EncoderEpipolarCfg:
     """config/model/encoder/epipolar.yaml with the re10k / co3d experiment overrides."""
     return EncoderEpipolarCfg(
         name="epipolar", d_backbone=512, d_feature=128, num_monocular_samples=32, num_surfaces=1, predict_opacity=False,
-        backbone=BackboneDinoCfg("dino", "dino_vitb8"), near_disparity=3.0,
+        backbone=BackboneDinoCfg("dino", "dino_vitb8", pretrained="random"), near_disparity=3.0,
         gaussian_adapter=GaussianAdapterCfg(gaussian_scale_min=0.5, gaussian_scale_max=15.0, color_sh_degree=4,
                                             feature_sh_degree=2),
         apply_bounds_shim=True,

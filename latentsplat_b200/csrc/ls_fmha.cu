@@ -49,28 +49,42 @@ __host__ __device__ constexpr uint32_t idesc(int n, bool b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// The probability / score-gradient tiles never leave the tensor core's own memory: the softmax warps read S (and dP) from TMEM
+// with tcgen05.ld, write P (dS) back IN PLACE with tcgen05.st, and the next MMA takes that tile as its A operand straight from
+// TMEM (tcgen05.mma with [a_tmem]): no shared-memory round trip, no proxy fence, and 32 KB less shared memory per CTA.
+// MMAs execute in issue order, so the MMA that overwrites a score buffer is simply issued behind the one that consumed it.
+// Shared-memory matrix descriptors split into their 32-bit halves: the high word is a compile-time constant per layout and the
+// low word is (address >> 4) | (LBO >> 4) << 16, so stepping through a tile is ONE 32-bit add of a constant per MMA instead of a
+// mask / shift / or chain (the single issuing thread is the bottleneck of these kernels: N = 64 MMAs last only 32 cycles).
+constexpr uint32_t kHiK = (1024u >> 4) | (1u << 14) | (2u << 29);                 // K-major, SBO 1024, SWIZZLE_128B
+constexpr uint32_t kHiMN = (512u >> 4) | (1u << 14) | (1u << 29);                 // MN-major, SBO 512, SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint32_t lo_k(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }                  // LBO 16
+__device__ __forceinline__ uint32_t lo_mn(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint64_t dsc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 template <int D>
 struct Fwd {
     static constexpr int DC = D / 32;
     static constexpr int Q_BYTES = DC * BM * 128;
     static constexpr int K_BYTES = DC * BN * 128;
     static constexpr int V_BYTES = DC * BN * 128;
-    static constexpr int P_BYTES = (BN / 32) * BM * 128;
-    static constexpr int SMEM = Q_BYTES + K_BYTES + V_BYTES + P_BYTES + 1024 + 64;
-    static constexpr int TMEM_COLS = D == 64 ? 128 : 256;        // S: 64 columns, PV: D columns
+    static constexpr int SMEM = Q_BYTES + K_BYTES + V_BYTES + 1024 + 64;
+    static constexpr int TMEM_COLS = D == 64 ? 128 : 256;        // S / P: 64 columns, O: D columns
+    static constexpr int CTAS = D == 64 ? 3 : 1;                 // 65 KB and 128 TMEM columns each
 };
 
+// ---- forward: one CTA per 128-query block, loop over 64-key blocks --------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(128, D == 64 ? 2 : 1)
+__global__ void __launch_bounds__(128, Fwd<D>::CTAS)
 k_fmha_fwd(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
            const __grid_constant__ CUtensorMap map_v, const LsFmha a) {
     using C = Fwd<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t sQ = smem_u32(smem), sK = sQ + C::Q_BYTES, sV = sK + C::K_BYTES, sP = sV + C::V_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::Q_BYTES + C::K_BYTES + C::V_BYTES + C::P_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-    const uint32_t b_q = smem_u32(bars), b_k = b_q + 8, b_v = b_q + 16, b_s = b_q + 24, b_o = b_q + 32;
+    const uint32_t sQ = smem_u32(smem), sK = sQ + C::Q_BYTES, sV = sK + C::K_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::Q_BYTES + C::K_BYTES + C::V_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const uint32_t b_q = smem_u32(bars), b_k = b_q + 8, b_v = b_q + 16, b_s = b_q + 24;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int bh = blockIdx.y, b = bh / a.H, h = bh - b * a.H;
@@ -83,7 +97,7 @@ k_fmha_fwd(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-        for (int i = 0; i < 5; ++i) mbar_init(b_q + 8 * i, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(b_q + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -106,107 +120,123 @@ k_fmha_fwd(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll
         for (int c = 0; c < C::DC; ++c) tma_load_2d(sV + c * (BN * 128), &map_v, b_v, col0 + 32 * c, tok0 + j * BN);
     };
-    if (tid == 0) {
+    const uint32_t q_lo = lo_k(sQ), k_lo = lo_k(sK), v_lo = lo_mn(sV, BN * 128);
+    auto issue_qk = [&]() {                                        // S = Q K^T (K = D in steps of 8)
+#pragma unroll
+        for (int c = 0; c < C::DC; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                tc_mma_tf32(tm_s, dsc(q_lo + ((c * (BM * 128) + k * 32) >> 4), kHiK), dsc(k_lo + ((c * (BN * 128) + k * 32) >> 4), kHiK),
+                            idesc(BN, false), (c | k) != 0 ? 1u : 0u);
+    };
+    if (warp == 0 && elect_one()) {                                // one elected lane issues every TMA load and MMA
         mbar_expect_tx(b_q, C::Q_BYTES);
 #pragma unroll
         for (int c = 0; c < C::DC; ++c) tma_load_2d(sQ + c * (BM * 128), &map_q, b_q, col0 + 32 * c, tok0 + q0);
         load_k(0);
         load_v(0);
+        mbar_wait(b_q, 0);
+        mbar_wait(b_k, 0);
+        tc_fence_after();
+        issue_qk();
+        tc_commit(b_s);
     }
 
     const float sl2 = a.scale * kLog2e;
-    float m = -INFINITY, l = 0.f;
-    float o[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = 0.f;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;        // this warp's TMEM lane quarter
+    float m_ref = -INFINITY, l = 0.f;                              // reference maximum of the exponentials (lazy), row sum
 
     for (int j = 0; j < nblk; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        if (tid == 0) {
-            if (j == 0) mbar_wait(b_q, 0);
-            mbar_wait(b_k, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < C::DC; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma_tf32(tm_s, make_desc(sQ + c * (BM * 128) + k * 32, 16, 1024, 2), make_desc(sK + c * (BN * 128) + k * 32, 16, 1024, 2),
-                                idesc(BN, false), (c | k) != 0 ? 1u : 0u);
-            tc_commit(b_s);
-        }
-        mbar_wait(b_s, ph);
+        mbar_wait(b_s, (uint32_t)j & 1u);                          // S(j) is complete -- and so is P V (j - 1)
         tc_fence_after();
-        if (tid == 0 && j + 1 < nblk) load_k(j + 1);               // S is complete: the K tile is free
-
-        // ---- online softmax of this thread's row ----
+        if (warp == 0 && elect_one()) {
+            if (j + 1 < nblk) load_k(j + 1);                       // the K tile is free
+            if (j > 0) load_v(j);                                  // the V tile is free
+        }
         uint32_t s0[32], s1[32];
         tc_ld32_nowait(tm_s + lane_base, s0);
         tc_ld32_nowait(tm_s + lane_base + 32, s1);
         tc_wait_ld();
         const int nvalid = a.L - j * BN;                           // keys of this block inside the sequence (>= 1)
         float mx = -INFINITY;
+        if (nvalid >= BN) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float x0 = i < nvalid ? __uint_as_float(s0[i]) * sl2 : -INFINITY;
-            const float x1 = i + 32 < nvalid ? __uint_as_float(s1[i]) * sl2 : -INFINITY;
-            s0[i] = __float_as_uint(x0);
-            s1[i] = __float_as_uint(x1);
-            mx = fmaxf(mx, fmaxf(x0, x1));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i >= nvalid) s0[i] = 0xff800000u;              // -inf: exp2 -> 0
+                if (i + 32 >= nvalid) s1[i] = 0xff800000u;
+                mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+            }
         }
-        const float m_new = fmaxf(m, mx);
-        const float alpha = ex2(m - m_new);                        // 0 on the first block (m = -inf)
+        mx *= sl2;                                                 // scale > 0
+        // Lazy rescaling: the exponentials keep their reference maximum until a row's maximum outgrows it by 2^8; only then is
+        // the running O (in TMEM, quiescent right now) multiplied down.  After the first blocks this is rare.
+        const bool grow = mx > m_ref + 8.f;
+        if (__any_sync(0xffffffffu, grow)) {
+            float alpha = 1.f;
+            if (grow) {
+                alpha = ex2(m_ref - mx);                           // 0 on the first block
+                m_ref = mx;
+                l *= alpha;
+            }
+            if (j > 0) {
+#pragma unroll
+                for (int c = 0; c < D / 32; ++c) {
+                    uint32_t o[32];
+                    tc_ld32(tm_o + lane_base + 32 * c, o);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tc_st32(tm_o + lane_base + 32 * c, o);
+                }
+            }
+        }
         float rs = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {                              // 16-byte units of key chunk 0 and 1
-            float p[4], r[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                p[e] = ex2(__uint_as_float(s0[4 * u + e]) - m_new);
-                r[e] = ex2(__uint_as_float(s1[4 * u + e]) - m_new);
-                rs += p[e] + r[e];
-            }
-            sts128(swz(sP, tid, u), p[0], p[1], p[2], p[3]);
-            sts128(swz(sP + BM * 128, tid, u), r[0], r[1], r[2], r[3]);
+        for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2(fmaf(__uint_as_float(s0[i]), sl2, -m_ref));
+            const float p1 = ex2(fmaf(__uint_as_float(s1[i]), sl2, -m_ref));
+            rs += p0 + p1;
+            s0[i] = __float_as_uint(p0);
+            s1[i] = __float_as_uint(p1);
         }
-        l = fmaf(l, alpha, rs);
-        m = m_new;
-#pragma unroll
-        for (int d = 0; d < D; ++d) o[d] *= alpha;
-        fence_async_smem();                                        // P (generic-proxy stores) -> visible to the tensor core
+        l += rs;
+        tc_st32(tm_s + lane_base, s0);                             // P over S, in place
+        tc_st32(tm_s + lane_base + 32, s1);
+        tc_wait_st();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
-            mbar_wait(b_v, ph);
+            mbar_wait(b_v, (uint32_t)j & 1u);
 #pragma unroll
-            for (int kk = 0; kk < BN / 8; ++kk)                    // 8 keys per MMA: P chunk kk/4, K step kk%4; V: two 4-row atoms
-                tc_mma_tf32(tm_o, make_desc(sP + (kk >> 2) * (BM * 128) + (kk & 3) * 32, 16, 1024, 2),
-                            make_desc(sV + kk * 1024, BN * 128, 512, 1), idesc(D, true), kk != 0 ? 1u : 0u);
-            tc_commit(b_o);
+            for (int kk = 0; kk < BN / 8; ++kk)                    // O += P V, 8 keys per MMA: A = P columns 8 kk.. from TMEM
+                tc_mma_tf32_ts(tm_o, tm_s + 8 * kk, dsc(v_lo + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (j | kk) != 0 ? 1u : 0u);
+            if (j + 1 < nblk) {
+                mbar_wait(b_k, (uint32_t)(j + 1) & 1u);
+                issue_qk();                                        // overwrites P only after the MMAs above have consumed it
+            }
+            tc_commit(b_s);
         }
-        mbar_wait(b_o, ph);
-        tc_fence_after();
-        if (tid == 0 && j + 1 < nblk) load_v(j + 1);               // PV is complete: the V tile (and P) are free
-#pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-            uint32_t pv[32];
-            tc_ld32(tm_o + lane_base + 32 * c, pv);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[32 * c + i] += __uint_as_float(pv[i]);
-        }
-        tc_fence_before();                                         // the next QK / PV overwrite S / PV after the next barrier
     }
-
+    mbar_wait(b_s, (uint32_t)nblk & 1u);
+    tc_fence_after();
     const int q = q0 + tid;
-    if (q < a.L) {
-        const float inv = 1.f / l;
-        float* dst = a.o + (long long)(tok0 + q) * a.ld_o + col0;
+    const float inv = 1.f / l;
+    float* dst = a.o + (long long)(tok0 + q) * a.ld_o + col0;
 #pragma unroll
-        for (int d = 0; d < D; d += 4)
-            *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
-        a.lse[(long long)bh * a.L + q] = m + log2f(l);
+    for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tc_ld32(tm_o + lane_base + 32 * c, o);                     // warp-collective: every lane loads, valid rows store
+        if (q < a.L) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + 32 * c + i) = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
+                                                                           __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+        }
     }
+    if (q < a.L) a.lse[(long long)bh * a.L + q] = m_ref + log2f(l);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -214,7 +244,6 @@ k_fmha_fwd(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
     }
 }
-
 
 // =================================================================================================================
 // backward
@@ -239,40 +268,64 @@ __global__ void __launch_bounds__(256) k_fmha_delta(const float* __restrict__ o,
     }
 }
 
+// Backward kernels: warp-specialised.  Warps 0..7 do the per-element math, two per TMEM lane quarter (warp w: rows
+// 32 (w & 3) .. +31, column half w >> 2); warp 8 issues every TMA load and every tcgen05.mma.  The score tiles S / dP are
+// double-buffered in TMEM and the streamed operand tiles multi-buffered in shared memory: the tensor core computes the scores of
+// block j + 1 while the math warps turn block j into dS (written over dP in TMEM), and the gradient MMA of block j -- A operand
+// straight from TMEM -- queues behind.  The math warps only ever wait for "scores ready"; nothing waits for them but the issuer.
+constexpr int kMathWarps = 8;
+constexpr int kBwdThreads = 32 * (kMathWarps + 1);
+
 template <int D, int BNB>
 struct Bwd {
     static constexpr int DC = D / 32;
     static constexpr int BIG = DC * BM * 128;          // a [128 x D] K-major tile
     static constexpr int SMALL = DC * BNB * 128;       // a [BNB x D] tile (K-major or MN-major)
-    static constexpr int PT = (BNB / 32) * BM * 128;   // a [128 x BNB] K-major tile written by the threads
-    static constexpr int SMEM_DQ = 2 * BIG + 3 * SMALL + PT + 1024 + 128;
-    static constexpr int SMEM_DKV = 2 * BIG + 4 * SMALL + 2 * PT + 2 * BNB * 4 + 1024 + 128;
-    static constexpr int TMEM_DQ = 256;                // S, dP (BNB each), dQ (D)
-    static constexpr int TMEM_DKV = D == 64 ? 256 : 512;   // S^T, dP^T (BNB each), dV, dK (D each)
+    static constexpr int CH = BNB / 2;                 // score columns per math thread
+    // dq: Q, dO resident; (K, V) K-major x KS stages; K MN-major x MS stages
+    static constexpr int DQ_KS = D == 64 ? 3 : 2, DQ_MS = D == 64 ? 2 : 1;
+    static constexpr int SMEM_DQ = 2 * BIG + DQ_KS * 2 * SMALL + DQ_MS * SMALL + 1024 + 256;
+    static constexpr int TMEM_DQ = D == 64 ? 512 : 256;          // 2 x (S, dP) of BNB columns + dQ (D)
+    // dkv: K, V resident; (Q, dO) K-major x QS stages; (Q, dO) MN-major x MS stages; lse / delta of the block's queries
+    static constexpr int DKV_QS = D == 64 ? 3 : 2, DKV_MS = D == 64 ? 2 : 1;
+    static constexpr int SMEM_DKV = 2 * BIG + DKV_QS * 2 * SMALL + DKV_MS * 2 * SMALL + 4 * BNB * 4 + 1024 + 256;
+    static constexpr int TMEM_DKV = 512;                         // 2 x (S^T, dP^T) + dV + dK
 };
+
+__device__ __forceinline__ void math_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 
 // ---- dQ: one CTA per 128-query block, loop over BNB-key blocks ----------------------------------------------------
 template <int D, int BNB>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
               const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
               const __grid_constant__ CUtensorMap map_kmn, const LsFmha a, const float* __restrict__ delta, float* __restrict__ dq) {
     using C = Bwd<D, BNB>;
+    constexpr int KS = C::DQ_KS, MS = C::DQ_MS, CH = C::CH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t sQ = smem_u32(smem), sdO = sQ + C::BIG, sK = sdO + C::BIG, sV = sK + C::SMALL, sKmn = sV + C::SMALL,
-                   sdS = sKmn + C::SMALL;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::BIG + 3 * C::SMALL + C::PT);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-    const uint32_t b_q = smem_u32(bars), b_kv = b_q + 8, b_kmn = b_q + 16, b_s = b_q + 24, b_o = b_q + 32;
+    const uint32_t sQ = smem_u32(smem), sdO = sQ + C::BIG, sK = sdO + C::BIG, sV = sK + KS * C::SMALL, sKmn = sV + KS * C::SMALL;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::BIG + 2 * KS * C::SMALL + MS * C::SMALL);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const uint32_t b0 = smem_u32(bars);
+    const uint32_t b_q = b0, b_kv = b0 + 8 /* [3] */, b_kmn = b0 + 32 /* [2] */, b_sfull = b0 + 48 /* [2] */, b_pready = b0 + 64 /* [2] */,
+                   b_odone = b0 + 80, b_final = b0 + 88;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, b = bh / a.H, h = bh - b * a.H;
     const int q0 = blockIdx.x * BM, tok0 = b * a.L, col0 = h * D;
     const int nblk = (a.L + BNB - 1) / BNB;
 
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(b_q + 8 * i, 1);
+        mbar_init(b_q, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(b_kv + 8 * i, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(b_kmn + 8 * i, 1); mbar_init(b_sfull + 8 * i, 1); mbar_init(b_pready + 8 * i, kMathWarps); }
+        mbar_init(b_odone, 1);
+        mbar_init(b_final, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -283,104 +336,122 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tm_s = tmem, tm_dp = tmem + BNB, tm_dq = tmem + 2 * BNB;
+    const uint32_t tm_dq = tmem + 4 * BNB;                         // S[b] at tmem + 2 b BNB, dP[b] (later dS[b]) right behind it
 
-    auto load_kv = [&](int j) {
-        mbar_expect_tx(b_kv, 2 * C::SMALL);
+    if (warp == kMathWarps) {
+        // ================= issuer warp: TMA + MMA, one lane =================
+        if (elect_one()) {
+            const uint32_t q_lo = lo_k(sQ), do_lo = lo_k(sdO), k_lo = lo_k(sK), v_lo = lo_k(sV), kmn_lo = lo_mn(sKmn, BNB * 128);
+            auto load_kv = [&](int j) {
+                const uint32_t st = (uint32_t)(j % KS), bar = b_kv + 8 * st;
+                mbar_expect_tx(bar, 2 * C::SMALL);
 #pragma unroll
-        for (int c = 0; c < C::DC; ++c) {
-            tma_load_2d(sK + c * (BNB * 128), &map_k, b_kv, col0 + 32 * c, tok0 + j * BNB);
-            tma_load_2d(sV + c * (BNB * 128), &map_v, b_kv, col0 + 32 * c, tok0 + j * BNB);
-        }
-    };
-    auto load_kmn = [&](int j) {
-        mbar_expect_tx(b_kmn, C::SMALL);
-#pragma unroll
-        for (int c = 0; c < C::DC; ++c) tma_load_2d(sKmn + c * (BNB * 128), &map_kmn, b_kmn, col0 + 32 * c, tok0 + j * BNB);
-    };
-    if (tid == 0) {
-        mbar_expect_tx(b_q, 2 * C::BIG);
-#pragma unroll
-        for (int c = 0; c < C::DC; ++c) {
-            tma_load_2d(sQ + c * (BM * 128), &map_q, b_q, col0 + 32 * c, tok0 + q0);
-            tma_load_2d(sdO + c * (BM * 128), &map_do, b_q, col0 + 32 * c, tok0 + q0);
-        }
-        load_kv(0);
-        load_kmn(0);
-    }
-    const int q = q0 + tid;
-    const bool q_ok = q < a.L;
-    const float lse2 = q_ok ? a.lse[(long long)bh * a.L + q] : 0.f;
-    const float dlt = q_ok ? delta[(long long)bh * a.L + q] : 0.f;
-    const float sl2 = a.scale * kLog2e;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-
-    for (int j = 0; j < nblk; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        if (tid == 0) {
-            if (j == 0) mbar_wait(b_q, 0);
-            mbar_wait(b_kv, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < C::DC; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t kd = make_desc(sK + c * (BNB * 128) + k * 32, 16, 1024, 2), vd = make_desc(sV + c * (BNB * 128) + k * 32, 16, 1024, 2);
-                    tc_mma_tf32(tm_s, make_desc(sQ + c * (BM * 128) + k * 32, 16, 1024, 2), kd, idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
-                    tc_mma_tf32(tm_dp, make_desc(sdO + c * (BM * 128) + k * 32, 16, 1024, 2), vd, idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
+                for (int c = 0; c < C::DC; ++c) {
+                    tma_load_2d(sK + st * C::SMALL + c * (BNB * 128), &map_k, bar, col0 + 32 * c, tok0 + j * BNB);
+                    tma_load_2d(sV + st * C::SMALL + c * (BNB * 128), &map_v, bar, col0 + 32 * c, tok0 + j * BNB);
                 }
-            tc_commit(b_s);
-        }
-        mbar_wait(b_s, ph);
-        tc_fence_after();
-        if (tid == 0 && j + 1 < nblk) load_kv(j + 1);
-        const int nvalid = a.L - j * BNB;
+            };
+            auto load_kmn = [&](int j) {
+                const uint32_t st = (uint32_t)(j % MS), bar = b_kmn + 8 * st;
+                mbar_expect_tx(bar, C::SMALL);
 #pragma unroll
-        for (int c = 0; c < BNB / 32; ++c) {
-            uint32_t s[32], dp[32];
-            tc_ld32_nowait(tm_s + lane_base + 32 * c, s);
-            tc_ld32_nowait(tm_dp + lane_base + 32 * c, dp);
-            tc_wait_ld();
+                for (int c = 0; c < C::DC; ++c) tma_load_2d(sKmn + st * C::SMALL + c * (BNB * 128), &map_kmn, bar, col0 + 32 * c, tok0 + j * BNB);
+            };
+            auto issue_s = [&](int j) {                            // S(j) = Q K^T, dP(j) = dO V^T into TMEM buffer j & 1
+                const uint32_t st = (uint32_t)(j % KS), tb = (uint32_t)(j & 1);
+                mbar_wait(b_kv + 8 * st, (uint32_t)(j / KS) & 1u);
+                tc_fence_after();
+                const uint32_t tm_s = tmem + tb * 2 * BNB, tm_dp = tm_s + BNB;
+                const uint32_t kl = k_lo + st * (C::SMALL >> 4), vl = v_lo + st * (C::SMALL >> 4);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float ds[4];
+                for (int c = 0; c < C::DC; ++c)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int i = 4 * u + e;
-                    const float p = (32 * c + i < nvalid) ? ex2(fmaf(__uint_as_float(s[i]), sl2, -lse2)) : 0.f;
-                    ds[e] = p * (__uint_as_float(dp[i]) - dlt) * a.scale;
-                }
-                sts128(swz(sdS + c * (BM * 128), tid, u), ds[0], ds[1], ds[2], ds[3]);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t oa = (c * (BM * 128) + k * 32) >> 4, ob = (c * (BNB * 128) + k * 32) >> 4;
+                        tc_mma_tf32(tm_s, dsc(q_lo + oa, kHiK), dsc(kl + ob, kHiK), idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tm_dp, dsc(do_lo + oa, kHiK), dsc(vl + ob, kHiK), idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
+                    }
+                tc_commit(b_sfull + 8 * tb);
+            };
+            mbar_expect_tx(b_q, 2 * C::BIG);
+#pragma unroll
+            for (int c = 0; c < C::DC; ++c) {
+                tma_load_2d(sQ + c * (BM * 128), &map_q, b_q, col0 + 32 * c, tok0 + q0);
+                tma_load_2d(sdO + c * (BM * 128), &map_do, b_q, col0 + 32 * c, tok0 + q0);
             }
+            for (int j = 0; j < KS && j < nblk; ++j) load_kv(j);
+            for (int j = 0; j < MS && j < nblk; ++j) load_kmn(j);
+            mbar_wait(b_q, 0);
+            issue_s(0);
+            if (nblk > 1) issue_s(1);
+            for (int j = 0; j < nblk; ++j) {
+                // S(j), dP(j) are complete (long ago): their K / V stage takes block j + KS
+                if (j + KS < nblk) {
+                    mbar_wait(b_sfull + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+                    load_kv(j + KS);
+                }
+                if (j >= 1 && j - 1 + MS < nblk) {                 // dQ(j - 1) is complete: its MN-major K stage takes block j - 1 + MS
+                    mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
+                    load_kmn(j - 1 + MS);
+                }
+                mbar_wait(b_pready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);    // dS(j) sits in TMEM over dP(j)
+                mbar_wait(b_kmn + 8 * (j % MS), (uint32_t)(j / MS) & 1u);
+                tc_fence_after();
+                const uint32_t tm_ds = tmem + (uint32_t)(j & 1) * 2 * BNB + BNB, ml = kmn_lo + (uint32_t)(j % MS) * (C::SMALL >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BNB / 8; ++kk)               // dQ += dS K, A = dS columns 8 kk.. from TMEM
+                    tc_mma_tf32_ts(tm_dq, tm_ds + 8 * kk, dsc(ml + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (j | kk) != 0 ? 1u : 0u);
+                tc_commit(b_odone);
+                if (j + 2 < nblk) issue_s(j + 2);                  // overwrites buffer j & 1 behind the MMAs that just consumed it
+            }
+            tc_commit(b_final);                                    // its own barrier: the math warps never followed b_odone's phases
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+    } else {
+        // ================= math warps =================
+        const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+        const int q = q0 + row;
+        const bool q_ok = q < a.L;
+        const float lse2 = q_ok ? a.lse[(long long)bh * a.L + q] : 0.f;
+        const float dlt = q_ok ? delta[(long long)bh * a.L + q] : 0.f;
+        const float sl2 = a.scale * kLog2e;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int j = 0; j < nblk; ++j) {
+            const uint32_t tb = (uint32_t)(j & 1);
+            mbar_wait(b_sfull + 8 * tb, (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
-            mbar_wait(b_kmn, ph);
+            uint32_t s[CH], dp[CH];
+            const uint32_t t_dp = tmem + tb * 2 * BNB + BNB + lane_base + half * CH;
+            tc_ld_nowait(tmem + tb * 2 * BNB + lane_base + half * CH, s);
+            tc_ld_nowait(t_dp, dp);
+            tc_wait_ld();
+            const int nvalid = a.L - j * BNB - half * CH;          // columns of this thread inside the sequence
+            if (nvalid >= CH) {
 #pragma unroll
-            for (int kk = 0; kk < BNB / 8; ++kk)
-                tc_mma_tf32(tm_dq, make_desc(sdS + (kk >> 2) * (BM * 128) + (kk & 3) * 32, 16, 1024, 2),
-                            make_desc(sKmn + kk * 1024, BNB * 128, 512, 1), idesc(D, true), (j | kk) != 0 ? 1u : 0u);
-            tc_commit(b_o);
+                for (int i = 0; i < CH; ++i)
+                    dp[i] = __float_as_uint(ex2(fmaf(__uint_as_float(s[i]), sl2, -lse2)) * (__uint_as_float(dp[i]) - dlt));
+            } else {
+#pragma unroll
+                for (int i = 0; i < CH; ++i)
+                    dp[i] = i < nvalid ? __float_as_uint(ex2(fmaf(__uint_as_float(s[i]), sl2, -lse2)) * (__uint_as_float(dp[i]) - dlt)) : 0u;
+            }
+            tc_st(t_dp, dp);                                       // dS over dP, in place (the 1/sqrt(d) factor is applied to dQ at the end)
+            tc_wait_st();
+            tc_fence_before();
+            warp_arrive(b_pready + 8 * tb, lane);
         }
-        mbar_wait(b_o, ph);                                        // dS and the MN-major K tile are free again
+        mbar_wait(b_final, 0);
         tc_fence_after();
-        if (tid == 0 && j + 1 < nblk) load_kmn(j + 1);
-        tc_fence_before();
-    }
-    {
-        float* dst = dq + (long long)(tok0 + q) * a.ld_q + col0;
+        float* dst = dq + (long long)(tok0 + q) * a.ld_q + col0 + half * (D / 2);
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < D / 64; ++c) {
             uint32_t r[32];
-            tc_ld32(tm_dq + lane_base + 32 * c, r);                // warp-collective: every lane loads, valid rows store
+            tc_ld32(tm_dq + lane_base + half * (D / 2) + 32 * c, r);           // warp-collective: every lane loads, valid rows store
             if (q_ok) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(dst + 32 * c + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                                                               __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    *reinterpret_cast<float4*>(dst + 32 * c + i) =
+                        make_float4(a.scale * __uint_as_float(r[i]), a.scale * __uint_as_float(r[i + 1]),
+                                    a.scale * __uint_as_float(r[i + 2]), a.scale * __uint_as_float(r[i + 3]));
             }
         }
     }
@@ -394,29 +465,37 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
 // ---- dK, dV: one CTA per 128-key block, loop over BNB-query blocks (transposed formulation) -----------------------
 template <int D, int BNB>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                const __grid_constant__ CUtensorMap map_qmn, const __grid_constant__ CUtensorMap map_domn, const LsFmha a,
                const float* __restrict__ delta, float* __restrict__ dk, float* __restrict__ dv) {
     using C = Bwd<D, BNB>;
+    constexpr int QS = C::DKV_QS, MS = C::DKV_MS, CH = C::CH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t sK = smem_u32(smem), sV = sK + C::BIG, sQ = sV + C::BIG, sdO = sQ + C::SMALL, sQmn = sdO + C::SMALL,
-                   sdOmn = sQmn + C::SMALL, sPT = sdOmn + C::SMALL, sdST = sPT + C::PT;
-    float* s_lse = reinterpret_cast<float*>(smem + 2 * C::BIG + 4 * C::SMALL + 2 * C::PT);
-    float* s_dlt = s_lse + BNB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dlt + BNB);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-    const uint32_t b_kv = smem_u32(bars), b_q = b_kv + 8, b_mn = b_kv + 16, b_s = b_kv + 24, b_o = b_kv + 32;
+    const uint32_t sK = smem_u32(smem), sV = sK + C::BIG, sQ = sV + C::BIG, sdO = sQ + QS * C::SMALL, sQmn = sdO + QS * C::SMALL,
+                   sdOmn = sQmn + MS * C::SMALL;
+    constexpr int kStatOff = 2 * C::BIG + 2 * QS * C::SMALL + 2 * MS * C::SMALL;
+    float* s_stat = reinterpret_cast<float*>(smem + kStatOff);                  // [2][2][BNB]: lse, delta
+    const uint32_t s_stat_u32 = sK + kStatOff;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 4 * BNB);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const uint32_t b0 = smem_u32(bars);
+    const uint32_t b_kv = b0, b_q = b0 + 8 /* [3] */, b_mn = b0 + 32 /* [2] */, b_sfull = b0 + 48 /* [2] */, b_pready = b0 + 64 /* [2] */,
+                   b_odone = b0 + 80, b_final = b0 + 88;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, b = bh / a.H, h = bh - b * a.H;
     const int k0 = blockIdx.x * BM, tok0 = b * a.L, col0 = h * D;
     const int nblk = (a.L + BNB - 1) / BNB;
 
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(b_kv + 8 * i, 1);
+        mbar_init(b_kv, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(b_q + 8 * i, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(b_mn + 8 * i, 1); mbar_init(b_sfull + 8 * i, 1); mbar_init(b_pready + 8 * i, kMathWarps); }
+        mbar_init(b_odone, 1);
+        mbar_init(b_final, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -427,118 +506,139 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tm_s = tmem, tm_dp = tmem + BNB, tm_dv = tmem + 2 * BNB, tm_dk = tmem + 2 * BNB + D;
+    const uint32_t tm_dv = tmem + 4 * BNB, tm_dk = tm_dv + D;
 
-    auto load_q = [&](int i) {
-        mbar_expect_tx(b_q, 2 * C::SMALL);
+    if (warp == kMathWarps) {
+        if (elect_one()) {
+            const uint32_t k_lo = lo_k(sK), v_lo = lo_k(sV), q_lo = lo_k(sQ), do_lo = lo_k(sdO), qmn_lo = lo_mn(sQmn, BNB * 128),
+                           domn_lo = lo_mn(sdOmn, BNB * 128);
+            auto load_q = [&](int i) {
+                const uint32_t st = (uint32_t)(i % QS), bar = b_q + 8 * st;
+                mbar_expect_tx(bar, 2 * C::SMALL);
 #pragma unroll
-        for (int c = 0; c < C::DC; ++c) {
-            tma_load_2d(sQ + c * (BNB * 128), &map_q, b_q, col0 + 32 * c, tok0 + i * BNB);
-            tma_load_2d(sdO + c * (BNB * 128), &map_do, b_q, col0 + 32 * c, tok0 + i * BNB);
-        }
-    };
-    auto load_mn = [&](int i) {
-        mbar_expect_tx(b_mn, 2 * C::SMALL);
-#pragma unroll
-        for (int c = 0; c < C::DC; ++c) {
-            tma_load_2d(sQmn + c * (BNB * 128), &map_qmn, b_mn, col0 + 32 * c, tok0 + i * BNB);
-            tma_load_2d(sdOmn + c * (BNB * 128), &map_domn, b_mn, col0 + 32 * c, tok0 + i * BNB);
-        }
-    };
-    if (tid == 0) {
-        mbar_expect_tx(b_kv, 2 * C::BIG);
-#pragma unroll
-        for (int c = 0; c < C::DC; ++c) {
-            tma_load_2d(sK + c * (BM * 128), &map_k, b_kv, col0 + 32 * c, tok0 + k0);
-            tma_load_2d(sV + c * (BM * 128), &map_v, b_kv, col0 + 32 * c, tok0 + k0);
-        }
-        load_q(0);
-        load_mn(0);
-    }
-    const float sl2 = a.scale * kLog2e;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-
-    for (int i = 0; i < nblk; ++i) {
-        const uint32_t ph = (uint32_t)i & 1u;
-        if (tid < BNB) {                                           // softmax statistics of this block's queries
-            const int q = i * BNB + tid;
-            s_lse[tid] = q < a.L ? a.lse[(long long)bh * a.L + q] : INFINITY;      // +inf -> p = 0 for queries outside the sequence
-            s_dlt[tid] = q < a.L ? delta[(long long)bh * a.L + q] : 0.f;
-        }
-        if (tid == 0) {
-            if (i == 0) mbar_wait(b_kv, 0);
-            mbar_wait(b_q, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < C::DC; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t qd = make_desc(sQ + c * (BNB * 128) + k * 32, 16, 1024, 2), od = make_desc(sdO + c * (BNB * 128) + k * 32, 16, 1024, 2);
-                    tc_mma_tf32(tm_s, make_desc(sK + c * (BM * 128) + k * 32, 16, 1024, 2), qd, idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
-                    tc_mma_tf32(tm_dp, make_desc(sV + c * (BM * 128) + k * 32, 16, 1024, 2), od, idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
+                for (int c = 0; c < C::DC; ++c) {
+                    tma_load_2d(sQ + st * C::SMALL + c * (BNB * 128), &map_q, bar, col0 + 32 * c, tok0 + i * BNB);
+                    tma_load_2d(sdO + st * C::SMALL + c * (BNB * 128), &map_do, bar, col0 + 32 * c, tok0 + i * BNB);
                 }
-            tc_commit(b_s);
+            };
+            auto load_mn = [&](int i) {
+                const uint32_t st = (uint32_t)(i % MS), bar = b_mn + 8 * st;
+                mbar_expect_tx(bar, 2 * C::SMALL);
+#pragma unroll
+                for (int c = 0; c < C::DC; ++c) {
+                    tma_load_2d(sQmn + st * C::SMALL + c * (BNB * 128), &map_qmn, bar, col0 + 32 * c, tok0 + i * BNB);
+                    tma_load_2d(sdOmn + st * C::SMALL + c * (BNB * 128), &map_domn, bar, col0 + 32 * c, tok0 + i * BNB);
+                }
+            };
+            auto issue_s = [&](int i) {                            // S^T(i) = K Q^T, dP^T(i) = V dO^T into TMEM buffer i & 1
+                const uint32_t st = (uint32_t)(i % QS), tb = (uint32_t)(i & 1);
+                mbar_wait(b_q + 8 * st, (uint32_t)(i / QS) & 1u);
+                tc_fence_after();
+                const uint32_t tm_s = tmem + tb * 2 * BNB, tm_dp = tm_s + BNB;
+                const uint32_t ql = q_lo + st * (C::SMALL >> 4), ol = do_lo + st * (C::SMALL >> 4);
+#pragma unroll
+                for (int c = 0; c < C::DC; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t oa = (c * (BM * 128) + k * 32) >> 4, ob = (c * (BNB * 128) + k * 32) >> 4;
+                        tc_mma_tf32(tm_s, dsc(k_lo + oa, kHiK), dsc(ql + ob, kHiK), idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tm_dp, dsc(v_lo + oa, kHiK), dsc(ol + ob, kHiK), idesc(BNB, false), (c | k) != 0 ? 1u : 0u);
+                    }
+                tc_commit(b_sfull + 8 * tb);
+            };
+            mbar_expect_tx(b_kv, 2 * C::BIG);
+#pragma unroll
+            for (int c = 0; c < C::DC; ++c) {
+                tma_load_2d(sK + c * (BM * 128), &map_k, b_kv, col0 + 32 * c, tok0 + k0);
+                tma_load_2d(sV + c * (BM * 128), &map_v, b_kv, col0 + 32 * c, tok0 + k0);
+            }
+            for (int i = 0; i < QS && i < nblk; ++i) load_q(i);
+            for (int i = 0; i < MS && i < nblk; ++i) load_mn(i);
+            mbar_wait(b_kv, 0);
+            issue_s(0);
+            if (nblk > 1) issue_s(1);
+            for (int i = 0; i < nblk; ++i) {
+                if (i + QS < nblk) {                               // S^T(i), dP^T(i) complete: their Q / dO stage takes block i + QS
+                    mbar_wait(b_sfull + 8 * (i & 1), (uint32_t)(i >> 1) & 1u);
+                    load_q(i + QS);
+                }
+                if (i >= 1 && i - 1 + MS < nblk) {                 // dV / dK (i - 1) complete: their MN-major stage takes block i - 1 + MS
+                    mbar_wait(b_odone, (uint32_t)(i - 1) & 1u);
+                    load_mn(i - 1 + MS);
+                }
+                mbar_wait(b_pready + 8 * (i & 1), (uint32_t)(i >> 1) & 1u);    // P^T(i), dS^T(i) sit in TMEM over S^T(i), dP^T(i)
+                mbar_wait(b_mn + 8 * (i % MS), (uint32_t)(i / MS) & 1u);
+                tc_fence_after();
+                const uint32_t tm_p = tmem + (uint32_t)(i & 1) * 2 * BNB, tm_ds = tm_p + BNB, mo = (uint32_t)(i % MS) * (C::SMALL >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BNB / 8; ++kk) {
+                    tc_mma_tf32_ts(tm_dv, tm_p + 8 * kk, dsc(domn_lo + mo + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (i | kk) != 0 ? 1u : 0u);
+                    tc_mma_tf32_ts(tm_dk, tm_ds + 8 * kk, dsc(qmn_lo + mo + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (i | kk) != 0 ? 1u : 0u);
+                }
+                tc_commit(b_odone);
+                if (i + 2 < nblk) issue_s(i + 2);
+            }
+            tc_commit(b_final);
         }
-        __syncthreads();                                           // s_lse / s_dlt visible
-        mbar_wait(b_s, ph);
-        tc_fence_after();
-        if (tid == 0 && i + 1 < nblk) load_q(i + 1);
-#pragma unroll
-        for (int c = 0; c < BNB / 32; ++c) {
-            uint32_t s[32], dp[32];
-            tc_ld32_nowait(tm_s + lane_base + 32 * c, s);
-            tc_ld32_nowait(tm_dp + lane_base + 32 * c, dp);
+    } else {
+        const int half = warp >> 2;
+        const float sl2 = a.scale * kLog2e;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int i = 0; i < nblk; ++i) {
+            if (tid < 2 * BNB) {                                   // softmax statistics of this block's queries
+                const int q = i * BNB + (tid < BNB ? tid : tid - BNB);
+                // lse = +inf makes p = 0 for queries outside the sequence
+                s_stat[(i & 1) * 2 * BNB + tid] =
+                    tid < BNB ? (q < a.L ? a.lse[(long long)bh * a.L + q] : INFINITY) : (q < a.L ? delta[(long long)bh * a.L + q] : 0.f);
+            }
+            math_bar_sync();
+            const uint32_t tb = (uint32_t)(i & 1);
+            mbar_wait(b_sfull + 8 * tb, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t s[CH], dp[CH];
+            const uint32_t t_s = tmem + tb * 2 * BNB + lane_base + half * CH, t_dp = t_s + BNB;
+            tc_ld_nowait(t_s, s);
+            tc_ld_nowait(t_dp, dp);
             tc_wait_ld();
+            const uint32_t st_u32 = s_stat_u32 + (uint32_t)((i & 1) * 2 * BNB + half * CH) * 4u;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float p[4], ds[4];
+            for (int u = 0; u < CH / 4; ++u) {
+                const float4 l4 = lds128(st_u32 + 16 * u), d4 = lds128(st_u32 + BNB * 4 + 16 * u);
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int jq = 32 * c + 4 * u + e;
-                    p[e] = ex2(fmaf(__uint_as_float(s[4 * u + e]), sl2, -s_lse[jq]));
-                    ds[e] = p[e] * (__uint_as_float(dp[4 * u + e]) - s_dlt[jq]) * a.scale;
+                    const float p = ex2(fmaf(__uint_as_float(s[4 * u + e]), sl2, -ls[e]));
+                    s[4 * u + e] = __float_as_uint(p);
+                    dp[4 * u + e] = __float_as_uint(p * (__uint_as_float(dp[4 * u + e]) - dl[e]));
                 }
-                sts128(swz(sPT + c * (BM * 128), tid, u), p[0], p[1], p[2], p[3]);
-                sts128(swz(sdST + c * (BM * 128), tid, u), ds[0], ds[1], ds[2], ds[3]);
             }
+            tc_st(t_s, s);                                         // P^T over S^T, dS^T over dP^T (1/sqrt(d) goes on dK at the end)
+            tc_st(t_dp, dp);
+            tc_wait_st();
+            tc_fence_before();
+            warp_arrive(b_pready + 8 * tb, lane);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            mbar_wait(b_mn, ph);
-#pragma unroll
-            for (int kk = 0; kk < BNB / 8; ++kk) {
-                const uint32_t aoff = (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-                tc_mma_tf32(tm_dv, make_desc(sPT + aoff, 16, 1024, 2), make_desc(sdOmn + kk * 1024, BNB * 128, 512, 1), idesc(D, true),
-                            (i | kk) != 0 ? 1u : 0u);
-                tc_mma_tf32(tm_dk, make_desc(sdST + aoff, 16, 1024, 2), make_desc(sQmn + kk * 1024, BNB * 128, 512, 1), idesc(D, true),
-                            (i | kk) != 0 ? 1u : 0u);
-            }
-            tc_commit(b_o);
-        }
-        mbar_wait(b_o, ph);
+        mbar_wait(b_final, 0);
         tc_fence_after();
-        if (tid == 0 && i + 1 < nblk) load_mn(i + 1);
-        tc_fence_before();
-        __syncthreads();                                           // s_lse / s_dlt are rewritten at the top of the next round
-    }
-    const int key = k0 + tid;
-    const bool ok = key < a.L;
+        const int key = k0 + 32 * (warp & 3) + lane;
+        const bool ok = key < a.L;
+        float* pv = dv + (long long)(tok0 + key) * a.ld_v + col0 + half * (D / 2);
+        float* pk = dk + (long long)(tok0 + key) * a.ld_k + col0 + half * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
-        uint32_t rv[32], rk[32];
-        tc_ld32_nowait(tm_dv + lane_base + 32 * c, rv);
-        tc_ld32_nowait(tm_dk + lane_base + 32 * c, rk);
-        tc_wait_ld();
-        if (ok) {
-            float* pv = dv + (long long)(tok0 + key) * a.ld_v + col0 + 32 * c;
-            float* pk = dk + (long long)(tok0 + key) * a.ld_k + col0 + 32 * c;
+        for (int c = 0; c < D / 64; ++c) {
+            uint32_t rv[32], rk[32];
+            tc_ld32_nowait(tm_dv + lane_base + half * (D / 2) + 32 * c, rv);
+            tc_ld32_nowait(tm_dk + lane_base + half * (D / 2) + 32 * c, rk);
+            tc_wait_ld();
+            if (ok) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                *reinterpret_cast<float4*>(pv + i) = make_float4(__uint_as_float(rv[i]), __uint_as_float(rv[i + 1]), __uint_as_float(rv[i + 2]), __uint_as_float(rv[i + 3]));
-                *reinterpret_cast<float4*>(pk + i) = make_float4(__uint_as_float(rk[i]), __uint_as_float(rk[i + 1]), __uint_as_float(rk[i + 2]), __uint_as_float(rk[i + 3]));
+                for (int i = 0; i < 32; i += 4) {
+                    *reinterpret_cast<float4*>(pv + 32 * c + i) = make_float4(__uint_as_float(rv[i]), __uint_as_float(rv[i + 1]),
+                                                                              __uint_as_float(rv[i + 2]), __uint_as_float(rv[i + 3]));
+                    *reinterpret_cast<float4*>(pk + 32 * c + i) =
+                        make_float4(a.scale * __uint_as_float(rk[i]), a.scale * __uint_as_float(rk[i + 1]),
+                                    a.scale * __uint_as_float(rk[i + 2]), a.scale * __uint_as_float(rk[i + 3]));
+                }
             }
         }
     }
@@ -549,7 +649,6 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_DKV) : "memory");
     }
 }
-
 
 // =================================================================================================================
 // row softmax (wide single-head attention: scores are materialised by ls_gemm_tf32, e.g. the VAE mid block, D = 512)
@@ -702,9 +801,9 @@ int launch_bwd(const LsFmha* a, const float* d_o, float* dq, float* dk, float* d
     if (once_q.ensure_smem(k_fmha_bwd_dq<D, BNB>, Bwd<D, BNB>::SMEM_DQ) != cudaSuccess) return ls_check_cuda("fmha dq smem attribute");
     if (once_kv.ensure_smem(k_fmha_bwd_dkv<D, BNB>, Bwd<D, BNB>::SMEM_DKV) != cudaSuccess) return ls_check_cuda("fmha dkv smem attribute");
     const dim3 grid((a->L + BM - 1) / BM, a->B * a->H);
-    k_fmha_bwd_dq<D, BNB><<<grid, 128, Bwd<D, BNB>::SMEM_DQ, stream>>>(q_big, do_big, k_small, v_small, k_mn, *a, delta, dq);
+    k_fmha_bwd_dq<D, BNB><<<grid, kBwdThreads, Bwd<D, BNB>::SMEM_DQ, stream>>>(q_big, do_big, k_small, v_small, k_mn, *a, delta, dq);
     if (ls_check_cuda("k_fmha_bwd_dq")) return -1;
-    k_fmha_bwd_dkv<D, BNB><<<grid, 128, Bwd<D, BNB>::SMEM_DKV, stream>>>(k_big, v_big, q_small, do_small, q_mn, do_mn, *a, delta, dk, dv);
+    k_fmha_bwd_dkv<D, BNB><<<grid, kBwdThreads, Bwd<D, BNB>::SMEM_DKV, stream>>>(k_big, v_big, q_small, do_small, q_mn, do_mn, *a, delta, dk, dv);
     return ls_check_cuda("k_fmha_bwd_dkv");
 }
 }  // namespace

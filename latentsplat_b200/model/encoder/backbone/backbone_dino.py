@@ -9,9 +9,14 @@ identical because ReLU and Linear are pointwise and `repeat` only replicates).
 """
 from __future__ import annotations
 
+import os
+import warnings
 from dataclasses import dataclass
 from fractions import Fraction
-from typing import Literal
+from pathlib import Path
+from typing import Literal, Optional
+
+import torch
 
 import torch.nn.functional as F
 from torch import Tensor, nn
@@ -26,6 +31,11 @@ class BackboneDinoCfg:
     name: Literal["dino"]
     model: Literal["dino_vits16", "dino_vits8", "dino_vitb16", "dino_vitb8"]
     upscale_mode: Literal["interpolate", "repeat"] = "repeat"
+    # The reference obtains PRETRAINED weights: torch.hub.load("facebookresearch/dino:main", cfg.model) (backbone_dino.py:33).
+    # There is no network here, so the official state_dict (same parameter names as our restatement, loaded strict=True) comes
+    # from a file: this field, else $LS_DINO_WEIGHTS, else pretrained/backbone/<model>.pth.  "random" = deliberately untrained
+    # (benchmarks, tests); None with no file present warns loudly once per construction.
+    pretrained: Optional[str] = None
 
 
 class BackboneDino(Backbone[BackboneDinoCfg]):
@@ -37,11 +47,27 @@ class BackboneDino(Backbone[BackboneDinoCfg]):
             assert n.denominator == 1
             self.n_repeats = int(n)
         self.dino = build_dino(cfg.model)
+        self._load_pretrained()
         d = CONFIGS[cfg.model][1]
         # NB: the reference hard-codes 768 (ViT-B); ViT-S checkpoints would not fit it either.
         # Linear, ReLU, Linear (:34-43); the ReLU runs in the first GEMM's epilogue, an Identity keeps the Sequential indices
         self.global_token_mlp = nn.Sequential(Linear(d, d, act="relu"), nn.Identity(), Linear(d, self.d_out))
         self.local_token_mlp = nn.Sequential(Linear(d, d, act="relu"), nn.Identity(), Linear(d, self.d_out))
+
+    def _load_pretrained(self) -> None:
+        choice = self.cfg.pretrained or os.environ.get("LS_DINO_WEIGHTS")
+        if choice == "random":
+            return
+        path = Path(choice) if choice else Path("pretrained") / "backbone" / f"{self.cfg.model}.pth"
+        if not path.exists():
+            if choice:
+                raise FileNotFoundError(f"DINO weights {path} not found (BackboneDinoCfg.pretrained / LS_DINO_WEIGHTS)")
+            warnings.warn(f"BackboneDino: no pretrained weights at {path}; the reference starts from torch.hub's pretrained "
+                          f"{self.cfg.model} -- this backbone is RANDOMLY initialised (set pretrained='random' to silence)",
+                          stacklevel=3)
+            return
+        state = torch.load(path, map_location="cpu", weights_only=True)
+        self.dino.load_state_dict(state.get("state_dict", state), strict=True)
 
     @property
     def patch_size(self) -> int:

@@ -56,11 +56,10 @@ class _Bf16AttentionCore(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad: Tensor):
-        q, k, v, out = ctx.inner
-        ctx.inner = None
+        q, k, v, out = ctx.inner              # kept (not cleared): a second backward through a retained graph must still work
         B, H, N, D = q.shape
         g = grad.to(torch.bfloat16).view(B, N, H, D).transpose(1, 2)
-        dq, dk, dv = torch.autograd.grad(out, (q, k, v), g)
+        dq, dk, dv = torch.autograd.grad(out, (q, k, v), g, retain_graph=True)
         packed = torch.empty((B, N, 3, H, D), dtype=grad.dtype, device=grad.device)
         for i, d in enumerate((dq, dk, dv)):
             packed[:, :, i].copy_(d.transpose(1, 2))

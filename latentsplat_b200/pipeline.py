@@ -49,9 +49,10 @@ class RenderPipeline(nn.Module):
         context, target = batch["context"], batch["target"]
         size = tuple(context["image"].shape[-2:]) if "image_shape" not in batch else batch["image_shape"]
         gaussians: VariationalGaussians = self.encoder(context, global_step, features=None, deterministic=deterministic)
-        g = gaussians.sample() if self.variational in ("gaussians", "none") else gaussians.flatten()
-        if deterministic and self.variational in ("gaussians", "none"):
-            g = gaussians.mode()
+        if self.variational not in ("gaussians", "none"):
+            g = gaussians.flatten()
+        else:                                  # model_wrapper.py:362 (sample) / :630 (mode); no RNG draw when deterministic
+            g = gaussians.mode() if deterministic else gaussians.sample()
         out = self.decoder(g, target["extrinsics"], target["intrinsics"], target["near"], target["far"], size,
                            return_colors=return_colors, return_features=True)
         latent_sample = out.feature_posterior.mode() if deterministic else out.feature_posterior.sample()

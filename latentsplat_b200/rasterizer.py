@@ -400,7 +400,33 @@ def rasterize_views(means3D: Tensor, cov3D: Tensor, opacities: Tensor, *, viewma
     mode with that many (tile, Gaussian) slots -- `debug.stats[2]` is 1 if the scene needed more (the excess
     entries of the affected tiles are dropped), `debug.stats[0]` is the number it needed.
     Returns (color|None (V,3,H,W), feature|None (V,C,H,W), alpha (V,H,W), depth (V,H,W), radii (V,G)).
+
+    More than LS_MAX_VALUE_CHANNELS (16) blended channels -- colour(3) + C, e.g. the variational kl_f16 / kl_f32 latents
+    (2*16+3 = 35, 2*64+3 = 131; the reference ships those autoencoder configs) -- are rendered in several passes of <= 16
+    channels over the same Gaussians: pass 0 carries the colour, alpha and depth, later passes only feature channels (their
+    alpha / depth outputs are dropped, so those gradients reach the geometry once).  Every pass repeats preprocess + sort (cost:
+    one rasterizer call per 16 channels); gradients of the shared inputs add up through autograd.
     """
+    n_color = 0 if (shs is None and colors_precomp is None) else 3
+    feats = feature_shs if feature_shs is not None else features
+    if feats is not None and n_color + feats.shape[2] > _capi.MAX_VALUE_CHANNELS:
+        common = dict(viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos, tanfov=tanfov, image_height=image_height,
+                      image_width=image_width, bg=bg, sh_degree=sh_degree, scene_scale=scene_scale,
+                      sort_smem_keys=sort_smem_keys, capacity=capacity)
+        key = "feature_shs" if feature_shs is not None else "features"
+        first = _capi.MAX_VALUE_CHANNELS - n_color
+        bounds = [0, first] + list(range(first + _capi.MAX_VALUE_CHANNELS, feats.shape[2], _capi.MAX_VALUE_CHANNELS)) + [feats.shape[2]]
+        bounds = sorted(set(bounds))
+        color = alpha = depth = radii = None
+        parts = []
+        for i, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+            out = rasterize_views(means3D, cov3D, opacities, shs=shs if i == 0 else None,
+                                  colors_precomp=colors_precomp if i == 0 else None, means2D=means2D if i == 0 else None,
+                                  debug=debug if i == 0 else None, **{key: feats[:, :, lo:hi]}, **common)
+            if i == 0:
+                color, _, alpha, depth, radii = out
+            parts.append(out[1])
+        return color, torch.cat(parts, dim=1), alpha, depth, radii
     a = _normalize(means3D, cov3D, opacities, viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos,
                    tanfov=tanfov, image_height=image_height, image_width=image_width, bg=bg, shs=shs,
                    colors_precomp=colors_precomp, features=features, feature_shs=feature_shs, sh_degree=sh_degree,

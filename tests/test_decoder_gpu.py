@@ -140,13 +140,14 @@ def test_sync_free_capacity_mode_and_cuda_graph_step(cuda):
     from latentsplat_b200.rasterizer import RasterCapacityError, check_overflow
     check_overflow(block=True)                               # everything so far fitted
     dec.raster_capacity = n // 2
-    fn(x)                                                    # (the truncated call itself is asynchronous)
-    assert int(dec.last_raster.stats[2].item()) == 1 and int(dec.last_raster.stats[0].item()) == n
     with pytest.raises(RasterCapacityError, match=f"needed {n} "):
-        check_overflow(block=True)
+        fn(x)                                                # the truncated forward is asynchronous; its own backward, the next
+        check_overflow(block=True)                           # call or an explicit check trips over the flag -- whichever is first
     check_overflow(block=True)                               # reported once
-    dec.raster_capacity = n // 2
-    fn(x)
+    assert int(dec.last_raster.stats[2].item()) == 1 and int(dec.last_raster.stats[0].item()) == n
+    with torch.no_grad():                                    # forward only: nothing polls until the next call
+        g = Gaussians(*[x[k] for k in keys])
+        dec(g, x["extrinsics"], x["intrinsics"], x["near"], x["far"], (cfg["H"], cfg["W"]))
     torch.cuda.synchronize()
     dec.raster_capacity = None
     with pytest.raises(RasterCapacityError):                 # the next forward call trips over the earlier overflow by itself

@@ -30,7 +30,7 @@ def build_encoder(variational=True, n_feature_channels=4):
     from latentsplat_b200.model.encoder.epipolar.epipolar_transformer import EpipolarTransformerCfg
     from latentsplat_b200.model.encoder.epipolar.image_self_attention import ImageSelfAttentionCfg
     sa, et, ga, enc = _mg().encoder_cfgs()
-    cfg = EncoderEpipolarCfg(**enc, backbone=BackboneDinoCfg("dino", "dino_vitb8"),
+    cfg = EncoderEpipolarCfg(**enc, backbone=BackboneDinoCfg("dino", "dino_vitb8", pretrained="random"),
                              gaussian_adapter=GaussianAdapterCfg(**ga),
                              epipolar_transformer=EpipolarTransformerCfg(self_attention=ImageSelfAttentionCfg(**sa), **et),
                              opacity_mapping=OpacityMappingCfg(0.0, 0.0, 1))
@@ -227,3 +227,22 @@ def test_reference_eval_sh_degree3_is_not_harmonic():
     gram = har.T @ har / len(v) * 4 * torch.pi
     assert (gram - torch.eye(16, dtype=torch.float64)).abs().max() < 0.03
     assert abs(float((ref[:, 14] * ref[:, 3]).mean() * 4 * torch.pi)) > 0.5   # not orthogonal to a degree-1 function
+
+
+def test_dino_backbone_pretrained_option(tmp_path):
+    """The reference loads pretrained DINO weights from torch.hub (backbone_dino.py:33); here: a state_dict file (strict), a loud
+    warning when none is present, an error when a named file is missing, "random" to opt out."""
+    from fractions import Fraction as Fr
+    from latentsplat_b200.model.encoder.backbone.backbone_dino import BackboneDino, BackboneDinoCfg
+    from latentsplat_b200.model.encoder.backbone.dino_vit import build_dino
+    donor = build_dino("dino_vits16")
+    with torch.no_grad():
+        donor.cls_token.fill_(0.25)
+    path = tmp_path / "dino_vits16.pth"
+    torch.save(donor.state_dict(), path)
+    bb = BackboneDino(BackboneDinoCfg("dino", "dino_vits16", pretrained=str(path)), 3, 64, Fr(1, 16))
+    assert float(bb.dino.cls_token.mean()) == 0.25
+    with pytest.raises(FileNotFoundError):
+        BackboneDino(BackboneDinoCfg("dino", "dino_vits16", pretrained=str(tmp_path / "missing.pth")), 3, 64, Fr(1, 16))
+    with pytest.warns(UserWarning, match="RANDOMLY initialised"):
+        BackboneDino(BackboneDinoCfg("dino", "dino_vits16"), 3, 64, Fr(1, 16))

@@ -120,3 +120,19 @@ def test_flat_gradients_follow_channels_last_parameters():
     assert conv.weight.grad.stride() == conv.weight.stride()
     conv(torch.randn(2, 4, 8, 8)).sum().backward()
     assert float(fg.flat.abs().sum()) > 0 and fg.flat.numel() == sum(p.numel() for p in conv.parameters())
+
+
+def test_math_mode_switch_turns_the_contraction_kernels_off_and_on():
+    """precision choices are one documented switch (latentsplat_b200.precision), not scattered module globals."""
+    import torch
+    from latentsplat_b200 import conv, fmha, gemm, precision
+    try:
+        precision.set_math_mode("fp32")
+        assert not (gemm.enabled or conv.ENABLED or fmha.ENABLED) and not torch.backends.cudnn.allow_tf32
+        assert precision.math_mode() == "fp32"
+    finally:
+        precision.set_math_mode("tf32")
+    assert gemm.enabled and conv.ENABLED and fmha.ENABLED and precision.math_mode() == "tf32"
+    import pytest
+    with pytest.raises(ValueError):
+        precision.set_math_mode("bf16")

@@ -455,3 +455,41 @@ def test_colour_sh_basis_switch_3dgs_matches_oracle(cuda, monkeypatch):
     _assert_grad(g["features"][ok], g_ref["dL_dfeatures"][ok], "features")
     diff = (out[0] - out_intree[0]).abs().max().item()
     assert diff > 1e-3, "the two conventions must give different colours for degree >= 1"
+
+
+def test_more_than_16_value_channels_render_in_passes(cuda):
+    """3 + 35 channels (a variational kl_f16-sized latent + colour) > LS_MAX_VALUE_CHANNELS: rasterize_views renders them in
+    passes of <= 16 channels; result and gradients equal rendering each feature channel group on its own."""
+    from latentsplat_b200.rasterizer import rasterize_views
+    G, H, W, C = 2000, 48, 64, 35
+    d = helpers.raster_case(G=G, H=H, W=W, seed=5, C=0, color="sh", sh_degree=1)
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=cuda)
+    gen = torch.Generator(cuda).manual_seed(2)
+    feats = torch.rand(1, G, C, device=cuda, generator=gen).requires_grad_(True)
+    means = t(d["means3D"])[None].requires_grad_(True)
+    shs = t(d["shs"])[None]
+    cam = dict(viewmatrix=t(d["viewmatrix"]).reshape(1, 4, 4), projmatrix=t(d["projmatrix"]).reshape(1, 4, 4),
+               campos=t(d["campos"]).reshape(1, 3), tanfov=t([[d["tanfovx"], d["tanfovy"]]]), image_height=H, image_width=W,
+               bg=t(d["bg"]).reshape(1, 3), sh_degree=1)
+    wf = torch.randn(1, C, H, W, device=cuda, generator=gen)
+    wc = torch.randn(1, 3, H, W, device=cuda, generator=gen)
+    color, feat, alpha, depth, radii = rasterize_views(means, t(d["cov3D"])[None], t(d["opacity"])[None], shs=shs, features=feats, **cam)
+    assert feat.shape == (1, C, H, W) and color.shape == (1, 3, H, W)
+    ((feat * wf).sum() + (color * wc).sum() + alpha.sum()).backward()
+    g_feat, g_means = feats.grad.clone(), means.grad.clone()
+    feats.grad = means.grad = None
+    # reference: colour + 13 channels in one call, the rest channel group by channel group (each <= 16)
+    total = 0
+    pieces = []
+    for i, (lo, hi) in enumerate([(0, 13), (13, 20), (20, 35)]):
+        o = rasterize_views(means, t(d["cov3D"])[None], t(d["opacity"])[None], shs=shs if i == 0 else None,
+                            features=feats[:, :, lo:hi], **cam)
+        pieces.append(o[1])
+        total = total + (o[1] * wf[:, lo:hi]).sum()
+        if i == 0:
+            total = total + (o[0] * wc).sum() + o[2].sum()
+            assert torch.equal(o[0], color) and torch.equal(o[2], alpha)
+    assert torch.equal(torch.cat(pieces, 1), feat)
+    total.backward()
+    _assert_grad(g_feat.cpu().numpy(), feats.grad.cpu().numpy(), "features (chunked)")
+    _assert_grad(g_means.cpu().numpy(), means.grad.cpu().numpy(), "means3D (chunked)")
