@@ -248,22 +248,24 @@ k_fmha_fwd(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 // =================================================================================================================
 // backward
 // =================================================================================================================
-// delta[b, h, q] = sum_d dO[q, h, d] * O[q, h, d]: one warp per (token, head)
+// delta[b, h, q] = sum_d dO[q, h, d] * O[q, h, d]: one thread per float4 of a token row (coalesced 16-byte loads), the D / 4
+// lanes of a head reduce with shuffles
 __global__ void __launch_bounds__(256) k_fmha_delta(const float* __restrict__ o, const float* __restrict__ d_o, float* __restrict__ delta,
                                                     int B, int H, int L, int D, long long ld_o) {
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (long long)B * L * H) return;
-    const int h = (int)(w % H);
-    const long long tok = w / H;
-    const float* po = o + tok * ld_o + h * D;
-    const float* pg = d_o + tok * ld_o + h * D;
+    const int per_head = D >> 2;                                   // 16 or 32 lanes
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, per_row = (long long)H * per_head;
+    const long long tok = t / per_row;
+    const int rem = (int)(t - tok * per_row);
     float acc = 0.f;
-    for (int d = lane; d < D; d += 32) acc = fmaf(po[d], pg[d], acc);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-        const int b = (int)(tok / L), q = (int)(tok - (long long)b * L);
+    const bool ok = tok < (long long)B * L;
+    if (ok) {
+        const float4 x = *reinterpret_cast<const float4*>(o + tok * ld_o + 4 * rem);
+        const float4 g = *reinterpret_cast<const float4*>(d_o + tok * ld_o + 4 * rem);
+        acc = (x.x * g.x + x.y * g.y) + (x.z * g.z + x.w * g.w);
+    }
+    for (int off = per_head >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (ok && (rem & (per_head - 1)) == 0) {
+        const int b = (int)(tok / L), q = (int)(tok - (long long)b * L), h = rem / per_head;
         delta[((long long)b * H + h) * L + q] = acc;
     }
 }
@@ -282,14 +284,17 @@ struct Bwd {
     static constexpr int BIG = DC * BM * 128;          // a [128 x D] K-major tile
     static constexpr int SMALL = DC * BNB * 128;       // a [BNB x D] tile (K-major or MN-major)
     static constexpr int CH = BNB / 2;                 // score columns per math thread
+    // (S, dP) score buffers in TMEM: the scores of block j + NB are issued as soon as block j has been consumed, NB - 1 blocks ahead
+    // of the math warps.  The streamed shared-memory tiles need one stage more than that (TMA latency is about one block of work).
+    static constexpr int NB_DQ = 2, NB_DKV = 2;             // (3 buffers + 4 K/V stages measured no faster: 122 vs 116 us on the DINO shape)
     // dq: Q, dO resident; (K, V) K-major x KS stages; K MN-major x MS stages
     static constexpr int DQ_KS = D == 64 ? 3 : 2, DQ_MS = D == 64 ? 2 : 1;
     static constexpr int SMEM_DQ = 2 * BIG + DQ_KS * 2 * SMALL + DQ_MS * SMALL + 1024 + 256;
-    static constexpr int TMEM_DQ = D == 64 ? 512 : 256;          // 2 x (S, dP) of BNB columns + dQ (D)
+    static constexpr int TMEM_DQ = D == 64 ? 512 : 256;          // NB x (S, dP) of BNB columns + dQ (D)
     // dkv: K, V resident; (Q, dO) K-major x QS stages; (Q, dO) MN-major x MS stages; lse / delta of the block's queries
     static constexpr int DKV_QS = D == 64 ? 3 : 2, DKV_MS = D == 64 ? 2 : 1;
     static constexpr int SMEM_DKV = 2 * BIG + DKV_QS * 2 * SMALL + DKV_MS * 2 * SMALL + 4 * BNB * 4 + 1024 + 256;
-    static constexpr int TMEM_DKV = 512;                         // 2 x (S^T, dP^T) + dV + dK
+    static constexpr int TMEM_DKV = 512;                         // NB x (S^T, dP^T) + dV + dK
 };
 
 __device__ __forceinline__ void math_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -305,15 +310,15 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
               const __grid_constant__ CUtensorMap map_kmn, const LsFmha a, const float* __restrict__ delta, float* __restrict__ dq) {
     using C = Bwd<D, BNB>;
-    constexpr int KS = C::DQ_KS, MS = C::DQ_MS, CH = C::CH;
+    constexpr int KS = C::DQ_KS, MS = C::DQ_MS, CH = C::CH, NB = C::NB_DQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sQ = smem_u32(smem), sdO = sQ + C::BIG, sK = sdO + C::BIG, sV = sK + KS * C::SMALL, sKmn = sV + KS * C::SMALL;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::BIG + 2 * KS * C::SMALL + MS * C::SMALL);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     const uint32_t b0 = smem_u32(bars);
-    const uint32_t b_q = b0, b_kv = b0 + 8 /* [3] */, b_kmn = b0 + 32 /* [2] */, b_sfull = b0 + 48 /* [2] */, b_pready = b0 + 64 /* [2] */,
-                   b_odone = b0 + 80, b_final = b0 + 88;
+    const uint32_t b_q = b0, b_kv = b0 + 8 /* [4] */, b_kmn = b0 + 40 /* [2] */, b_sfull = b0 + 56 /* [3] */, b_pready = b0 + 80 /* [3] */,
+                   b_odone = b0 + 104, b_final = b0 + 112;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, b = bh / a.H, h = bh - b * a.H;
@@ -322,8 +327,9 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     if (tid == 0) {
         mbar_init(b_q, 1);
-        for (int i = 0; i < 3; ++i) mbar_init(b_kv + 8 * i, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(b_kmn + 8 * i, 1); mbar_init(b_sfull + 8 * i, 1); mbar_init(b_pready + 8 * i, kMathWarps); }
+        for (int i = 0; i < 4; ++i) mbar_init(b_kv + 8 * i, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(b_sfull + 8 * i, 1); mbar_init(b_pready + 8 * i, kMathWarps); }
+        for (int i = 0; i < 2; ++i) mbar_init(b_kmn + 8 * i, 1);
         mbar_init(b_odone, 1);
         mbar_init(b_final, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -336,7 +342,7 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tm_dq = tmem + 4 * BNB;                         // S[b] at tmem + 2 b BNB, dP[b] (later dS[b]) right behind it
+    const uint32_t tm_dq = tmem + NB * 2 * BNB;                    // S[b] at tmem + 2 b BNB, dP[b] (later dS[b]) right behind it
 
     if (warp == kMathWarps) {
         // ================= issuer warp: TMA + MMA, one lane =================
@@ -357,8 +363,8 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < C::DC; ++c) tma_load_2d(sKmn + st * C::SMALL + c * (BNB * 128), &map_kmn, bar, col0 + 32 * c, tok0 + j * BNB);
             };
-            auto issue_s = [&](int j) {                            // S(j) = Q K^T, dP(j) = dO V^T into TMEM buffer j & 1
-                const uint32_t st = (uint32_t)(j % KS), tb = (uint32_t)(j & 1);
+            auto issue_s = [&](int j) {                            // S(j) = Q K^T, dP(j) = dO V^T into TMEM buffer j % NB
+                const uint32_t st = (uint32_t)(j % KS), tb = (uint32_t)(j % NB);
                 mbar_wait(b_kv + 8 * st, (uint32_t)(j / KS) & 1u);
                 tc_fence_after();
                 const uint32_t tm_s = tmem + tb * 2 * BNB, tm_dp = tm_s + BNB;
@@ -382,27 +388,26 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             for (int j = 0; j < KS && j < nblk; ++j) load_kv(j);
             for (int j = 0; j < MS && j < nblk; ++j) load_kmn(j);
             mbar_wait(b_q, 0);
-            issue_s(0);
-            if (nblk > 1) issue_s(1);
+            for (int j = 0; j < NB && j < nblk; ++j) issue_s(j);
             for (int j = 0; j < nblk; ++j) {
                 // S(j), dP(j) are complete (long ago): their K / V stage takes block j + KS
                 if (j + KS < nblk) {
-                    mbar_wait(b_sfull + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+                    mbar_wait(b_sfull + 8 * (j % NB), (uint32_t)(j / NB) & 1u);
                     load_kv(j + KS);
                 }
                 if (j >= 1 && j - 1 + MS < nblk) {                 // dQ(j - 1) is complete: its MN-major K stage takes block j - 1 + MS
                     mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
                     load_kmn(j - 1 + MS);
                 }
-                mbar_wait(b_pready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);    // dS(j) sits in TMEM over dP(j)
+                mbar_wait(b_pready + 8 * (j % NB), (uint32_t)(j / NB) & 1u);   // dS(j) sits in TMEM over dP(j)
                 mbar_wait(b_kmn + 8 * (j % MS), (uint32_t)(j / MS) & 1u);
                 tc_fence_after();
-                const uint32_t tm_ds = tmem + (uint32_t)(j & 1) * 2 * BNB + BNB, ml = kmn_lo + (uint32_t)(j % MS) * (C::SMALL >> 4);
+                const uint32_t tm_ds = tmem + (uint32_t)(j % NB) * 2 * BNB + BNB, ml = kmn_lo + (uint32_t)(j % MS) * (C::SMALL >> 4);
 #pragma unroll
                 for (int kk = 0; kk < BNB / 8; ++kk)               // dQ += dS K, A = dS columns 8 kk.. from TMEM
                     tc_mma_tf32_ts(tm_dq, tm_ds + 8 * kk, dsc(ml + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (j | kk) != 0 ? 1u : 0u);
                 tc_commit(b_odone);
-                if (j + 2 < nblk) issue_s(j + 2);                  // overwrites buffer j & 1 behind the MMAs that just consumed it
+                if (j + NB < nblk) issue_s(j + NB);                // overwrites buffer j % NB behind the MMAs that just consumed it
             }
             tc_commit(b_final);                                    // its own barrier: the math warps never followed b_odone's phases
         }
@@ -416,8 +421,8 @@ k_fmha_bwd_dq(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const float sl2 = a.scale * kLog2e;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         for (int j = 0; j < nblk; ++j) {
-            const uint32_t tb = (uint32_t)(j & 1);
-            mbar_wait(b_sfull + 8 * tb, (uint32_t)(j >> 1) & 1u);
+            const uint32_t tb = (uint32_t)(j % NB);
+            mbar_wait(b_sfull + 8 * tb, (uint32_t)(j / NB) & 1u);
             tc_fence_after();
             uint32_t s[CH], dp[CH];
             const uint32_t t_dp = tmem + tb * 2 * BNB + BNB + lane_base + half * CH;
@@ -471,7 +476,7 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
                const __grid_constant__ CUtensorMap map_qmn, const __grid_constant__ CUtensorMap map_domn, const LsFmha a,
                const float* __restrict__ delta, float* __restrict__ dk, float* __restrict__ dv) {
     using C = Bwd<D, BNB>;
-    constexpr int QS = C::DKV_QS, MS = C::DKV_MS, CH = C::CH;
+    constexpr int QS = C::DKV_QS, MS = C::DKV_MS, CH = C::CH, NB = C::NB_DKV;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sK = smem_u32(smem), sV = sK + C::BIG, sQ = sV + C::BIG, sdO = sQ + QS * C::SMALL, sQmn = sdO + QS * C::SMALL,
@@ -480,10 +485,10 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
     float* s_stat = reinterpret_cast<float*>(smem + kStatOff);                  // [2][2][BNB]: lse, delta
     const uint32_t s_stat_u32 = sK + kStatOff;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 4 * BNB);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const uint32_t b0 = smem_u32(bars);
-    const uint32_t b_kv = b0, b_q = b0 + 8 /* [3] */, b_mn = b0 + 32 /* [2] */, b_sfull = b0 + 48 /* [2] */, b_pready = b0 + 64 /* [2] */,
-                   b_odone = b0 + 80, b_final = b0 + 88;
+    const uint32_t b_kv = b0, b_q = b0 + 8 /* [3] */, b_mn = b0 + 32 /* [2] */, b_sfull = b0 + 48 /* [3] */, b_pready = b0 + 72 /* [3] */,
+                   b_odone = b0 + 96, b_final = b0 + 104;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, b = bh / a.H, h = bh - b * a.H;
@@ -492,8 +497,8 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
 
     if (tid == 0) {
         mbar_init(b_kv, 1);
-        for (int i = 0; i < 3; ++i) mbar_init(b_q + 8 * i, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(b_mn + 8 * i, 1); mbar_init(b_sfull + 8 * i, 1); mbar_init(b_pready + 8 * i, kMathWarps); }
+        for (int i = 0; i < 3; ++i) { mbar_init(b_q + 8 * i, 1); mbar_init(b_sfull + 8 * i, 1); mbar_init(b_pready + 8 * i, kMathWarps); }
+        for (int i = 0; i < 2; ++i) mbar_init(b_mn + 8 * i, 1);
         mbar_init(b_odone, 1);
         mbar_init(b_final, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -506,7 +511,7 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tm_dv = tmem + 4 * BNB, tm_dk = tm_dv + D;
+    const uint32_t tm_dv = tmem + NB * 2 * BNB, tm_dk = tm_dv + D;
 
     if (warp == kMathWarps) {
         if (elect_one()) {
@@ -530,8 +535,8 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
                     tma_load_2d(sdOmn + st * C::SMALL + c * (BNB * 128), &map_domn, bar, col0 + 32 * c, tok0 + i * BNB);
                 }
             };
-            auto issue_s = [&](int i) {                            // S^T(i) = K Q^T, dP^T(i) = V dO^T into TMEM buffer i & 1
-                const uint32_t st = (uint32_t)(i % QS), tb = (uint32_t)(i & 1);
+            auto issue_s = [&](int i) {                            // S^T(i) = K Q^T, dP^T(i) = V dO^T into TMEM buffer i % NB
+                const uint32_t st = (uint32_t)(i % QS), tb = (uint32_t)(i % NB);
                 mbar_wait(b_q + 8 * st, (uint32_t)(i / QS) & 1u);
                 tc_fence_after();
                 const uint32_t tm_s = tmem + tb * 2 * BNB, tm_dp = tm_s + BNB;
@@ -555,28 +560,27 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
             for (int i = 0; i < QS && i < nblk; ++i) load_q(i);
             for (int i = 0; i < MS && i < nblk; ++i) load_mn(i);
             mbar_wait(b_kv, 0);
-            issue_s(0);
-            if (nblk > 1) issue_s(1);
+            for (int i = 0; i < NB && i < nblk; ++i) issue_s(i);
             for (int i = 0; i < nblk; ++i) {
                 if (i + QS < nblk) {                               // S^T(i), dP^T(i) complete: their Q / dO stage takes block i + QS
-                    mbar_wait(b_sfull + 8 * (i & 1), (uint32_t)(i >> 1) & 1u);
+                    mbar_wait(b_sfull + 8 * (i % NB), (uint32_t)(i / NB) & 1u);
                     load_q(i + QS);
                 }
                 if (i >= 1 && i - 1 + MS < nblk) {                 // dV / dK (i - 1) complete: their MN-major stage takes block i - 1 + MS
                     mbar_wait(b_odone, (uint32_t)(i - 1) & 1u);
                     load_mn(i - 1 + MS);
                 }
-                mbar_wait(b_pready + 8 * (i & 1), (uint32_t)(i >> 1) & 1u);    // P^T(i), dS^T(i) sit in TMEM over S^T(i), dP^T(i)
+                mbar_wait(b_pready + 8 * (i % NB), (uint32_t)(i / NB) & 1u);   // P^T(i), dS^T(i) sit in TMEM over S^T(i), dP^T(i)
                 mbar_wait(b_mn + 8 * (i % MS), (uint32_t)(i / MS) & 1u);
                 tc_fence_after();
-                const uint32_t tm_p = tmem + (uint32_t)(i & 1) * 2 * BNB, tm_ds = tm_p + BNB, mo = (uint32_t)(i % MS) * (C::SMALL >> 4);
+                const uint32_t tm_p = tmem + (uint32_t)(i % NB) * 2 * BNB, tm_ds = tm_p + BNB, mo = (uint32_t)(i % MS) * (C::SMALL >> 4);
 #pragma unroll
                 for (int kk = 0; kk < BNB / 8; ++kk) {
                     tc_mma_tf32_ts(tm_dv, tm_p + 8 * kk, dsc(domn_lo + mo + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (i | kk) != 0 ? 1u : 0u);
                     tc_mma_tf32_ts(tm_dk, tm_ds + 8 * kk, dsc(qmn_lo + mo + ((kk * 1024) >> 4), kHiMN), idesc(D, true), (i | kk) != 0 ? 1u : 0u);
                 }
                 tc_commit(b_odone);
-                if (i + 2 < nblk) issue_s(i + 2);
+                if (i + NB < nblk) issue_s(i + NB);
             }
             tc_commit(b_final);
         }
@@ -592,8 +596,8 @@ k_fmha_bwd_dkv(const __grid_constant__ CUtensorMap map_k, const __grid_constant_
                     tid < BNB ? (q < a.L ? a.lse[(long long)bh * a.L + q] : INFINITY) : (q < a.L ? delta[(long long)bh * a.L + q] : 0.f);
             }
             math_bar_sync();
-            const uint32_t tb = (uint32_t)(i & 1);
-            mbar_wait(b_sfull + 8 * tb, (uint32_t)(i >> 1) & 1u);
+            const uint32_t tb = (uint32_t)(i % NB);
+            mbar_wait(b_sfull + 8 * tb, (uint32_t)(i / NB) & 1u);
             tc_fence_after();
             uint32_t s[CH], dp[CH];
             const uint32_t t_s = tmem + tb * 2 * BNB + lane_base + half * CH, t_dp = t_s + BNB;
@@ -785,8 +789,8 @@ namespace {
 template <int D, int BNB>
 int launch_bwd(const LsFmha* a, const float* d_o, float* dq, float* dk, float* dv, float* delta, cudaStream_t stream) {
     const long long cols = (long long)a->H * D, rows = (long long)a->B * a->L;
-    const long long warps = rows * a->H;
-    k_fmha_delta<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(a->o, d_o, delta, a->B, a->H, a->L, D, a->ld_o);
+    const long long lanes = rows * a->H * (D / 4);
+    k_fmha_delta<<<(unsigned)((lanes + 255) / 256), 256, 0, stream>>>(a->o, d_o, delta, a->B, a->H, a->L, D, a->ld_o);
     if (ls_check_cuda("k_fmha_delta")) return -1;
     const CUtensorMapSwizzle KM = CU_TENSOR_MAP_SWIZZLE_128B, MN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     CUtensorMap q_big, do_big, k_small, v_small, k_mn, k_big, v_big, q_small, do_small, q_mn, do_mn;
