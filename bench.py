@@ -9,8 +9,8 @@ Workloads (`--workload`, named in config.workload):
         context views 256x256, full encoder (DINO ViT-B/8 + epipolar transformer) -> 393 216 variational Gaussians
         per scene -> sample -> splat V_t target views -> latent sample -> 1/8 rescale -> VAE decoder with skip
         injection -> PatchGAN logits (generator term, discriminator frozen); loss = 10 mse(colour) + l1(decoded image)
-        + hinge generator term; backward to every weight; fused Adam step; for N > 1 a bucketed NCCL all-reduce of the
-        flat gradient buffer overlapped with backward.  fp32 weights/activations, NHWC.  Ours (sm_100a, libls_raster.so):
+        + hinge generator term; backward to every weight; fused Adam step; for N > 1 one NCCL all-reduce of the flat
+        gradient buffer between the two graphs.  fp32 weights/activations, NHWC.  Ours (sm_100a, libls_raster.so):
         rasterizer fwd+bwd, every Linear (tcgen05 TF32 GEMM), every convolution (tcgen05 implicit GEMM), the attention
         cores (tcgen05 flash attention; GEMM + softmax for the VAE mid block), epipolar gather + depth encoding,
         weight-absorbed cross-attention, fused depth/Gaussian-adapter tail, GroupNorm+SiLU, LayerNorm.  Library: PatchGAN
@@ -389,9 +389,11 @@ def run_full(args, cfg):
     from latentsplat_b200.parallel import BucketedAllReduce, FlatGradients
     fgrads = FlatGradients(params)
     flat_grad = fgrads.flat
-    # N > 1: bucketed all-reduce launched by gradient hooks DURING backward on a communication stream, captured into the
-    # step's CUDA graph together with the kernels (LS_BENCH_ALLREDUCE=after: one exposed all-reduce behind the graph)
-    overlap = world > 1 and os.environ.get("LS_BENCH_ALLREDUCE", "overlap") == "overlap"
+    # N > 1, default: one NCCL all-reduce of the flat buffer between the fwd+bwd graph and the Adam graph (measured path).
+    # LS_BENCH_ALLREDUCE=overlap: bucketed all-reduce launched by gradient hooks DURING backward on a communication stream and
+    # captured into the step's CUDA graph (parallel.BucketedAllReduce; verified on gloo, NOT yet on NCCL: the first 2-GPU attempt
+    # hung inside the capture, so it stays opt-in)
+    overlap = world > 1 and os.environ.get("LS_BENCH_ALLREDUCE", "after") == "overlap"
     reducer = BucketedAllReduce(fgrads, bucket_bytes=32 << 20) if overlap else None
     opt = torch.optim.Adam(params, lr=1.5e-5, fused=True, capturable=True)
 

@@ -217,7 +217,7 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
         x0 = tx * ((1 << p.bw_log2) + (CG == 2 ? p.sub_dx : 0));
     };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         // ------------------------------ TMA producer (every CTA) ------------------
         uint32_t it = 0;
         for (int item = worker; item < n_items; item += n_workers) {
@@ -247,7 +247,7 @@ k_conv_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
+    } else if (warp == 1 && rank == 0 && elect_one()) {
         // ------------------------------ MMA issuer (leader CTA) -------------------
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
@@ -398,7 +398,7 @@ k_conv_w(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         return true;
     };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         // ------------------------------ TMA producer (every CTA) ------------------
         uint32_t it = 0;
         long long cur = worker;
@@ -434,7 +434,7 @@ k_conv_w(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                 if (++xb == p.tiles_x) { xb = 0; if (++yb == p.tiles_y) { yb = 0; ++n; } }
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
+    } else if (warp == 1 && rank == 0 && elect_one()) {
         // ------------------------------ MMA issuer (leader CTA) -------------------
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);

@@ -186,7 +186,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         nkb = min(nkb_total, kb0 + kb_per_split) - kb0;      // >= 1 by construction of `splits`
     };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         // ------------------------------ TMA producer ------------------------------
         uint32_t it = 0;                                       // global k-block counter -> stage / phase
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -212,7 +212,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         // ------------------------------ MMA issuer --------------------------------
         // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
@@ -367,7 +367,7 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         nkb = min(nkb_total, kb0 + kb_per_split) - kb0;
     };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         // ------------------------------ TMA producer (both CTAs) ------------------------------
         uint32_t it = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
@@ -395,7 +395,7 @@ k_gemm_tf32_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
+    } else if (warp == 1 && rank == 0 && elect_one()) {
         // ------------------------------ MMA issuer (leader CTA only) --------------------------
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);

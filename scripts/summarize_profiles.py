@@ -36,7 +36,7 @@ if launches.exists():
     import re
     ours = sum(a[1] for k, a in agg.items() if re.search(r"\bls[a-z]?::", k))
     md = [f"# {tag}: ncu launch list of the timed region of `python bench.py` (cudaProfilerStart/Stop range; gpu__time_duration.sum, --clock-control none)",
-          "", f"{len(rows)} launches, {tot / 1e3:.2f} ms GPU time in total; our kernels (`ls::*`, `lsg::*`, `lsa::*`, `lse::*`, `lsn::*`) = {100 * ours / tot:.1f} % of it.",
+          "", f"{len(rows)} launches, {tot / 1e3:.2f} ms GPU time in total; our kernels (`ls::*`, `lsg::*`, `lsc::*`, `lsf::*`, `lsa::*`, `lse::*`, `lsh::*`, `lsn::*`) = {100 * ours / tot:.1f} % of it.",
           "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
           "| share | total µs | launches | avg µs | grid | block | kernel |", "|---:|---:|---:|---:|---|---|---|"]
     for k, (n, t, g, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
@@ -54,7 +54,10 @@ if rep.exists():
             "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
             "inst_executed", "smsp__thread_inst_executed_per_inst_executed.ratio",
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
-            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "launch__grid_size",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "launch__grid_size",
             "launch__block_size", "smsp__cycles_active.avg"]
     md = [f"# {tag}: ncu --set full capture ({rep.name})", ""]
     traffic = {}
