@@ -181,6 +181,11 @@ LS_API int ls_raster_backward(const LsRasterScene* scene, const LsRasterState* s
 LS_API const char* ls_last_error(void); /* thread-local, never NULL */
 LS_API int ls_raster_abi_version(void);
 
+/* 1 when the specialised coefficient backward (colour SH degree 4 in the in-tree basis, 4 or 8 feature channels of SH degree 2,
+ * G % 4 == 0) applies to this scene: the caller should then allocate DENSE SH gradient rows (color_grad_pitch = feature_grad_pitch
+ * = 0) -- the warp's 32 rows leave shared memory as one bulk copy; otherwise rows padded to 8 floats are the faster layout. */
+LS_API int ls_raster_dense_sh_grads(const LsRasterScene* scene);
+
 #ifdef __cplusplus
 }
 #endif

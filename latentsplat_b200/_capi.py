@@ -112,7 +112,7 @@ FEATURE_NONE, FEATURE_PRECOMP, FEATURE_SH = 0, 1, 2
 STAGE_GEOMETRY, STAGE_SCATTER, STAGE_SORT, STAGE_BLEND, STAGE_RENDER, STAGE_ALL = 1, 2, 4, 8, 14, 15
 BWD_BLEND, BWD_GEOMETRY, BWD_ALL = 1, 2, 3
 ABI_VERSION = 2
-EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version",
+EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_last_error", "ls_raster_abi_version", "ls_raster_dense_sh_grads",
            "ls_gemm_tf32", "ls_sq_attention_forward", "ls_sq_attention_backward",
            "ls_absorbed_attention_forward", "ls_absorbed_attention_backward",
            "ls_epipolar_gather_forward", "ls_epipolar_gather_backward", "ls_groupnorm_forward", "ls_groupnorm_backward",
@@ -203,6 +203,8 @@ def load() -> C.CDLL:
     lib.ls_gaussian_head_forward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadOut), C.c_void_p]
     lib.ls_gaussian_head_backward.restype = C.c_int
     lib.ls_gaussian_head_backward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadGrad), C.c_void_p]
+    lib.ls_raster_dense_sh_grads.restype = C.c_int
+    lib.ls_raster_dense_sh_grads.argtypes = [C.POINTER(LsRasterScene)]
     lib.ls_fmha_forward.restype = C.c_int
     lib.ls_fmha_forward.argtypes = [C.POINTER(LsFmha), C.c_void_p]
     lib.ls_fmha_backward.restype = C.c_int

@@ -170,6 +170,78 @@ __device__ __forceinline__ void sh_patch_3dgs(int deg, float X, float Y, float Z
     if (kGrad) { db[14][0] = -2.f * c35 * X * Y; db[14][1] = c35 * (Z * Z - X * X); db[14][2] = 2.f * c35 * Y * Z; }
 }
 
+// d/d(x,y,z) of sum_k sg[k] * basis_k(x, y, z): the derivative table of sh_basis contracted on the fly (no 25 x 3 array),
+// for callers that hold sg[k] = sum_c sh[k][c] * dL/dvalue[c] in registers.  Generated from sh_basis above (same expressions).
+template <int DEG>
+__device__ __forceinline__ void sh_basis_vjp(float x, float y, float z, const float* __restrict__ sg, float* __restrict__ ddir) {
+    if (DEG < 1) return;
+    const float c1 = 0.4886025119029199f;
+    ddir[0] = fmaf(-c1, sg[1], ddir[0]);
+    ddir[1] = fmaf(c1, sg[2], ddir[1]);
+    ddir[2] = fmaf(-c1, sg[3], ddir[2]);
+    if (DEG < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    const float c20 = 1.0925484305920792f, c22 = 0.31539156525252005f, c24 = 0.5462742152960396f;
+    ddir[0] = fmaf(c20 * z, sg[4], ddir[0]);
+    ddir[2] = fmaf(c20 * x, sg[4], ddir[2]);
+    ddir[0] = fmaf(-c20 * y, sg[5], ddir[0]);
+    ddir[1] = fmaf(-c20 * x, sg[5], ddir[1]);
+    ddir[0] = fmaf(-2.f * c22 * x, sg[6], ddir[0]);
+    ddir[1] = fmaf(4.f * c22 * y, sg[6], ddir[1]);
+    ddir[2] = fmaf(-2.f * c22 * z, sg[6], ddir[2]);
+    ddir[1] = fmaf(-c20 * z, sg[7], ddir[1]);
+    ddir[2] = fmaf(-c20 * y, sg[7], ddir[2]);
+    ddir[0] = fmaf(-2.f * c24 * x, sg[8], ddir[0]);
+    ddir[2] = fmaf(2.f * c24 * z, sg[8], ddir[2]);
+    if (DEG < 3) return;
+    const float c30 = -0.5900435899266435f, c31 = 2.890611442640554f, c32 = -0.4570457994644658f,
+                c33 = 0.3731763325901154f, c35 = 1.445305721320277f;
+    ddir[0] = fmaf(3.f * c30 * (zz - xx), sg[9], ddir[0]);
+    ddir[2] = fmaf(6.f * c30 * xz, sg[9], ddir[2]);
+    ddir[0] = fmaf(c31 * yz, sg[10], ddir[0]);
+    ddir[1] = fmaf(c31 * xz, sg[10], ddir[1]);
+    ddir[2] = fmaf(c31 * xy, sg[10], ddir[2]);
+    ddir[0] = fmaf(c32 * (4.f * yy - zz - 3.f * xx), sg[11], ddir[0]);
+    ddir[1] = fmaf(8.f * c32 * xy, sg[11], ddir[1]);
+    ddir[2] = fmaf(-2.f * c32 * xz, sg[11], ddir[2]);
+    ddir[0] = fmaf(-6.f * c33 * xy, sg[12], ddir[0]);
+    ddir[1] = fmaf(c33 * (6.f * yy - 3.f * zz - 3.f * xx), sg[12], ddir[1]);
+    ddir[2] = fmaf(-6.f * c33 * yz, sg[12], ddir[2]);
+    ddir[0] = fmaf(-2.f * c32 * xz, sg[13], ddir[0]);
+    ddir[1] = fmaf(8.f * c32 * yz, sg[13], ddir[1]);
+    ddir[2] = fmaf(c32 * (4.f * yy - 3.f * zz - xx), sg[13], ddir[2]);
+    ddir[0] = fmaf(-2.f * c35 * xz, sg[14], ddir[0]);
+    ddir[2] = fmaf(c35 * (3.f * zz - xx), sg[14], ddir[2]);
+    ddir[0] = fmaf(-6.f * c30 * xz, sg[15], ddir[0]);
+    ddir[2] = fmaf(3.f * c30 * (zz - xx), sg[15], ddir[2]);
+    if (DEG < 4) return;
+    const float c40 = 2.5033429417967046f, c41 = -1.7701307697799304f, c42 = 0.9461746957575601f,
+                c43 = -0.6690465435572892f, c44 = 0.10578554691520431f, c46 = 0.47308734787878004f,
+                c48 = 0.6258357354491761f;
+    const float s7y1 = 7.f * yy - 1.f, s7y3 = 7.f * yy - 3.f;
+    ddir[0] = fmaf(c40 * z * (zz - 3.f * xx), sg[16], ddir[0]);
+    ddir[2] = fmaf(c40 * x * (3.f * zz - xx), sg[16], ddir[2]);
+    ddir[0] = fmaf(3.f * c41 * y * (zz - xx), sg[17], ddir[0]);
+    ddir[1] = fmaf(c41 * x * (3.f * zz - xx), sg[17], ddir[1]);
+    ddir[2] = fmaf(6.f * c41 * xy * z, sg[17], ddir[2]);
+    ddir[0] = fmaf(c42 * z * s7y1, sg[18], ddir[0]);
+    ddir[1] = fmaf(14.f * c42 * xz * y, sg[18], ddir[1]);
+    ddir[2] = fmaf(c42 * x * s7y1, sg[18], ddir[2]);
+    ddir[0] = fmaf(c43 * y * s7y3, sg[19], ddir[0]);
+    ddir[1] = fmaf(c43 * x * (21.f * yy - 3.f), sg[19], ddir[1]);
+    ddir[1] = fmaf(c44 * y * (140.f * yy - 60.f), sg[20], ddir[1]);
+    ddir[1] = fmaf(c43 * z * (21.f * yy - 3.f), sg[21], ddir[1]);
+    ddir[2] = fmaf(c43 * y * s7y3, sg[21], ddir[2]);
+    ddir[0] = fmaf(-2.f * c46 * x * s7y1, sg[22], ddir[0]);
+    ddir[1] = fmaf(14.f * c46 * (zz - xx) * y, sg[22], ddir[1]);
+    ddir[2] = fmaf(2.f * c46 * z * s7y1, sg[22], ddir[2]);
+    ddir[0] = fmaf(-6.f * c41 * xy * z, sg[23], ddir[0]);
+    ddir[1] = fmaf(c41 * z * (zz - 3.f * xx), sg[23], ddir[1]);
+    ddir[2] = fmaf(3.f * c41 * y * (zz - xx), sg[23], ddir[2]);
+    ddir[0] = fmaf(c48 * 4.f * x * (xx - 3.f * zz), sg[24], ddir[0]);
+    ddir[2] = fmaf(c48 * 4.f * z * (zz - 3.f * xx), sg[24], ddir[2]);
+}
+
 // geometry record slot 7: two fp16 half-extents (x, y) of the alpha >= 1/255 region, rounded up
 __device__ __forceinline__ float2 unpack_extent(float packed) {
     const uint32_t u = __float_as_uint(packed);
@@ -220,6 +292,17 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+
+// shared -> global, plain store or fp32 add (cp.reduce): `bytes` a multiple of 16; completion through the bulk async-group
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- warp-cooperative staging of per-Gaussian coefficient rows ---------------------------------------------------
 // A thread per Gaussian reading its own 300-B SH row makes every warp-level load touch 32 different sectors for 128

@@ -241,13 +241,21 @@ __device__ __forceinline__ void accum(float* dst, float v, bool atomic) {
     if (atomic) atomicAdd(dst, v); else *dst = v;
 }
 
+// FC = 0: any configuration (SH rows staged 24 floats at a time through a small per-warp buffer).
+// FC = 4 | 8: the product's configuration -- colour SH degree 4 in the in-tree basis, FC feature channels of SH degree 2, dense
+// gradient rows, G % 4 == 0.  Each warp's 32 consecutive coefficient rows (32 x 300 B colour, 32 x FC x 36 B features) are ONE
+// contiguous piece of memory: a single cp.async.bulk brings them to shared memory while the warp does its geometry backward, the
+// gradients overwrite them in place (every index a compile-time constant: basis and partial sums live in registers, no local
+// frame) and one bulk store -- or cp.reduce add when a scene has several views -- takes them back.  No LSU traffic to HBM.
+template <int FC>
 __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, const LsRasterState st,
                                                         const LsRasterGrads gr) {
-    __shared__ float s_stage[8][32 * kStagePitch];
+    __shared__ float s_stage[FC == 0 ? 8 : 1][32 * kStagePitch];
+    extern __shared__ __align__(16) unsigned char s_pre[];
     const int v = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    float* stage = s_stage[threadIdx.x >> 5];
+    float* stage = s_stage[FC == 0 ? (threadIdx.x >> 5) : 0];
     float* mine = stage + lane * kStagePitch;
     const int i0 = i - lane, nrows = min(32, sc.G - i0);       // this warp's 32 consecutive Gaussians
     if (nrows <= 0) return;                                     // warp-uniform: the grid's tail beyond G
@@ -263,6 +271,22 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
     const bool at = sc.views_per_scene > 1;
     if (at && alive_mask == 0u) return;                         // warp-uniform
     const uint32_t row_mask = at ? alive_mask : (nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+    constexpr int kCRow = 75, kFRow = FC * 9;                      // floats per colour / feature coefficient row (fast path)
+    float* wbuf = nullptr;
+    uint32_t wbar = 0;
+    if constexpr (FC > 0) {
+        const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        wbuf = reinterpret_cast<float*>(s_pre) + (size_t)warp * 32 * (kCRow + kFRow);
+        wbar = smem_u32(reinterpret_cast<uint64_t*>(s_pre + (size_t)nwarps * 32 * (kCRow + kFRow) * 4) + warp);
+        if (lane == 0) {
+            mbar_init(wbar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(wbar, (uint32_t)nrows * (kCRow + kFRow) * 4u);
+            bulk_load(smem_u32(wbuf), sc.color + si0 * kCRow, (uint32_t)nrows * kCRow * 4u, wbar);
+            bulk_load(smem_u32(wbuf + 32 * kCRow), sc.feature + si0 * kFRow, (uint32_t)nrows * kFRow * 4u, wbar);
+        }
+        __syncwarp();
+    }
     if (!at && i < sc.G && !alive) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) gr.dL_dmeans3D[3 * si + k] = 0.f;
@@ -363,13 +387,15 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
     float u[3] = {0.f, 0.f, 0.f}, inv = 0.f;
     float ddir[3] = {0.f, 0.f, 0.f};
     float basis[25];
-    float dbasis[25][3];
+    float dbasis[FC == 0 ? 25 : 1][3];
     if (need_dir && alive) {
         const float* cp = sc.campos + 3 * v;
         const float d0 = p[0] - cp[0], d1 = p[1] - cp[1], d2 = p[2] - cp[2];
         inv = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
         u[0] = d0 * inv; u[1] = d1 * inv; u[2] = d2 * inv;
-        if (permuted) {            // [EXT] 3DGS coefficient order: in-tree polynomials at (y, z, x); ddir is un-permuted after the colour loop
+        if constexpr (FC > 0) {
+            sh_basis<false>(4, u[0], u[1], u[2], basis, nullptr);
+        } else if (permuted) {     // [EXT] 3DGS order: in-tree polynomials at (y, z, x), k = 14 patched; ddir is un-permuted after the colour loop
             sh_basis<true>(sc.sh_degree, u[1], u[2], u[0], basis, dbasis);
             sh_patch_3dgs<true>(sc.sh_degree, u[1], u[2], u[0], basis, dbasis);
         } else {
@@ -377,6 +403,63 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
             sh_basis<true>(deg, u[0], u[1], u[2], basis, dbasis);
         }
     }
+    if constexpr (FC > 0) {
+        // ---- specialised coefficient backward: rows in shared memory, every index a compile-time constant ----
+        float* crow = wbuf + lane * kCRow;
+        const uint32_t frow = smem_u32(wbuf + 32 * kCRow) + (uint32_t)lane * kFRow * 4u;
+        mbar_wait(wbar, 0);                                                        // the warp's rows have landed
+        if (alive) {
+            const uint8_t cl = st.clamped[vi];
+            const float g0 = (cl & 1) ? 0.f : r[7], g1 = (cl & 2) ? 0.f : r[8], g2 = (cl & 4) ? 0.f : r[9];
+            float sg[25];
+#pragma unroll
+            for (int k = 0; k < 25; ++k) {
+                const float s0 = crow[3 * k], s1 = crow[3 * k + 1], s2 = crow[3 * k + 2];
+                sg[k] = fmaf(s0, g0, fmaf(s1, g1, s2 * g2));
+                crow[3 * k] = basis[k] * g0; crow[3 * k + 1] = basis[k] * g1; crow[3 * k + 2] = basis[k] * g2;
+            }
+            sh_basis_vjp<4>(u[0], u[1], u[2], sg, ddir);
+            float gf[FC], sf[9];
+#pragma unroll
+            for (int ch = 0; ch < FC; ++ch) gf[ch] = r[10 + ch];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sf[k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kFRow / 4; ++j) {                                  // flat (channel, coefficient) index, one float4 at a time
+                const float4 x4 = lstc::lds128(frow + 16 * j);
+                const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int f = 4 * j + e, ch = f / 9, k = f - 9 * ch;           // compile-time after unrolling
+                    sf[k] = fmaf(x[e], gf[ch], sf[k]);
+                    o[e] = basis[k] * gf[ch];
+                }
+                lstc::sts128(frow + 16 * j, o[0], o[1], o[2], o[3]);
+            }
+            sh_basis_vjp<2>(u[0], u[1], u[2], sf, ddir);
+        } else {                                                                   // culled here: its rows carry zeros
+#pragma unroll
+            for (int k = 0; k < kCRow; ++k) crow[k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kFRow / 4; ++j) lstc::sts128(frow + 16 * j, 0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();                                                  // generic-proxy writes -> visible to the bulk copy engine
+        __syncwarp();
+        if (lane == 0) {
+            float* dc = gr.dL_dcolor_in + si0 * kCRow;
+            float* df = gr.dL_dfeature_in + si0 * kFRow;
+            if (at) {
+                bulk_reduce_add_f32(dc, smem_u32(wbuf), (uint32_t)nrows * kCRow * 4u);
+                bulk_reduce_add_f32(df, smem_u32(wbuf + 32 * kCRow), (uint32_t)nrows * kFRow * 4u);
+            } else {
+                bulk_store(dc, smem_u32(wbuf), (uint32_t)nrows * kCRow * 4u);
+                bulk_store(df, smem_u32(wbuf + 32 * kCRow), (uint32_t)nrows * kFRow * 4u);
+            }
+            bulk_commit();
+            bulk_wait_read_all();                                                  // shared memory must outlive the engine's reads
+        }
+    } else {
     if (sc.color_mode == LS_COLOR_PRECOMP) {
         if (alive) {
 #pragma unroll
@@ -459,6 +542,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
             stage_store(stage, dfs0, pitch, c0, len_out, row_mask, at, lane);
         }
     }
+    }   // generic coefficient path
     if (!alive) return;                                        // no warp-level operation below this line
     if (need_dir) {
         const float dot = u[0] * ddir[0] + u[1] * ddir[1] + u[2] * ddir[2];
@@ -472,6 +556,13 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const LsRasterScene sc, 
 }  // namespace ls
 
 using namespace ls;
+
+// 1 when the specialised coefficient backward applies to this scene configuration: the caller then allocates DENSE gradient rows
+// (pitch = row length; the generic kernel prefers rows padded to 8 floats, see LsRasterGrads.color_grad_pitch)
+extern "C" int ls_raster_dense_sh_grads(const LsRasterScene* sc) {
+    return sc && sc->color_mode == LS_COLOR_SH && sc->sh_degree == 4 && sc->feature_mode == LS_FEATURE_SH && sc->feature_sh_degree == 2 &&
+           (sc->C == 4 || sc->C == 8) && sc->G % 4 == 0;
+}
 
 extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* st, const LsRasterGrads* gr,
                                   int32_t stages, void* stream_) {
@@ -520,7 +611,25 @@ extern "C" int ls_raster_backward(const LsRasterScene* sc, const LsRasterState* 
         if (sc->feature_mode == LS_FEATURE_PRECOMP) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * sc->C, stream);
         if (sc->feature_mode == LS_FEATURE_SH) cudaMemsetAsync(gr->dL_dfeature_in, 0, sizeof(float) * SG * fpitch, stream);
     }
+    const int crow = 3 * (sc->sh_degree + 1) * (sc->sh_degree + 1), frow = sc->C * (sc->feature_sh_degree + 1) * (sc->feature_sh_degree + 1);
+    const bool dense = (gr->color_grad_pitch == 0 || gr->color_grad_pitch == crow) && (gr->feature_grad_pitch == 0 || gr->feature_grad_pitch == frow);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(sc->color) | reinterpret_cast<uintptr_t>(sc->feature) |
+                           reinterpret_cast<uintptr_t>(gr->dL_dcolor_in) | reinterpret_cast<uintptr_t>(gr->dL_dfeature_in)) & 15) == 0;
+    if (ls_raster_dense_sh_grads(sc) && dense && aligned) {
+        constexpr int kWarps = 4;
+        dim3 gridf((sc->G + 32 * kWarps - 1) / (32 * kWarps), sc->n_views);
+        const int smem = kWarps * 32 * (75 + sc->C * 9) * 4 + kWarps * 8;
+        static lstc::PerDeviceOnce once4, once8;
+        if (sc->C == 4) {
+            if (smem > 48 * 1024 && once4.ensure_smem(k_preprocess_bwd<4>, smem) != cudaSuccess) return ls_check_cuda("preprocess bwd smem attribute");
+            k_preprocess_bwd<4><<<gridf, 32 * kWarps, smem, stream>>>(*sc, *st, *gr);
+        } else {
+            if (smem > 48 * 1024 && once8.ensure_smem(k_preprocess_bwd<8>, smem) != cudaSuccess) return ls_check_cuda("preprocess bwd smem attribute");
+            k_preprocess_bwd<8><<<gridf, 32 * kWarps, smem, stream>>>(*sc, *st, *gr);
+        }
+        return ls_check_cuda("backward");
+    }
     dim3 grid2((sc->G + 255) / 256, sc->n_views);
-    k_preprocess_bwd<<<grid2, 256, 0, stream>>>(*sc, *st, *gr);
+    k_preprocess_bwd<0><<<grid2, 256, 0, stream>>>(*sc, *st, *gr);
     return ls_check_cuda("backward");
 }

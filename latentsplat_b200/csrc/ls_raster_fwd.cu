@@ -34,10 +34,12 @@ namespace ls {
 // =========================================================================================
 // R.1 preprocess: one thread per (view, Gaussian)
 // =========================================================================================
-__global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, const LsRasterState st) {
-    const int v = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sc.G) return;
+// FC = 0: any configuration.  FC = 4 | 8 (colour SH degree 4 in the in-tree basis, FC feature channels of SH degree 2, G % 4 == 0):
+// the warp's 32 coefficient rows arrive in shared memory by one cp.async.bulk each while the threads cull and project; survivors
+// evaluate their SH from there with compile-time indices (see k_preprocess_bwd<FC>).
+template <int FC>
+__device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const LsRasterState& st, const int v, const int i,
+                                               const float* wbuf, const uint32_t wbar) {
     const int s_idx = v / sc.views_per_scene;
     const size_t vi = (size_t)v * sc.G + i;
     const size_t si = (size_t)s_idx * sc.G + i;
@@ -108,13 +110,24 @@ __global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, cons
         }
     }
     if (color_sh) {
-        const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1);
-        const float* __restrict__ sh = sc.color + si * (size_t)(n * 3);
         float r = 0.f, g = 0.f, b = 0.f;
-        for (int k = 0; k < n; ++k) {
-            r = fmaf(basis[k], sh[3 * k + 0], r);
-            g = fmaf(basis[k], sh[3 * k + 1], g);
-            b = fmaf(basis[k], sh[3 * k + 2], b);
+        if constexpr (FC > 0) {
+            mbar_wait(wbar, 0);                                    // the warp's rows have landed
+            const float* __restrict__ sh = wbuf + (threadIdx.x & 31) * 75;       // row pitch 75: conflict-free
+#pragma unroll
+            for (int k = 0; k < 25; ++k) {
+                r = fmaf(basis[k], sh[3 * k + 0], r);
+                g = fmaf(basis[k], sh[3 * k + 1], g);
+                b = fmaf(basis[k], sh[3 * k + 2], b);
+            }
+        } else {
+            const int n = (sc.sh_degree + 1) * (sc.sh_degree + 1);
+            const float* __restrict__ sh = sc.color + si * (size_t)(n * 3);
+            for (int k = 0; k < n; ++k) {
+                r = fmaf(basis[k], sh[3 * k + 0], r);
+                g = fmaf(basis[k], sh[3 * k + 1], g);
+                b = fmaf(basis[k], sh[3 * k + 2], b);
+            }
         }
         r += 0.5f; g += 0.5f; b += 0.5f;
         st.clamped[vi] = (uint8_t)((r < 0.f ? 1 : 0) | (g < 0.f ? 2 : 0) | (b < 0.f ? 4 : 0));
@@ -125,13 +138,32 @@ __global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, cons
     if (sc.feature_mode == LS_FEATURE_PRECOMP) {
         for (int c = 0; c < sc.C; ++c) crec[ncol + c] = sc.feature[si * sc.C + c];
     } else if (sc.feature_mode == LS_FEATURE_SH) {
-        if (permuted) sh_basis<false>(sc.feature_sh_degree, d0, d1, d2, basis, nullptr);
-        const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1);
-        const float* __restrict__ fs = sc.feature + si * (size_t)(sc.C * n);
-        for (int c = 0; c < sc.C; ++c) {
-            float r = 0.f;
-            for (int k = 0; k < n; ++k) r = fmaf(basis[k], fs[c * n + k], r);
-            crec[ncol + c] = 0.5f + r;  // cuda_splatting.py:97
+        if constexpr (FC > 0) {
+            const uint32_t frow = smem_u32(wbuf + 32 * 75) + (uint32_t)(threadIdx.x & 31) * FC * 36u;
+            float acc[FC];
+#pragma unroll
+            for (int c = 0; c < FC; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int j = 0; j < FC * 9 / 4; ++j) {                 // flat (channel, coefficient) index, one float4 at a time
+                const float4 x4 = lstc::lds128(frow + 16 * j);
+                const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int f = 4 * j + e, c = f / 9, k = f - 9 * c;           // compile-time after unrolling
+                    acc[c] = fmaf(basis[k], x[e], acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < FC; ++c) crec[ncol + c] = 0.5f + acc[c];
+        } else {
+            if (permuted) sh_basis<false>(sc.feature_sh_degree, d0, d1, d2, basis, nullptr);
+            const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1);
+            const float* __restrict__ fs = sc.feature + si * (size_t)(sc.C * n);
+            for (int c = 0; c < sc.C; ++c) {
+                float r = 0.f;
+                for (int k = 0; k < n; ++k) r = fmaf(basis[k], fs[c * n + k], r);
+                crec[ncol + c] = 0.5f + r;  // cuda_splatting.py:97
+            }
         }
     }
 
@@ -158,6 +190,37 @@ __global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, cons
     uint32_t* cnt = st.tile_count + (size_t)v * gx * gy;
     for (int y = rmin[1]; y < rmax[1]; ++y)
         for (int x = rmin[0]; x < rmax[0]; ++x) atomicAdd(cnt + y * gx + x, 1u);
+}
+
+template <int FC>
+__global__ void __launch_bounds__(256) k_preprocess(const LsRasterScene sc, const LsRasterState st) {
+    extern __shared__ __align__(16) unsigned char s_pre[];
+    const int v = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* wbuf = nullptr;
+    uint32_t wbar = 0;
+    if constexpr (FC > 0) {
+        constexpr int kRow = 75 + FC * 9;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const int i0 = i - lane, nrows = min(32, sc.G - i0);
+        if (nrows <= 0) return;                                    // warp-uniform
+        float* buf = reinterpret_cast<float*>(s_pre) + (size_t)warp * 32 * kRow;
+        wbuf = buf;
+        wbar = smem_u32(reinterpret_cast<uint64_t*>(s_pre + (size_t)nwarps * 32 * kRow * 4) + warp);
+        if (lane == 0) {
+            const size_t si0 = (size_t)(v / sc.views_per_scene) * sc.G + i0;
+            mbar_init(wbar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(wbar, (uint32_t)nrows * kRow * 4u);
+            bulk_load(smem_u32(buf), sc.color + si0 * 75, (uint32_t)nrows * 300u, wbar);
+            bulk_load(smem_u32(buf + 32 * 75), sc.feature + si0 * (FC * 9), (uint32_t)nrows * FC * 36u, wbar);
+        }
+        __syncwarp();
+        if (i < sc.G) preprocess_one<FC>(sc, st, v, i, wbuf, wbar);
+        if (lane == 0) mbar_wait(wbar, 0);                         // never leave with the copy still in flight
+    } else {
+        if (i < sc.G) preprocess_one<0>(sc, st, v, i, nullptr, 0u);
+    }
 }
 
 // =========================================================================================
@@ -601,8 +664,23 @@ extern "C" int ls_raster_forward(const LsRasterScene* sc, const LsRasterState* s
     if (stages & LS_STAGE_GEOMETRY) {
         cudaMemsetAsync(st->tile_count, 0, sizeof(uint32_t) * (size_t)n_slots, stream);
         if (sc->G > 0) {
-            dim3 grid((sc->G + 255) / 256, sc->n_views);
-            k_preprocess<<<grid, 256, 0, stream>>>(*sc, *st);
+            const bool aligned = ((reinterpret_cast<uintptr_t>(sc->color) | reinterpret_cast<uintptr_t>(sc->feature)) & 15) == 0;
+            if (ls_raster_dense_sh_grads(sc) && aligned) {         // the specialised configuration (also used by the backward)
+                constexpr int kWarps = 4;
+                dim3 gridf((sc->G + 32 * kWarps - 1) / (32 * kWarps), sc->n_views);
+                const int smem = kWarps * 32 * (75 + sc->C * 9) * 4 + kWarps * 8;
+                static lstc::PerDeviceOnce once4, once8;
+                if (sc->C == 4) {
+                    if (smem > 48 * 1024 && once4.ensure_smem(k_preprocess<4>, smem) != cudaSuccess) return ls_check_cuda("preprocess smem attribute");
+                    k_preprocess<4><<<gridf, 32 * kWarps, smem, stream>>>(*sc, *st);
+                } else {
+                    if (smem > 48 * 1024 && once8.ensure_smem(k_preprocess<8>, smem) != cudaSuccess) return ls_check_cuda("preprocess smem attribute");
+                    k_preprocess<8><<<gridf, 32 * kWarps, smem, stream>>>(*sc, *st);
+                }
+            } else {
+                dim3 grid((sc->G + 255) / 256, sc->n_views);
+                k_preprocess<0><<<grid, 256, 0, stream>>>(*sc, *st);
+            }
         }
         // geometry launched on its own = exact sizing: the caller reads stats[0] and allocates, nothing can overflow
         const long long cap_check = (stages & LS_STAGE_RENDER) ? (long long)st->capacity : -1LL;

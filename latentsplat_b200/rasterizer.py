@@ -250,13 +250,13 @@ class RasterCall:
         return self.images
 
     @staticmethod
-    def _padded_rows(like: Tensor):
+    def _padded_rows(like: Tensor, dense: bool = False):
         """Gradient buffer for per-Gaussian coefficient rows (S, G, a, b): rows of a*b floats padded to a multiple of 8 floats
         (whole 32-byte sectors, see LsRasterGrads.color_grad_pitch).  Returns (buffer (S, G, pitch), view shaped like `like`,
         pitch); rows of <= 4 floats (precomputed colours / features) stay dense."""
         S, G = like.shape[:2]
         row = like[0, 0].numel()
-        if like.dim() != 4 or row <= 4 or row % 8 == 0:
+        if dense or like.dim() != 4 or row <= 4 or row % 8 == 0:
             buf = torch.empty_like(like)
             return buf, buf, 0
         pitch = (row + 7) // 8 * 8
@@ -269,10 +269,12 @@ class RasterCall:
         with torch.cuda.device(dev):
             cbuf = cview = fbuf = fview = None
             self.color_pitch = self.feature_pitch = 0
+            # the specialised coefficient backward moves a warp's rows as one bulk copy and wants them dense
+            dense = bool(self.lib.ls_raster_dense_sh_grads(C.byref(self.scene)))
             if self.color is not None:
-                cbuf, cview, self.color_pitch = self._padded_rows(self.color)
+                cbuf, cview, self.color_pitch = self._padded_rows(self.color, dense)
             if self.feature is not None:
-                fbuf, fview, self.feature_pitch = self._padded_rows(self.feature)
+                fbuf, fview, self.feature_pitch = self._padded_rows(self.feature, dense)
             self.grad_buf = dict(color=cbuf, feature=fbuf)
             self.grad_out = dict(
                 record=torch.empty((V, G, self.buf.sizes.grad_stride), device=dev),

@@ -45,7 +45,9 @@ if launches.exists():
     print("wrote", out / f"{tag}_launches.md")
 
 if rep.exists():
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep is read through ncu; a .csv is the `--page raw --csv` dump already made on the GPU box
+    raw = rep.read_text() if rep.suffix == ".csv" else \
+        subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

@@ -493,3 +493,46 @@ def test_more_than_16_value_channels_render_in_passes(cuda):
     total.backward()
     _assert_grad(g_feat.cpu().numpy(), feats.grad.cpu().numpy(), "features (chunked)")
     _assert_grad(g_means.cpu().numpy(), means.grad.cpu().numpy(), "means3D (chunked)")
+
+
+@pytest.mark.parametrize("C,views", [(4, 1), (8, 1), (8, 3)])
+def test_specialised_sh_path_matches_generic_kernels(cuda, C, views):
+    """Colour SH degree 4 + C feature channels of SH degree 2 with G % 4 == 0 take the bulk-staged, register-resident preprocess
+    kernels (k_preprocess<FC>, k_preprocess_bwd<FC>); G % 4 != 0 (one Gaussian dropped) takes the generic ones.  Same inputs on
+    the shared Gaussians => same images and gradients (different summation order only), with 1 and with 3 views per scene
+    (plain bulk store vs cp.reduce add)."""
+    from latentsplat_b200 import _capi
+    from latentsplat_b200.rasterizer import rasterize_views
+    G, H, W = 4096 + 36, 64, 80                                    # several full warps + a ragged tail warp of 4 rows
+    d = helpers.raster_case(G=G, H=H, W=W, seed=91, C=0, color="sh", sh_degree=4)
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=cuda)
+    fsh = synthetic.random_sh(G, C, 2, seed=19).to(cuda)[None]
+    vm = t(d["viewmatrix"]).reshape(1, 4, 4).repeat(views, 1, 1)
+    pm = t(d["projmatrix"]).reshape(1, 4, 4).repeat(views, 1, 1)
+    if views > 1:                                                  # shifted copies of the camera: different cull sets per view
+        for k in range(1, views):
+            vm[k, 3, 0] += 0.05 * k
+            pm[k] = vm[k] @ (torch.linalg.inv(vm[0]) @ pm[0])
+    cam = dict(viewmatrix=vm, projmatrix=pm, campos=t(d["campos"]).reshape(1, 3).repeat(views, 1),
+               tanfov=t([[d["tanfovx"], d["tanfovy"]]]).repeat(views, 1), image_height=H, image_width=W,
+               bg=t(d["bg"]).reshape(1, 3).repeat(views, 1), sh_degree=4)
+    gen = torch.Generator(cuda).manual_seed(4)
+    wc, wf = torch.randn(views, 3, H, W, device=cuda, generator=gen), torch.randn(views, C, H, W, device=cuda, generator=gen)
+    opac = t(d["opacity"])[None].clone()
+    opac[:, -1] = 0.0                                              # the Gaussian that is dropped below is invisible in both runs
+    res = []
+    for drop in (0, 1):                                            # drop = 1: G % 4 != 0 -> generic kernels
+        n = G - drop
+        leaves = [x[:, :n].clone().requires_grad_(True) for x in (t(d["means3D"])[None], t(d["shs"])[None], fsh)]
+        sc = _capi.LsRasterScene(views, views, n, H, W, C, _capi.COLOR_SH, 4, _capi.FEATURE_SH, 2, *([None] * 11))
+        import ctypes
+        assert bool(_capi.load().ls_raster_dense_sh_grads(ctypes.byref(sc))) == (drop == 0)
+        color, feat, alpha, depth, _ = rasterize_views(leaves[0], t(d["cov3D"])[None, :n], opac[:, :n], shs=leaves[1],
+                                                       feature_shs=leaves[2], **cam)
+        ((color * wc).sum() + (feat * wf).sum() + alpha.sum()).backward()
+        res.append((color.detach(), feat.detach(), [x.grad for x in leaves]))
+    (c0, f0, g0), (c1, f1, g1) = res
+    assert helpers.rel_err(c0.cpu().numpy(), c1.cpu().numpy()) < 1e-5 and helpers.rel_err(f0.cpu().numpy(), f1.cpu().numpy()) < 1e-5
+    for name, a, b in zip(("means3D", "shs", "feature_shs"), g0, g1):
+        _assert_grad(a[:, :G - 1].cpu().numpy(), b.cpu().numpy(), f"{name} (specialised vs generic)")
+        assert float(a[:, G - 1].abs().max()) == 0.0
