@@ -47,7 +47,10 @@ CFG = dict(B=4, V_t=1, V_c=2, G=65_536, C=4, color_sh_degree=4, feature_sh_degre
 
 def workload_name(cfg) -> str:
     if cfg.get("workload", "splat") == "full":
-        return (f"re10k_shaped_full_step (BASELINE configs[1]): B={cfg['B']} scene pairs/GPU, V_c=2 context views {H}x{W}, "
+        bc = cfg.get("baseline_config")
+        label = {1: "re10k_shaped_full_step (BASELINE configs[1])", 2: "co3d_shaped_full_step (BASELINE configs[2]: f=1.2, V_t=3)",
+                 3: "re10k_shaped_full_step_b8 (BASELINE configs[3])"}.get(bc, "full_step (no BASELINE config: custom sizes)")
+        return (f"{label}: B={cfg['B']} scene pairs/GPU, focal {cfg['f']}, V_c=2 context views {H}x{W}, "
                 f"encoder(DINO ViT-B/8 + epipolar transformer) -> 393216 Gaussians/scene -> splat V_t={cfg['V_t']} target "
                 "views -> VAE kl-f8 decoder with skips -> PatchGAN logits; fwd+bwd+fused Adam; OUR sm_100a kernels: rasterizer fwd+bwd, every Linear "
                 "(tcgen05 TF32 GEMM fwd/dgrad/wgrad with bias/GELU/residual epilogues), every convolution (tcgen05 implicit GEMM over "
@@ -958,6 +961,8 @@ def run_ours(args, cfg):
         peak, peak_src = measured_peaks()
         ms, num_rendered = stage_profile(dec, dev_batch, cfg)
         nbytes = stage_bytes(cfg, views_per_step, num_rendered)
+        if FWD_ONLY:                                         # configs[4] is forward only: the backward stages are not part of its step
+            ms = {k: v for k, v in ms.items() if not k.endswith("_bwd")}
         dom = max(ms, key=ms.get)
         ach = nbytes[dom] / (ms[dom] / 1000) / 1e9
         traffic = None

@@ -272,7 +272,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 }
 
 // =================================================================================================================
-// EXPERIMENTAL (off unless LS_GEMM_2CTA=1): cta_group::2 variant -- a cluster of two CTAs (one TPC) owns a 256 x BN tile.
+// cta_group::2 variant (default for M > 128; LS_GEMM_2CTA=0 selects the 1-CTA kernel) -- a cluster of two CTAs (one TPC) owns a 256 x BN tile.
 // Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows); the leader's tcgen05.mma.cta_group::2 reads
 // A and B from both CTAs' shared memory, so per MMA (135 tensor cycles at M256 N256 K8) a CTA streams 4 KB of A +
 // 4 KB of B instead of 4 + 8 KB -- the shared-memory bandwidth that caps the 1-CTA kernel at 57-60 % tensor pipe.
@@ -282,10 +282,10 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 //   empty[s]  one per CTA, released by the leader's tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11)
 //   tfull[a]  one per CTA, same multicast commit -> each CTA's epilogue drains its own 128 TMEM lanes
 //   tempty[a] lives in the leader, 8 arrivals (4 epilogue warps x 2 CTAs; the peer arrives through shared::cluster)
-// Round-1 status: passes tests/test_gemm_gpu.py (all four operand layouts, tails, split-K, bias/activation, Linear
-// forward/backward) with LS_GEMM_2CTA=1 and is 4-13 % faster than the 1-CTA kernel on the DINO shapes
-// (scripts/gemm_ab.py: 8200x3072x768 506 -> 525 TF/s, 8200x768x3072 429 -> 484 TF/s); it stays opt-in until the
-// whole step has been validated with it and the remaining limiter (epilogue drain / wave quantisation) is profiled.
+// Status: passes tests/test_gemm_gpu.py (all four operand layouts, tails, split-K, bias / activation / residual epilogues, Linear
+// forward/backward) and the whole GPU suite; 4-13 % faster than the 1-CTA kernel on the DINO shapes (scripts/gemm_ab.py:
+// 8200x3072x768 506 -> 525 TF/s, 8200x768x3072 429 -> 484 TF/s); whole-step A/B on one box (round 2): GEMM family 13.58 -> 12.78 ms,
+// step 76.35 -> 75.12 ms -- hence the default.
 // =================================================================================================================
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;        // shared::cluster address of the even (leader) CTA's copy
 
@@ -490,7 +490,7 @@ int launch_s(const CUtensorMap& ma, const CUtensorMap& mb, const LsGemmArgs* a, 
     return ls_check_cuda("k_gemm_tf32");
 }
 
-// EXPERIMENTAL 2-CTA launch (LS_GEMM_2CTA=1): grid.x counts 256-row tiles, one cluster of two CTAs per work item slot.
+// 2-CTA launch: grid.x counts 256-row tiles, one cluster of two CTAs per work item slot.
 constexpr int smem_bytes_2cta(int stages, int bn) { return stages * (A_BYTES + (bn / 2) * BK * 4) + PATCH_BYTES + 1024 + 256; }
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
@@ -520,7 +520,7 @@ bool use_2cta() {
     static int flag = -1;
     if (flag < 0) {
         const char* e = getenv("LS_GEMM_2CTA");
-        flag = (e && atoi(e) == 1) ? 1 : 0;
+        flag = (e && atoi(e) == 0) ? 0 : 1;                 // on by default
     }
     return flag == 1;
 }
@@ -570,7 +570,7 @@ extern "C" int ls_gemm_tf32(const LsGemmArgs* a, void* stream_) {
     const int BN = pick_bn(a->N);
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (use_2cta() && a->M > BM) {                     // experimental cta_group::2 path: 256-row tiles, B box = BN/2 rows
+    if (use_2cta() && a->M > BM) {                     // cta_group::2 path: 256-row tiles, B box = BN/2 rows
         if (a->a_mn_major ? make_map(&ma, a->A, a->M, a->K, a->lda, 32, sw_mn) : make_map(&ma, a->A, a->K, a->M, a->lda, BM, sw_k)) return -1;
         if (a->b_mn_major ? make_map(&mb, a->B, a->N, a->K, a->ldb, 32, sw_mn) : make_map(&mb, a->B, a->K, a->N, a->ldb, (uint32_t)(BN / 2), sw_k)) return -1;
         dim3 grid2((a->M + 2 * BM - 1) / (2 * BM), (a->N + BN - 1) / BN, split);

@@ -49,8 +49,8 @@ __device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const Ls
     st.radii[vi] = 0;
     st.tiles_touched[vi] = 0;
     st.clamped[vi] = 0;
-    grec[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    grec[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // a culled Gaussian leaves a zero geometry record (written on the way out: survivors write their record once, not twice)
+    auto cull = [&]() { grec[0] = make_float4(0.f, 0.f, 0.f, 0.f); grec[1] = make_float4(0.f, 0.f, 0.f, 0.f); };
 
     const float* __restrict__ vm = sc.viewmatrix + 16 * v;
     const float* __restrict__ pm = sc.projmatrix + 16 * v;
@@ -62,7 +62,7 @@ __device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const Ls
     const float p[3] = {mul_(sc.means3D[3 * si], scale), mul_(sc.means3D[3 * si + 1], scale),
                         mul_(sc.means3D[3 * si + 2], scale)};
     const float zv = xform_row(vm, 2, p[0], p[1], p[2]);
-    if (zv <= 0.2f) return;  // [EXT] near cull
+    if (zv <= 0.2f) { cull(); return; }  // [EXT] near cull
     const float hx = xform_row(pm, 0, p[0], p[1], p[2]);
     const float hy = xform_row(pm, 1, p[0], p[1], p[2]);
     const float hw = xform_row(pm, 3, p[0], p[1], p[2]);
@@ -75,7 +75,7 @@ __device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const Ls
     Cov2D q;
     cov2d(p, fx, fy, tanx, tany, cv, vm, q);
     const float det = sub_(mul_(q.a, q.c), mul_(q.b, q.b));
-    if (det == 0.0f) return;
+    if (det == 0.0f) { cull(); return; }
     const float det_inv = div_(1.0f, det);
     const float cxx = mul_(q.c, det_inv), cxy = mul_(-q.b, det_inv), cyy = mul_(q.a, det_inv);
     const float mid = mul_(0.5f, add_(q.a, q.c));
@@ -87,13 +87,14 @@ __device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const Ls
     int rmin[2], rmax[2];
     get_rect(px, py, radius, gx, gy, rmin, rmax);
     const int ntiles = (rmax[0] - rmin[0]) * (rmax[1] - rmin[1]);
-    if (ntiles == 0) return;
+    if (ntiles == 0) { cull(); return; }
 
     // ---- colour / feature values of this Gaussian for this view -----------------------
     const int ncol = n_color(sc.color_mode);
     float* crec = st.chan + vi * st.chan_stride;
     const bool color_sh = color_is_sh(sc.color_mode), permuted = sc.color_mode == LS_COLOR_SH_3DGS;
     const bool need_dir = color_sh || sc.feature_mode == LS_FEATURE_SH;
+    float col3[3] = {0.f, 0.f, 0.f};                               // colour of the specialised path (stored with the features)
     float basis[25];
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
     if (need_dir) {
@@ -131,7 +132,8 @@ __device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const Ls
         }
         r += 0.5f; g += 0.5f; b += 0.5f;
         st.clamped[vi] = (uint8_t)((r < 0.f ? 1 : 0) | (g < 0.f ? 2 : 0) | (b < 0.f ? 4 : 0));
-        crec[0] = fmaxf(r, 0.f); crec[1] = fmaxf(g, 0.f); crec[2] = fmaxf(b, 0.f);
+        if constexpr (FC > 0) { col3[0] = fmaxf(r, 0.f); col3[1] = fmaxf(g, 0.f); col3[2] = fmaxf(b, 0.f); }
+        else { crec[0] = fmaxf(r, 0.f); crec[1] = fmaxf(g, 0.f); crec[2] = fmaxf(b, 0.f); }
     } else if (sc.color_mode == LS_COLOR_PRECOMP) {
         crec[0] = sc.color[3 * si]; crec[1] = sc.color[3 * si + 1]; crec[2] = sc.color[3 * si + 2];
     }
@@ -153,8 +155,14 @@ __device__ __forceinline__ void preprocess_one(const LsRasterScene& sc, const Ls
                     acc[c] = fmaf(basis[k], x[e], acc[c]);
                 }
             }
+            // the whole channel record (colour + features, padded to float4s) leaves in 16-byte stores
+            constexpr int kVals = (3 + FC + 3) / 4 * 4;
+            float vals[kVals];
 #pragma unroll
-            for (int c = 0; c < FC; ++c) crec[ncol + c] = 0.5f + acc[c];
+            for (int q = 0; q < kVals; ++q) vals[q] = q < 3 ? col3[q] : (q < 3 + FC ? 0.5f + acc[q - 3] : 0.f);
+#pragma unroll
+            for (int q = 0; q < kVals; q += 4)
+                *reinterpret_cast<float4*>(crec + q) = make_float4(vals[q], vals[q + 1], vals[q + 2], vals[q + 3]);
         } else {
             if (permuted) sh_basis<false>(sc.feature_sh_degree, d0, d1, d2, basis, nullptr);
             const int n = (sc.feature_sh_degree + 1) * (sc.feature_sh_degree + 1);
