@@ -448,7 +448,8 @@ def run_full(args, cfg):
         n0 = capi.KERNEL_LAUNCHES[0]
         fwd_bwd(dev_flat)
         gpu_launches = capi.KERNEL_LAUNCHES[0] - n0          # OUR kernels per step (rasterizer, GEMMs, fused attention)
-        capacity = pipe.decoder.calibrate_raster_capacity(slack=1.5)
+        # 3x the size of the second step: Adam moves every weight each step and the key lists grow by ~1 % per step at first
+        capacity = pipe.decoder.calibrate_raster_capacity(slack=3.0)
         num_rendered = pipe.decoder.last_raster.num_rendered
         n_eager = max(3, args.steps // 4)
         opt_step()                                            # untimed: Adam state allocation, fused-kernel selection
@@ -458,20 +459,33 @@ def run_full(args, cfg):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
 
-    g_fb = GraphedStep(fwd_bwd, dev_flat, warmup=warm)
-    g_opt = GraphedStep(opt_step, {}, warmup=1)
+    from latentsplat_b200.rasterizer import RasterCapacityError, reset_overflow_guard
+    graphs = {}
+    overflowed = [False]
+
+    def capture():
+        graphs["fb"] = GraphedStep(fwd_bwd, dev_flat, warmup=warm)
+        graphs["opt"] = GraphedStep(opt_step, {}, warmup=1)
 
     def step():
-        r = g_fb.replay()
+        g_fb = graphs["fb"]
+        try:
+            r = g_fb.replay()
+        except RasterCapacityError:            # the weights move every step and with them the key-list size: note it, keep the
+            overflowed[0] = True               # ranks in lock-step (replay anyway) and discard this attempt below
+            reset_overflow_guard()
+            g_fb.graph.replay()
+            r = g_fb.static_out
         if reducer is None:
             fgrads.all_reduce_mean()           # no-op at world size 1
-        g_opt.replay()
+        graphs["opt"].replay()
         return r
 
     def step_e2e():
-        g_fb.load(pinned)
+        graphs["fb"].load(pinned)
         return float(step()["loss"].item())
 
+    capture()
     for _ in range(warm):
         step(); step_e2e()
     if args.profiler_range:
@@ -485,12 +499,30 @@ def run_full(args, cfg):
         print(json.dumps({"profiler_range": args.profiler_range, "steps": args.steps,
                           "ms_per_step_under_profiler": dev_ms / args.steps}), flush=True)
         return
-    with ClockSampler(local_rank) as clk:
-        dev_ms, wall_ms = timed_loop(step, args.steps)
-        e2e_ms, _ = timed_loop(step_e2e, args.steps)
-    clocks = clk.summary()
-    if int(pipe.decoder.last_raster.stats[2].item()):
-        raise SystemExit(f"rasterizer key capacity {capacity} overflowed; result invalid")
+    # The optimiser really updates the weights, so the scene -- and the number of (tile, Gaussian) pairs -- drifts from step to
+    # step.  An attempt whose key lists overflowed on ANY rank is discarded: every rank doubles the capacity, re-captures and
+    # measures again (the decision is all-reduced so that the ranks stay in lock-step).
+    for attempt in range(4):
+        with ClockSampler(local_rank) as clk:
+            dev_ms, wall_ms = timed_loop(step, args.steps)
+            e2e_ms, _ = timed_loop(step_e2e, args.steps)
+        clocks = clk.summary()
+        flag = torch.tensor([float(overflowed[0] or int(pipe.decoder.last_raster.stats[2].item()) != 0)], device=device)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if not bool(flag.item()):
+            break
+        capacity *= 2
+        pipe.decoder.raster_capacity = capacity
+        overflowed[0] = False
+        reset_overflow_guard()
+        graphs.clear()
+        capture()
+        for _ in range(warm):
+            step()
+        overflowed[0] = False
+    else:
+        raise SystemExit(f"rasterizer key capacity {capacity} overflowed four times in a row; result invalid")
 
     t = torch.tensor([dev_ms, e2e_ms, eager_ms], device=device, dtype=torch.float64)
     if world > 1:

@@ -21,7 +21,7 @@ from torch import Tensor, nn
 from . import _capi
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_views", "RasterDebug", "RasterCall",
-           "RasterCapacityError", "check_overflow", "reserve_overflow_slots"]
+           "RasterCapacityError", "check_overflow", "reserve_overflow_slots", "reset_overflow_guard"]
 
 
 class RasterCapacityError(RuntimeError):
@@ -100,6 +100,14 @@ _GUARD = _OverflowGuard()
 def reserve_overflow_slots(n: int = 8) -> None:
     """Pre-allocate the pinned flag buffers that sync-free calls captured into a CUDA graph will write to."""
     _GUARD.reserve(n)
+
+
+def reset_overflow_guard() -> None:
+    """Forget every outstanding / graph-resident overflow flag (after the caller has dealt with an overflow, e.g. re-captured its
+    CUDA graph with a larger capacity: the old graph's flag buffer would otherwise keep reporting)."""
+    _GUARD.free.extend(h for _, h, _ in _GUARD.pending)
+    _GUARD.pending.clear()
+    _GUARD.resident.clear()
 
 
 def check_overflow(block: bool = False) -> None:
