@@ -394,8 +394,8 @@ def run_full(args, cfg):
     flat_grad = fgrads.flat
     # N > 1, default: one NCCL all-reduce of the flat buffer between the fwd+bwd graph and the Adam graph (measured path).
     # LS_BENCH_ALLREDUCE=overlap: bucketed all-reduce launched by gradient hooks DURING backward on a communication stream and
-    # captured into the step's CUDA graph (parallel.BucketedAllReduce; verified on gloo, NOT yet on NCCL: the first 2-GPU attempt
-    # hung inside the capture, so it stays opt-in)
+    # captured into the step's CUDA graph (parallel.BucketedAllReduce; verified on gloo, but it HANGS on NCCL at 2 GPUs right after the
+    # first eager backward -- see DESIGN.md section 1 row (e) -- so it stays opt-in and unmeasured)
     overlap = world > 1 and os.environ.get("LS_BENCH_ALLREDUCE", "after") == "overlap"
     reducer = BucketedAllReduce(fgrads, bucket_bytes=32 << 20) if overlap else None
     opt = torch.optim.Adam(params, lr=1.5e-5, fused=True, capturable=True)
