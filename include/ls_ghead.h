@@ -73,6 +73,17 @@ typedef struct LsGaussianHeadGrad {
 LS_API int ls_gaussian_head_forward(const LsGaussianHead* args, const LsGaussianHeadOut* out, void* stream /* cudaStream_t */);
 LS_API int ls_gaussian_head_backward(const LsGaussianHead* args, const LsGaussianHeadGrad* grads, void* stream /* cudaStream_t */);
 
+/* Reparameterised sample of the variational Gaussians' feature harmonics (VariationalGaussians.sample ->
+ * DiagonalGaussianDistribution.sample, /root/reference/src/model/diagonal_gaussian_distribution.py:30-36, 78-81; called at
+ * model_wrapper.py:362): params (rows, 2*half) = [mean | logvar] per row, eps (rows, half) standard-normal draws (torch's RNG),
+ *   out = mean + exp(0.5 * clamp(logvar, lo, hi)) * eps          -- one pass instead of clamp / exp / exp / mul / add
+ *   d_params = [g | g * eps * 0.5 * std * 1(lo <= logvar <= hi)]  -- written as one (rows, 2*half) tensor
+ * half % 4 == 0, 16-byte aligned pointers. */
+LS_API int ls_reparam_forward(const float* params, const float* eps, float* out, int64_t rows, int32_t half, float lo, float hi,
+                              void* stream /* cudaStream_t */);
+LS_API int ls_reparam_backward(const float* params, const float* eps, const float* g, float* d_params, int64_t rows, int32_t half,
+                               float lo, float hi, void* stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

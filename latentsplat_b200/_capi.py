@@ -120,7 +120,7 @@ EXPORTS = ("ls_raster_sizes", "ls_raster_forward", "ls_raster_backward", "ls_las
            "ls_groupnorm_nhwc_forward", "ls_groupnorm_nhwc_backward",
            "ls_conv2d_out_size", "ls_conv2d_forward", "ls_conv2d_dgrad", "ls_conv2d_wgrad", "ls_act_backward",
            "ls_upconv2x_workspace", "ls_upconv2x_forward", "ls_upconv2x_dgrad", "ls_upconv2x_wgrad",
-           "ls_gaussian_head_forward", "ls_gaussian_head_backward", "ls_fmha_forward", "ls_fmha_backward",
+           "ls_gaussian_head_forward", "ls_gaussian_head_backward", "ls_reparam_forward", "ls_reparam_backward", "ls_fmha_forward", "ls_fmha_backward",
            "ls_softmax_rows_forward", "ls_softmax_rows_backward")
 
 _lib = None
@@ -203,6 +203,10 @@ def load() -> C.CDLL:
     lib.ls_gaussian_head_forward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadOut), C.c_void_p]
     lib.ls_gaussian_head_backward.restype = C.c_int
     lib.ls_gaussian_head_backward.argtypes = [C.POINTER(LsGaussianHead), C.POINTER(LsGaussianHeadGrad), C.c_void_p]
+    lib.ls_reparam_forward.restype = C.c_int
+    lib.ls_reparam_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]
+    lib.ls_reparam_backward.restype = C.c_int
+    lib.ls_reparam_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]
     lib.ls_raster_dense_sh_grads.restype = C.c_int
     lib.ls_raster_dense_sh_grads.argtypes = [C.POINTER(LsRasterScene)]
     lib.ls_fmha_forward.restype = C.c_int

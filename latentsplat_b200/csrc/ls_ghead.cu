@@ -373,9 +373,72 @@ static int check(const LsGaussianHead* a) {
     return 0;
 }
 
+// ---- reparameterised sample of a diagonal Gaussian stored as params = [mean | logvar] per row -------------------------------
+// out[r, j] = mean + exp(0.5 * clamp(logvar, lo, hi)) * eps,   params row r = (mean[0..half), logvar[0..half)), half % 4 == 0
+__global__ void __launch_bounds__(256) k_reparam_fwd(const float* __restrict__ params, const float* __restrict__ eps,
+                                                     float* __restrict__ out, long long rows, int half, float lo, float hi) {
+    const int q = half >> 2;                                               // float4s per half row
+    const long long n4 = rows * q;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / q;
+        const int j = (int)(t - r * q) << 2;
+        const float4 m = *reinterpret_cast<const float4*>(params + r * 2 * half + j);
+        const float4 lv = *reinterpret_cast<const float4*>(params + r * 2 * half + half + j);
+        const float4 e = *reinterpret_cast<const float4*>(eps + r * half + j);
+        float4 o;
+        o.x = fmaf(expf(0.5f * fminf(fmaxf(lv.x, lo), hi)), e.x, m.x);
+        o.y = fmaf(expf(0.5f * fminf(fmaxf(lv.y, lo), hi)), e.y, m.y);
+        o.z = fmaf(expf(0.5f * fminf(fmaxf(lv.z, lo), hi)), e.z, m.z);
+        o.w = fmaf(expf(0.5f * fminf(fmaxf(lv.w, lo), hi)), e.w, m.w);
+        *reinterpret_cast<float4*>(out + r * half + j) = o;
+    }
+}
+
+// d_params[r] = (g, g * eps * 0.5 * std * [lo <= logvar <= hi])   (torch.clamp passes the gradient on the closed interval)
+__global__ void __launch_bounds__(256) k_reparam_bwd(const float* __restrict__ params, const float* __restrict__ eps,
+                                                     const float* __restrict__ g, float* __restrict__ d_params, long long rows, int half,
+                                                     float lo, float hi) {
+    const int q = half >> 2;
+    const long long n4 = rows * q;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / q;
+        const int j = (int)(t - r * q) << 2;
+        const float4 lv = *reinterpret_cast<const float4*>(params + r * 2 * half + half + j);
+        const float4 e = *reinterpret_cast<const float4*>(eps + r * half + j);
+        const float4 go = *reinterpret_cast<const float4*>(g + r * half + j);
+        auto dl = [&](float l, float ee, float gg) { return (l >= lo && l <= hi) ? gg * ee * 0.5f * expf(0.5f * l) : 0.f; };
+        *reinterpret_cast<float4*>(d_params + r * 2 * half + j) = go;
+        *reinterpret_cast<float4*>(d_params + r * 2 * half + half + j) = make_float4(dl(lv.x, e.x, go.x), dl(lv.y, e.y, go.y), dl(lv.z, e.z, go.z), dl(lv.w, e.w, go.w));
+    }
+}
+
+static int check_reparam(const void* a, const void* b, const void* c, long long rows, int half) {
+    if (!a || !b || !c) return ls_fail("reparam: NULL pointer");
+    if (rows <= 0 || half <= 0 || half % 4) return ls_fail("reparam: rows=%lld half=%d (half must be a positive multiple of 4)", rows, half);
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) return ls_fail("reparam: pointers must be 16-byte aligned");
+    return 0;
+}
+
 }  // namespace lsh
 
 using namespace lsh;
+
+extern "C" int ls_reparam_forward(const float* params, const float* eps, float* out, int64_t rows, int32_t half, float lo, float hi, void* stream) {
+    if (check_reparam(params, eps, out, rows, half)) return -1;
+    const long long n4 = rows * (half / 4);
+    const unsigned blocks = (unsigned)(n4 + 255) / 256 < 148u * 16u ? (unsigned)((n4 + 255) / 256) : 148u * 16u;
+    k_reparam_fwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, eps, out, rows, half, lo, hi);
+    return ls_check_cuda("k_reparam_fwd");
+}
+
+extern "C" int ls_reparam_backward(const float* params, const float* eps, const float* g, float* d_params, int64_t rows, int32_t half,
+                                   float lo, float hi, void* stream) {
+    if (check_reparam(params, eps, g, rows, half) || check_reparam(d_params, eps, g, rows, half)) return -1;
+    const long long n4 = rows * (half / 4);
+    const unsigned blocks = (unsigned)(n4 + 255) / 256 < 148u * 16u ? (unsigned)((n4 + 255) / 256) : 148u * 16u;
+    k_reparam_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, eps, g, d_params, rows, half, lo, hi);
+    return ls_check_cuda("k_reparam_bwd");
+}
 
 extern "C" int ls_gaussian_head_forward(const LsGaussianHead* a, const LsGaussianHeadOut* o, void* stream) {
     if (check(a)) return -1;

@@ -13,6 +13,7 @@ import torch
 from torch import Tensor
 
 from .projection import get_world_rays, homogenize_points, homogenize_vectors, intersect_rays, matvec, project_camera_space
+from latentsplat_b200.geometry.inverse import inv_affine4x4  # closed-form camera inverses (no cuSOLVER)
 
 
 def _is_in_bounds(xy: Tensor, epsilon: float = 1e-6) -> Tensor:
@@ -67,7 +68,7 @@ def project_rays(origins: Tensor, directions: Tensor, extrinsics: Tensor, intrin
                  near: Optional[Tensor] = None, far: Optional[Tensor] = None, epsilon: float = 1e-6) -> dict:
     """World rays -> the image-space segment they trace in the camera (extrinsics, intrinsics)
     (epipolar_lines.py:157-251).  Returns t_min, t_max, xy_min, xy_max, overlaps_image."""
-    world_to_cam = torch.linalg.inv_ex(extrinsics, check_errors=False).inverse
+    world_to_cam = inv_affine4x4(extrinsics)
     origins = matvec(world_to_cam, homogenize_points(origins))[..., :3]
     directions = matvec(world_to_cam, homogenize_vectors(directions))[..., :3]
 

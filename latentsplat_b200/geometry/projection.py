@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import torch
 from torch import Tensor
+from latentsplat_b200.geometry.inverse import inv3x3, inv_affine4x4  # closed-form camera inverses (no cuSOLVER)
 
 
 def homogenize_points(points: Tensor) -> Tensor:
@@ -36,7 +37,7 @@ def transform_cam2world(homogeneous_coordinates: Tensor, extrinsics: Tensor) -> 
 
 
 def transform_world2cam(homogeneous_coordinates: Tensor, extrinsics: Tensor) -> Tensor:
-    return transform_rigid(homogeneous_coordinates, torch.linalg.inv_ex(extrinsics, check_errors=False).inverse)
+    return transform_rigid(homogeneous_coordinates, inv_affine4x4(extrinsics))
 
 
 def project_camera_space(points: Tensor, intrinsics: Tensor, epsilon: float = torch.finfo(torch.float32).eps,
@@ -56,7 +57,7 @@ def project(points: Tensor, extrinsics: Tensor, intrinsics: Tensor,
 
 def unproject(coordinates: Tensor, z: Tensor, intrinsics: Tensor) -> Tensor:
     """Normalised image coordinates + depth -> camera-space points (projection.py:79-95)."""
-    inv = torch.linalg.inv_ex(intrinsics, check_errors=False).inverse
+    inv = inv3x3(intrinsics)
     rays = matvec(inv, homogenize_points(coordinates))
     return rays * z[..., None]
 

@@ -20,6 +20,7 @@ import torch
 from torch import Tensor
 
 from ...rasterizer import RasterDebug, rasterize_views
+from latentsplat_b200.geometry.inverse import inv3x3, inv_affine4x4  # closed-form camera inverses (no cuSOLVER)
 
 
 _FOV_RAYS: dict = {}
@@ -37,7 +38,7 @@ def _fov_rays(device) -> Tensor:
 
 def get_fov(intrinsics: Tensor) -> Tensor:
     """Field of view (x, y) of normalised intrinsics; /root/reference/src/geometry/projection.py:233-247."""
-    inv = torch.linalg.inv_ex(intrinsics, check_errors=False).inverse
+    inv = inv3x3(intrinsics)
     rays = torch.einsum("bij,kj->kbi", inv, _fov_rays(intrinsics.device))   # left, right, top, bottom
     rays = rays / rays.norm(dim=-1, keepdim=True)
     return torch.stack(((rays[0] * rays[1]).sum(dim=-1).acos(), (rays[2] * rays[3]).sum(dim=-1).acos()), dim=-1)
@@ -76,7 +77,7 @@ def _upper_triangle(cov: Tensor) -> Tensor:
 def _camera_matrices(extrinsics: Tensor, near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor):
     """view (transposed), full projection (transposed) as at cuda_splatting.py:114-118."""
     projection = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
-    view = torch.linalg.inv_ex(extrinsics, check_errors=False).inverse.transpose(1, 2)
+    view = inv_affine4x4(extrinsics).transpose(1, 2)
     return view, view @ projection
 
 
@@ -222,7 +223,7 @@ def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     """Depth (or a transform of it) rendered as a fake colour (cuda_splatting.py:298-340)."""
     v = extrinsics.shape[0]
     means_v = gaussian_means.repeat_interleave(views_per_scene, dim=0) if views_per_scene > 1 else gaussian_means
-    world2cam = torch.linalg.inv_ex(extrinsics, check_errors=False).inverse
+    world2cam = inv_affine4x4(extrinsics)
     z = torch.einsum("bj,bgj->bg", world2cam[:, 2, :3], means_v) + world2cam[:, 2, 3:4]
     if mode == "disparity":
         z = 1 / z

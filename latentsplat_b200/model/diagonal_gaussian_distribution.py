@@ -12,6 +12,50 @@ import torch
 from torch import Tensor
 
 
+def _fused_ok(params: Optional[Tensor], dim: int) -> bool:
+    if params is None or not (params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()):
+        return False
+    width = 1
+    for n in params.shape[dim:]:
+        width *= n
+    return width % 8 == 0 and params.numel() > 0
+
+
+class _ReparamFn(torch.autograd.Function):
+    """sample = mean + std * eps on libls_raster.so::ls_reparam_* (include/ls_ghead.h): params = cat(mean, logvar) along `dim`, i.e.
+    rows of [mean | logvar] once everything from `dim` on is flattened."""
+
+    @staticmethod
+    def forward(ctx, params: Tensor, eps: Tensor, dim: int, lo: float, hi: float) -> Tensor:
+        import ctypes as C
+        from latentsplat_b200 import _capi
+        dim = dim % params.dim()
+        width = params[(0,) * dim].numel() if dim else params.numel()
+        rows, half = params.numel() // width, width // 2
+        eps = eps.contiguous()
+        out = torch.empty_like(eps)
+        with torch.cuda.device(params.device):
+            _capi.check(_capi.load().ls_reparam_forward(params.data_ptr(), eps.data_ptr(), out.data_ptr(), rows, half, lo, hi,
+                                                        torch.cuda.current_stream().cuda_stream), "ls_reparam_forward")
+        _capi.KERNEL_LAUNCHES[0] += 1
+        ctx.save_for_backward(params, eps)
+        ctx.cfg = (rows, half, lo, hi)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        from latentsplat_b200 import _capi
+        params, eps = ctx.saved_tensors
+        rows, half, lo, hi = ctx.cfg
+        g = g.contiguous()
+        d_params = torch.empty_like(params)
+        with torch.cuda.device(params.device):
+            _capi.check(_capi.load().ls_reparam_backward(params.data_ptr(), eps.data_ptr(), g.data_ptr(), d_params.data_ptr(), rows, half,
+                                                         lo, hi, torch.cuda.current_stream().cuda_stream), "ls_reparam_backward")
+        _capi.KERNEL_LAUNCHES[0] += 1
+        return d_params, None, None, None, None
+
+
 class DiagonalGaussianDistribution:
     def __init__(self, mean: Optional[Tensor] = None, logvar: Optional[Tensor] = None,
                  params: Optional[Tensor] = None, dim: int = 0,
@@ -30,17 +74,20 @@ class DiagonalGaussianDistribution:
 
     # -- logvar / std / var ------------------------------------------------------------
     def _set_logvar(self, val: Optional[Tensor]) -> None:
+        self._raw_logvar = val
         if val is None:
             self._logvar, self._std, self._var = None, 0.0, 0.0  # zero variance by default
             return
         if val.shape != self.mean.shape:
             raise AssertionError("Shapes of mean and logvar must be identical")
-        self._logvar = torch.clamp(val, *self.logvar_interval)
-        self._std = torch.exp(0.5 * self._logvar)
-        self._var = torch.exp(self._logvar)
+        self._raw_logvar = val
+        self._logvar = self._std = self._var = None            # clamp / exp run on first use (the render path needs none of them
+                                                               # when it samples through the fused kernel below)
 
     @property
     def logvar(self) -> Optional[Tensor]:
+        if self._logvar is None and self._raw_logvar is not None:
+            self._logvar = torch.clamp(self._raw_logvar, *self.logvar_interval)
         return self._logvar
 
     @logvar.setter
@@ -49,10 +96,14 @@ class DiagonalGaussianDistribution:
 
     @property
     def std(self):
+        if self._std is None:
+            self._std = torch.exp(0.5 * self.logvar)
         return self._std
 
     @property
     def var(self):
+        if self._var is None:
+            self._var = torch.exp(self.logvar)
         return self._var
 
     # -- params ------------------------------------------------------------------------
@@ -78,9 +129,13 @@ class DiagonalGaussianDistribution:
 
     # -- distribution ops --------------------------------------------------------------
     def sample(self) -> Tensor:
-        if isinstance(self.std, float) and self.std == 0:
+        if self._raw_logvar is None:
             return self.mean
-        return self.mean + self.std * torch.randn_like(self.mean)
+        eps = torch.randn_like(self.mean)
+        if _fused_ok(self._params, self.dim):
+            # CUDA: mean + exp(0.5 clamp(logvar)) * eps in one pass over the packed params, its gradient in one pass back
+            return _ReparamFn.apply(self._params, eps, self.dim, *self.logvar_interval)
+        return self.mean + self.std * eps
 
     def mode(self) -> Tensor:
         return self.mean

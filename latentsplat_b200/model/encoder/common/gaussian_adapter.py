@@ -11,6 +11,7 @@ from ....geometry.projection import get_world_rays
 from ....misc.cache import device_constant
 from ....misc.sh_utils import sh_rotation_matrices
 from .gaussians import build_covariance, outer_sym, quaternion_to_matrix  # noqa: F401
+from latentsplat_b200.geometry.inverse import inv2x2  # closed-form camera inverses (no cuSOLVER)
 
 
 @dataclass
@@ -119,7 +120,7 @@ class GaussianAdapter(nn.Module):
         return torch.cat(parts, dim=-1)
 
     def get_scale_multiplier(self, intrinsics: Tensor, pixel_size: Tensor, multiplier: float = 0.1) -> Tensor:
-        inv = torch.linalg.inv_ex(intrinsics[..., :2, :2], check_errors=False).inverse
+        inv = inv2x2(intrinsics[..., :2, :2])
         return (multiplier * torch.einsum("...ij,j->...i", inv, pixel_size)).sum(dim=-1)
 
     @property

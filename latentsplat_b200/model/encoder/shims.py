@@ -6,6 +6,7 @@ import torch
 from torch import Tensor
 
 from ...misc.cache import device_constant
+from latentsplat_b200.geometry.inverse import inv2x2  # closed-form camera inverses (no cuSOLVER)
 
 
 def apply_patch_shim_to_views(views: dict, patch_size: int) -> dict:
@@ -33,7 +34,7 @@ def compute_depth_for_disparity(extrinsics: Tensor, intrinsics: Tensor, image_sh
     baselines = deltas.flatten(1).max(dim=1).values
     h, w = image_shape
     pixel_size = device_constant((1 / w, 1 / h), extrinsics.device)
-    inv = torch.linalg.inv_ex(intrinsics[..., :2, :2], check_errors=False).inverse
+    inv = inv2x2(intrinsics[..., :2, :2])
     pixel_size = torch.einsum("...ij,j->...i", inv, pixel_size)
     return baselines / (disparity * pixel_size.flatten(1).mean(dim=1))
 

@@ -58,3 +58,21 @@ print("---- kernels ----")
 ka = [e for e in ka if not e.key.startswith('aten::') and e.key not in ('FWD','BWD') and 'Backward' not in e.key and not e.key.startswith('_') and 'autograd' not in e.key]
 for e in ka[:50]:
     print(f"{e.self_device_time_total/1e3:9.2f} ms {100*e.self_device_time_total/tot:5.1f}% {e.count:5d}x  {e.key[:110]}")
+
+# ---- where does the remaining torch glue come from: aten ops by (op, input shapes, first repo frame) ----
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True, with_stack=True) as prof2:
+    step(); torch.cuda.synchronize()
+import collections
+agg = collections.OrderedDict()
+for ev in prof2.events():
+    if not ev.name.startswith("aten::") or ev.self_device_time_total <= 0:
+        continue
+    frame = next((f for f in (ev.stack or []) if "latentsplat_b200" in f or "bench.py" in f), "?")
+    frame = frame.split("latentsplat_b200/")[-1][:70]
+    shapes = str([s for s in (ev.input_shapes or []) if s])[:70]
+    a = agg.setdefault((ev.name, shapes, frame), [0, 0.0])
+    a[0] += 1
+    a[1] += ev.self_device_time_total
+print("---- aten glue by (op, shapes, repo frame) ----")
+for (name, shapes, frame), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+    print(f"{t/1e3:8.2f} ms {n:4d}x {name[6:]:28s} {shapes:70s} {frame}")

@@ -76,3 +76,26 @@ def test_fused_gaussian_head_matches_explicit_sequence(cuda, deterministic, expo
     ray_ok = same.view(b, v, r, spp).all(dim=-1)
     _close(gd[ray_ok], rd[ray_ok], "d depth logits")
     _close(gr[ray_ok], rr[ray_ok], "d raw Gaussian parameters")
+
+
+def test_fused_reparameterised_sample_matches_torch(cuda):
+    """DiagonalGaussianDistribution.sample() on the packed params (ls_reparam_*): same draws (torch RNG, same call), same values and
+    gradients as mean + exp(0.5 clamp(logvar)) * eps, including the clamp's closed-interval gradient."""
+    import torch
+    from latentsplat_b200.model.diagonal_gaussian_distribution import DiagonalGaussianDistribution
+    g = torch.Generator(cuda).manual_seed(3)
+    params = torch.randn(3, 1000, 8, 9, device=cuda, generator=g) * 12.0          # logvars beyond both clamp bounds
+    params[0, 0, 4, 0], params[0, 1, 4, 0] = -30.0, 20.0                            # exactly on the bounds: gradient passes
+    w = torch.randn(3, 1000, 4, 9, device=cuda, generator=g)
+    res = []
+    for fused in (True, False):
+        p = params.clone().requires_grad_(True)
+        d = DiagonalGaussianDistribution(params=p if fused else None, mean=None if fused else p[:, :, :4], logvar=None if fused else p[:, :, 4:],
+                                         dim=2)
+        torch.manual_seed(77)
+        s = d.sample()
+        (s * w).sum().backward()
+        res.append((s.detach(), p.grad.clone()))
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-5)
+    assert res[0][1][0, 0, 4, 0] != 0 and res[0][1][0, 1, 4, 0] != 0

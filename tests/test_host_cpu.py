@@ -136,3 +136,24 @@ def test_math_mode_switch_turns_the_contraction_kernels_off_and_on():
     import pytest
     with pytest.raises(ValueError):
         precision.set_math_mode("bf16")
+
+
+def test_closed_form_camera_inverses_match_lapack():
+    """geometry/inverse.py (adjugate formulas, no cuSOLVER) against torch.linalg.inv in float64, incl. autograd."""
+    import torch
+    from latentsplat_b200 import synthetic
+    from latentsplat_b200.geometry.inverse import inv2x2, inv3x3, inv_affine4x4
+    g = torch.Generator().manual_seed(0)
+    pose = torch.stack([synthetic.pose(0.3 * i, -4.0 + i, 0.05 * i, 0.02) for i in range(5)]).double()
+    pose[:, :3, :3] *= 1.7                                       # a scaled rigid transform is still affine
+    k3 = synthetic.intrinsics(0.9)[None].repeat(5, 1, 1).double() + 0.01 * torch.randn(5, 3, 3, generator=g).double()
+    for fn, m in ((inv_affine4x4, pose), (inv3x3, k3), (inv2x2, k3[:, :2, :2])):
+        m = m.clone().requires_grad_(True)
+        ours, ref = fn(m), torch.linalg.inv(m)
+        torch.testing.assert_close(ours, ref, rtol=1e-10, atol=1e-12)
+        w = torch.randn(ours.shape, generator=g).double()
+        (ga,) = torch.autograd.grad((ours * w).sum(), m)
+        (gb,) = torch.autograd.grad((torch.linalg.inv(m) * w).sum(), m)
+        rows = 3 if fn is inv_affine4x4 else m.shape[-2]        # the (0, 0, 0, 1) row of a pose is a constant, not a variable
+        torch.testing.assert_close(ga[:, :rows], gb[:, :rows], rtol=1e-8, atol=1e-10)
+    assert torch.equal(inv_affine4x4(pose.float())[:, 3], torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(5, 4))
