@@ -407,10 +407,34 @@ def run_full(args, cfg):
     views_per_step = cfg["B"] * cfg["V_t"]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
 
+    loss_fn = full_loss
+    if args.losses == "reference":
+        # the late-training loss stack of config/experiment/re10k.yaml:20-36 through latentsplat_b200.loss:
+        # rendered colour: 10 mse + 0.5 lpips; decoded image: l1 + lpips + 0.5 generator with the adaptive GAN weight (two extra
+        # partial backward passes to the decoder's conv_out.weight).  LPIPS-VGG has random weights here (no network), same compute.
+        from latentsplat_b200.loss import (LossGeneratorCfg, LossGroupCfg, LossL1Cfg, LossLpipsCfg, LossMseCfg, LpipsVgg, get_loss_group)
+        from latentsplat_b200.loss.loss_lpips import LossLpips
+        from latentsplat_b200.model.types import GroundTruth, Prediction
+        vgg = LpipsVgg(weights="random").to(device).to(memory_format=torch.channels_last)
+        g_render = get_loss_group("target/render/image", LossGroupCfg(nll=[LossMseCfg(weight=10), LossLpipsCfg(weight=0.5)]))
+        g_comb = get_loss_group("target/combined", LossGroupCfg(nll=[LossL1Cfg(), LossLpipsCfg()], generator=LossGeneratorCfg(weight=0.5)))
+        for grp in (g_render, g_comb):
+            for l in grp.nll_losses:
+                if isinstance(l, LossLpips):
+                    l.lpips = vgg                              # one VGG for both groups
+            grp.to(device)
+
+        def loss_fn(out, target_image):
+            gt = GroundTruth(image=target_image)
+            a, _ = g_render.forward_generator(Prediction(image=out.render.color), gt, 10 ** 6)
+            b, _ = g_comb.forward_generator(Prediction(image=out.image, logits_fake=out.logits_fake), gt, 10 ** 6,
+                                            last_layer_weights=pipe.autoencoder.last_layer_weights)
+            return a + b
+
     def fwd_bwd(inp):
         flat_grad.zero_()
         out = pipe(unflatten_batch(inp), global_step=0, discriminate=True)
-        loss = full_loss(out, inp["target.image"])
+        loss = loss_fn(out, inp["target.image"])
         if reducer is not None:
             reducer.begin()
         loss.backward()
@@ -560,6 +584,9 @@ def run_full(args, cfg):
                                        "captured inside the graph (only the last bucket is exposed)" if reducer is not None else
                                        "one NCCL all-reduce between the two graphs")
                                     + f"; rasterizer sync-free ({capacity} key slots, overflow raises RasterCapacityError)",
+                       "losses": ("10 mse + l1 + 0.5 generator term (scalar heads)" if args.losses == "scalar" else
+                                  "re10k.yaml late-training stack: mse + LPIPS-VGG (random weights) on the render, l1 + LPIPS + generator with "
+                                  "adaptive GAN weight on the decoded image"),
                        "eager_exact_ms_per_step": eager_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "stages": stages,
@@ -1052,6 +1079,10 @@ def main():
                          "skip the e2e / stage / CPU-baseline legs (numbers printed by such a run are not bench values)")
     ap.add_argument("--focal", type=float, default=CFG["f"], help="normalised focal length (RE10k-shaped 0.86, CO3D-shaped 1.2)")
     ap.add_argument("--fwd-only", action="store_true", help="splat workload: forward only (BASELINE configs[4])")
+    ap.add_argument("--losses", default="scalar", choices=["scalar", "reference"],
+                    help="full workload: 'scalar' = 10 mse + l1 + 0.5 generator term (the round-1 / default step); 'reference' = the "
+                         "late-training stack of config/experiment/re10k.yaml (mse + LPIPS on the rendered colour, l1 + LPIPS + "
+                         "generator term with the adaptive GAN weight on the decoded image) through latentsplat_b200.loss")
     ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="reproduce BASELINE.json configs[N] exactly: 1 = RE10k-shaped full step B=4 V_t=1 (the default), "
                          "2 = CO3D-shaped full step B=2, 2->3 views, f=1.2, background 0, variational sampling in the timed region, "

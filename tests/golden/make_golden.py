@@ -218,9 +218,61 @@ def encoder_goldens(out):
     np.savez(out / "patch_gan.npz", out=y.numpy(), inventory=np.array([f"{n}:{'x'.join(map(str, s))}" for n, s in dinv]))
 
 
+def loss_inputs(seed: int = 23):
+    """Seeded Prediction / GroundTruth fields + a toy "last layer": image = W (3x3 channel mix) applied to x, logits from the image."""
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=gen)
+    return dict(W=torch.randn(3, 3, generator=gen) * 0.5 + torch.eye(3), x=r(2, 2, 3, 12, 16), gt_image=r(2, 2, 3, 12, 16),
+                depth=r(2, 2, 12, 16) * 4.0 - 0.5, near=torch.tensor([[1.0, 0.8], [1.2, 1.0]]), far=torch.tensor([[20.0, 30.0], [15.0, 25.0]]),
+                mean=torch.randn(2, 2, 4, 6, 8, generator=gen), logvar=torch.randn(2, 2, 4, 6, 8, generator=gen) * 3.0,
+                logits_real=torch.randn(2, 2, 1, 3, 4, generator=gen), Wd=torch.randn(1, 3, generator=gen))
+
+
+def loss_goldens(out):
+    """tests/golden/losses.npz: every loss of /root/reference/src/loss and LossGroup's generator / discriminator passes incl. the
+    adaptive weight, computed by the reference's own modules on seeded CPU inputs."""
+    from src.loss import (LossDepthCfg, LossDiscriminatorCfg, LossGeneratorCfg, LossGroupCfg, LossKlCfg, LossL1Cfg, LossMseCfg,
+                          get_loss_group)
+    from src.model.diagonal_gaussian_distribution import DiagonalGaussianDistribution
+    from src.model.types import GroundTruth, Prediction
+    x = loss_inputs()
+    W = x["W"].clone().requires_grad_(True)
+    image = torch.einsum("oc,bvchw->bvohw", W, x["x"])
+    logits_fake = torch.einsum("oc,bvchw->bvohw", x["Wd"], image)[..., ::4, ::4]
+    pred = Prediction(image=image, posterior=DiagonalGaussianDistribution(x["mean"], x["logvar"], dim=2), depth=x["depth"],
+                      logits_fake=logits_fake, logits_real=x["logits_real"])
+    gt = GroundTruth(image=x["gt_image"], near=x["near"], far=x["far"])
+    res = {}
+    for tag, depth_cfg in (("plain", LossDepthCfg(weight=0.25)),
+                           ("bilateral2", LossDepthCfg(weight=0.25, sigma_image=10.0, use_second_derivative=True))):
+        for disc in ("hinge", "vanilla"):
+            cfg = LossGroupCfg(nll=[LossMseCfg(weight=10.0), LossL1Cfg(weight=1.0), LossKlCfg(weight=1e-3), depth_cfg],
+                               generator=LossGeneratorCfg(weight=0.5, apply_after_step=3),
+                               discriminator=LossDiscriminatorCfg(weight=2.0, loss=disc, apply_after_step=3))
+            group = get_loss_group("target", cfg)
+            for step in (0, 7):
+                total, d = group.forward_generator(pred, gt, step, last_layer_weights=W)
+                key = f"{tag}_{disc}_s{step}"
+                res[f"{key}_gen_total"] = total.detach().numpy()
+                for k, v in d.items():
+                    res[f"{key}_gen_{k}_u"] = v.unweighted.detach().numpy()
+                    res[f"{key}_gen_{k}_w"] = v.weighted.detach().numpy()
+                if step >= 3:
+                    total, d = group.forward_discriminator(pred, gt, step)
+                    res[f"{key}_dis_total"] = total.detach().numpy()
+                    for k, v in d.items():
+                        res[f"{key}_dis_{k}_u"] = v.unweighted.detach().numpy()
+                        res[f"{key}_dis_{k}_w"] = v.weighted.detach().numpy()
+    np.savez(out / "losses.npz", **res)
+    print("wrote losses.npz with", len(res), "values")
+
+
 def main():
     install_reference()
     out = Path(__file__).resolve().parent
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":      # only the loss fixture (the others are unchanged)
+        loss_goldens(out)
+        return
 
     # ---- SH ---------------------------------------------------------------------------
     from src.misc.sh_utils import eval_sh
@@ -258,6 +310,7 @@ def main():
     np.savez_compressed(out / "render_cuda.npz", color=o.color.numpy(), feature_mean=o.feature_posterior.mean.numpy(),
                         feature_logvar=o.feature_posterior.logvar.numpy(), mask=o.mask.numpy(), depth=o.depth.numpy())
     encoder_goldens(out)
+    loss_goldens(out)
     print("wrote", [p.name for p in out.glob("*.npz")])
 
 
