@@ -25,8 +25,14 @@ def test_lpips_vgg_on_cuda_matches_cpu(cuda):
     want = ref(a_cpu, b)
     (g_cpu,) = torch.autograd.grad(want, a_cpu)
     assert abs(got.item() - want.item()) <= 2e-2 * abs(want.item()), (got.item(), want.item())
-    err = (g_gpu.cpu() - g_cpu).abs().max().item()
-    assert err <= 5e-2 * g_cpu.abs().max().item(), f"d lpips / d image: {err:.3e} vs {g_cpu.abs().max().item():.3e}"
+    # the image gradient of a randomly initialised 13-layer VGG is ~1e-6 per pixel and passes 26 TF32 contractions (forward and
+    # input-gradient): compare direction and size of the whole field, not single pixels
+    g_gpu = g_gpu.cpu().double().flatten()
+    g_ref = g_cpu.double().flatten()
+    cos = torch.dot(g_gpu, g_ref) / (g_gpu.norm() * g_ref.norm())
+    rel = (g_gpu - g_ref).norm() / g_ref.norm()
+    print(f"d lpips / d image: cosine {cos.item():.5f}, relative L2 error {rel.item():.3e}")
+    assert torch.isfinite(g_gpu).all() and cos.item() > 0.999 and rel.item() < 5e-2      # measured on B200: 0.99982, 1.9e-2
 
 
 def test_adaptive_gan_weight_through_decoder_last_layer(cuda):
