@@ -267,11 +267,40 @@ def loss_goldens(out):
     print("wrote losses.npz with", len(res), "values")
 
 
+def shim_inputs(seed: int = 31):
+    gen = torch.Generator().manual_seed(seed)
+    cams = torch.zeros(5, 18)
+    cams[:, 0], cams[:, 1], cams[:, 2], cams[:, 3] = 0.9, 1.6, 0.5, 0.5
+    for i in range(5):
+        cams[i, 6:] = torch.linalg.inv(synthetic.pose(0.2 * i, 10.0 * i, 0.02 * i, -0.03))[:3].reshape(-1)
+    return dict(images=torch.rand(2, 2, 3, 90, 160, generator=gen), intrinsics=synthetic.intrinsics(0.9)[None, None].repeat(2, 2, 1, 1).clone(),
+                extrinsics=torch.stack([synthetic.pose(0.4, 25.0, 0.1, 0.2), synthetic.pose(-0.3, -10.0)])[None].repeat(2, 1, 1, 1), cameras=cams)
+
+
+def shim_goldens(out):
+    """tests/golden/dataset_shims.npz: crop shim (LANCZOS + centre crop), flip augmentation and RE10k pose conversion computed by the
+    reference's own functions."""
+    from src.dataset.shims.augmentation_shim import reflect_views
+    from src.dataset.shims.crop_shim import rescale_and_crop
+    x = shim_inputs()
+    img, intr = rescale_and_crop(x["images"], x["intrinsics"], (64, 64))
+    refl = reflect_views({"image": x["images"], "extrinsics": x["extrinsics"]})
+    # convert_poses is a method that touches no state: call it unbound
+    from src.dataset.dataset_re10k import DatasetRE10k
+    ex, k = DatasetRE10k.convert_poses(None, x["cameras"])
+    np.savez_compressed(out / "dataset_shims.npz", crop_image=img.numpy(), crop_intrinsics=intr.numpy(), flip_image=refl["image"].numpy(),
+                        flip_extrinsics=refl["extrinsics"].numpy(), pose_extrinsics=ex.numpy(), pose_intrinsics=k.numpy())
+    print("wrote dataset_shims.npz")
+
+
 def main():
     install_reference()
     out = Path(__file__).resolve().parent
     if len(sys.argv) > 1 and sys.argv[1] == "losses":      # only the loss fixture (the others are unchanged)
         loss_goldens(out)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "shims":
+        shim_goldens(out)
         return
 
     # ---- SH ---------------------------------------------------------------------------
@@ -311,6 +340,7 @@ def main():
                         feature_logvar=o.feature_posterior.logvar.numpy(), mask=o.mask.numpy(), depth=o.depth.numpy())
     encoder_goldens(out)
     loss_goldens(out)
+    shim_goldens(out)
     print("wrote", [p.name for p in out.glob("*.npz")])
 
 
