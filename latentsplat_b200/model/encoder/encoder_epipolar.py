@@ -102,7 +102,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         x = self.backbone(images)
         return self.backbone_projection(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2), 1
 
-    def _gaussian_head(self, features: Tensor, c2w_rotations: Tensor) -> Tensor:
+    def _gaussian_head(self, features: Tensor, c2w_rotations: Tensor, color_major: bool = False) -> Tensor:
         """to_gaussians(features) (:97-103) -- with the SH masking and the camera-to-world SH rotation of the Gaussian
         adapter (gaussian_adapter.py:44-61, 104-105) folded into the Linear: both are linear maps T_view of the raw
         output, so  T_v (W x + b) = (T_v W) x + T_v b  and each context view gets its own effective weight."""
@@ -118,6 +118,16 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
             t[:, :, o, o] = 1.0
             t[:, :, o + 1, o + 1] = 1.0
             t[:, :, o + 2:o + d, o + 2:o + d] = t_adapter
+        if color_major:
+            # emit the colour SH block coefficient-major ((n, xyz) instead of (xyz, n)): that is the layout the rasterizer reads
+            # (cuda_splatting.py:91), so the fused tail can hand out a transposed VIEW and no (G, 3, 25) <-> (G, 25, 3) copy is made
+            # in either direction.  A row permutation of T, i.e. of the effective weight -- free.
+            n = self.gaussian_adapter.d_color_sh
+            perm = torch.arange(srf * d, device=t.device)
+            for k in range(srf):
+                o = k * d + 9                                                                   # 2 offsets + 3 scales + 4 quaternion
+                perm[o:o + 3 * n] = o + torch.arange(3 * n, device=t.device).view(3, n).t().reshape(-1)
+            t = t[:, :, perm]
         weight = t @ lin.weight                                                                 # (b, v, srf*d, d_feature)
         bias = (t @ lin.bias[:, None])[..., 0]
         return grouped_linear(act(features).flatten(0, 1), weight.flatten(0, 1), bias.flatten(0, 1)).unflatten(0, (b, v))
@@ -190,7 +200,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         dlog = dp.projection(features)                                                          # (b, v, r, 2 * buckets)
         if not gaussian_head.supported(dlog, dlog, dp.num_samples, cfg.num_surfaces, spp, dp.use_transmittance, cfg.predict_opacity):
             return None
-        raw = self._gaussian_head(features, context["extrinsics"][..., :3, :3])                 # (b, v, r, 2 + adapter.d_in)
+        raw = self._gaussian_head(features, context["extrinsics"][..., :3, :3], color_major=True)   # (b, v, r, 2 + adapter.d_in)
         # the reference's draw: torch.rand over (*pdf.shape[:-1], num_samples) = (b, v, r, srf, spp)
         u = None if deterministic else torch.rand((b, v, r, cfg.num_surfaces, spp), device=features.device).reshape(b, v, r, spp)
         om = cfg.opacity_mapping
@@ -202,7 +212,8 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         feature_harmonics = fsh.unflatten(-1, (ga.n_feature_channels, ga.d_feature_sh))
         feature_harmonics = DiagonalGaussianDistribution(
             **{"params" if self.variational else "mean": feature_harmonics}, dim=-2)
-        return VariationalGaussians(means, cov, opac, csh.unflatten(-1, (3, ga.d_color_sh)), feature_harmonics)
+        # csh rows are coefficient-major (see _gaussian_head): (b, G, 3, n) as the API wants it is a transposed view
+        return VariationalGaussians(means, cov, opac, csh.unflatten(-1, (ga.d_color_sh, 3)).transpose(-1, -2), feature_harmonics)
 
     def get_data_shim(self):
         def data_shim(batch: dict) -> dict:
