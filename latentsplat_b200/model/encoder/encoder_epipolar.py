@@ -193,8 +193,7 @@ class EncoderEpipolar(Encoder[EncoderEpipolarCfg]):
         dp, ga, cfg = self.depth_predictor, self.gaussian_adapter, self.cfg
         spp = 1 if deterministic else cfg.gaussians_per_pixel
         if (visualization_dump is not None or not FOLD_HARMONICS or dp.to_pdf._forward_hooks or dp.to_offset._forward_hooks
-                or not gaussian_head.supported(features, features, dp.num_samples, cfg.num_surfaces, spp, dp.use_transmittance,
-                                               cfg.predict_opacity)):
+                or not (gaussian_head.ENABLED and features.is_cuda and features.dtype == torch.float32)):
             return None
         b, v, r, _ = features.shape
         dlog = dp.projection(features)                                                          # (b, v, r, 2 * buckets)
