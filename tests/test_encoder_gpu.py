@@ -19,17 +19,21 @@ from test_encoder_cpu import GOLD, _mg, build_encoder
 pytestmark = pytest.mark.gpu
 
 
-def test_gpu_encoder_matches_reference_golden(cuda):
+def test_gpu_encoder_matches_reference_golden(cuda, monkeypatch):
     g = np.load(GOLD / "encoder.npz")
     model = build_encoder()
     helpers.init_by_name(model, seed=3)
     model = model.to(cuda).to(memory_format=torch.channels_last)
     ctx = {k: v.to(cuda) for k, v in _mg().encoder_context().items()}
-    from latentsplat_b200 import _capi
+    from latentsplat_b200 import _capi, gaussian_head
+    tail_calls = []
+    fused = gaussian_head.gaussian_head
+    monkeypatch.setattr(gaussian_head, "gaussian_head", lambda *a, **k: (tail_calls.append(1), fused(*a, **k))[1])
     launches = _capi.KERNEL_LAUNCHES[0]
     with torch.no_grad():
         det = model(ctx, 0, deterministic=True)
     assert _capi.KERNEL_LAUNCHES[0] - launches > 100, "the encoder did not run on our kernels"
+    assert tail_calls, "the fused depth-sampling + Gaussian-adapter tail (k_ghead_*) was bypassed"     # a dead guard hid this once
     got = dict(means=det.means, cov=det.covariances, opac=det.opacities, csh=det.color_harmonics, fsh=det.feature_harmonics.params)
     want_means = g["det_means"]
     a_means = got["means"].cpu().numpy()[:, ::5]
