@@ -47,3 +47,21 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0
+
+
+def test_config_presets_are_labelled_by_their_baseline_config():
+    """--config N must label the line with configs[N] (round 1 shipped lines whose label named another config)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    base = dict(bench.CFG, workload="full")
+    assert "BASELINE configs[1]" in bench.workload_name(dict(base, baseline_config=1))
+    two = bench.workload_name(dict(base, baseline_config=2, B=2, V_t=3, f=1.2))
+    assert "configs[2]" in two and "configs[1]" not in two and "focal 1.2" in two and "V_t=3" in two
+    assert "configs[3]" in bench.workload_name(dict(base, baseline_config=3, B=8))
+    assert "no BASELINE config" in bench.workload_name(dict(base, baseline_config=None, B=3))
+    old = bench.FWD_ONLY
+    try:
+        bench.FWD_ONLY = True
+        assert bench.workload_name(dict(bench.CFG, workload="splat")).startswith("splat_fwd_only")
+    finally:
+        bench.FWD_ONLY = old
